@@ -1,0 +1,152 @@
+/*
+ * adapt_b200.h -- C ABI of libadapt_b200.so: the B200-native (sm_100a) wavefront path tracer that
+ * stands behind AdaPT's `--type pt` renderer.
+ *
+ * Boundary replaced (reference = Enigmatisms/AdaPT, paths relative to the reference root):
+ *   - renderer/vanilla_renderer.py:26-120   Renderer.__init__ / Renderer.render (one spp per call)
+ *   - tracer/path_tracer.py:54-141,245-274  PathTracer.__init__ / initialze (scene upload)
+ *   - tracer/tracer_base.py:117-134         load_primitives
+ *   - tracer/path_tracer.py:181-211         get_check_point / load_check_point (accumulation + counter)
+ *   - tracer/bvh/bvh.cpp:274-296            bvh_cpp.bvh_build (pybind11 module, native boundary #2)
+ * The Python class `adapt_b200.renderer.vanilla_renderer.Renderer` binds these entry points with
+ * ctypes and exposes the reference's constructor / attributes, so `render.py` drives it unchanged.
+ *
+ * Conventions: plain pointers and sizes only; every host array passed in is COPIED before the call
+ * returns (the caller keeps ownership); every function returns 0 on success or a negative
+ * adapt_status and never throws; adapt_last_error() gives the message of the last failure on the
+ * calling thread.  A handle is NOT thread-safe: one driver thread, one CUDA stream per handle.
+ */
+#ifndef ADAPT_B200_H
+#define ADAPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ADAPT_OK = 0,
+    ADAPT_ERR_INVALID = -1,   /* bad argument / inconsistent scene description          */
+    ADAPT_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string)   */
+    ADAPT_ERR_NO_DEVICE = -3, /* no CUDA device: this library has no CPU fallback        */
+    ADAPT_ERR_STATE = -4      /* call order violated (e.g. render before create)         */
+} adapt_status;
+
+/* One BRDF/BSDF per object. Mirrors reference `BRDF` (bxdf/brdf.py:152-158) and `BSDF`
+ * (bxdf/bsdf.py:68-73, of whose medium only `ior` is read on this path). 64 bytes. */
+typedef struct {
+    int32_t kind;      /* 0 = BRDF (opaque), 1 = BSDF                                              */
+    int32_t type;      /* BRDF: 0 phong 1 lambertian 2 specular 3 microfacet 4 mod-phong           */
+                       /*       5 fresnel-blend 6 oren-nayar 7 thin-coat; BSDF: 0 det-refraction,  */
+                       /*       1 lambertian transmission, -1 null                                 */
+    int32_t is_delta;
+    float k_d[3], k_s[3], k_g[3], mean[3];
+    float ior;
+} adapt_bxdf;
+
+/* Mirrors reference `TaichiSource` (emitters/abtract_source.py:44-54). 64 bytes. */
+typedef struct {
+    int32_t type;        /* 0 point, 1 area, 2 spot, 4 collimated */
+    int32_t obj_ref_id;  /* object the emitter is attached to, or -1 */
+    int32_t bool_bits;   /* b0 pos-delta, b1 dir-delta, b2 area, b3 infinite, b4 in free space */
+    float intensity[3], dir[3], pos[3];
+    float inv_area, r, emit_time, _pad;
+} adapt_emitter;
+
+/* Everything PathTracer.__init__ receives, flattened. */
+typedef struct {
+    /* geometry: array_info of parsers/xml_parser.py:171-175 */
+    int32_t n_prims;
+    int32_t n_objects;
+    const float*   primitives;  /* [n_prims*9]  (N,3,3): triangle vertices; sphere = (center, (r,r,r), 0) */
+    const float*   n_g;         /* [n_prims*3]  geometric normals                                          */
+    const float*   n_s;         /* [n_prims*9]  per-vertex shading normals, or NULL (has_vertex_normal=0)  */
+    const float*   uvs;         /* [n_prims*6]  per-vertex uv, or NULL (unused until textures land)        */
+    const int32_t* obj_info;    /* [n_objects*3] (first_prim, n_prims, type 0 mesh / 1 sphere), tracer/path_tracer.py:252-256 */
+    const float*   obj_aabb;    /* [n_objects*6] (min, max) per object, parsers/obj_desc.py:9-25           */
+    const int32_t* emitter_id;  /* [n_objects]   attached emitter index or -1                              */
+    const adapt_bxdf* bxdfs;    /* [n_objects]                                                             */
+    int32_t n_emitters;
+    const adapt_emitter* emitters; /* [n_emitters], obj_ref_id already resolved (path_tracer.py:271-274)   */
+    /* camera / film: tracer/tracer_base.py:36-75 */
+    int32_t width, height;
+    float cam_r[9];             /* row-major 3x3 */
+    float cam_t[3];
+    float inv_focal, half_w, half_h;
+    int32_t do_crop, start_x, end_x, start_y, end_y;
+    /* integrator flags: tracer/path_tracer.py:63-69 */
+    int32_t max_bounce, num_shadow_ray, use_rr, rr_bounce_th, use_mis;
+    int32_t anti_alias, stratified_sampling, brdf_two_sides, has_v_normal;
+    float   rr_threshold;
+    float   world_ior;
+    /* back-end knobs */
+    uint64_t seed;              /* counter-based RNG seed; sample k of pixel p always draws the same stream */
+    int32_t device_id;          /* CUDA ordinal                                                              */
+    int32_t n_pixels;           /* pixels owned by this handle (tile partition), 0 = whole film / crop window */
+    const int32_t* pixel_list;  /* [n_pixels] film indices i*height + j owned by this handle, or NULL        */
+    int32_t pool_size;          /* path slots kept in flight, 0 = auto                                       */
+    int32_t reserved[7];
+} adapt_scene_desc;
+
+/* Counters since create (or the last adapt_reset_stats). Ray counts are the calls the reference
+ * would make: closest = ray_intersect*, shadow = does_intersect*. */
+typedef struct {
+    uint64_t paths;             /* pixel-samples finished                       */
+    uint64_t rays_closest;      /* closest-hit rays traced (primary + secondary) */
+    uint64_t rays_shadow;       /* any-hit shadow rays traced                    */
+    uint64_t iterations;        /* wavefront iterations                          */
+    uint64_t kernel_launches;   /* CUDA kernels launched by this library          */
+    float ms_logic, ms_closest, ms_shadow, ms_total; /* CUDA-event time per stage */
+    uint64_t nodes_visited;     /* BVH nodes fetched by k_closest (0 unless built with ADAPT_COUNT_NODES) */
+    uint64_t prims_tested;
+    uint64_t reserved[4];
+} adapt_stats;
+
+typedef struct adapt_handle adapt_handle;
+
+/* Scene upload + BVH build (replaces PathTracer.__init__ incl. bvh_process). */
+int adapt_create(adapt_handle** out, const adapt_scene_desc* desc);
+void adapt_destroy(adapt_handle* h);
+
+/* Enqueue n_spp samples per owned pixel (Renderer.render called n_spp times). Asynchronous with
+ * respect to the host where possible; adapt_sync / adapt_read_accum are the sync points. */
+int adapt_render(adapt_handle* h, int32_t n_spp);
+int adapt_sync(adapt_handle* h);
+
+/* Framebuffer: `color` sum in the reference layout (w,h,3) indexed [i=x][j=y], and the sample
+ * counter `cnt` (tracer/path_tracer.py:81, tracer_base.py:102). */
+int adapt_read_accum(adapt_handle* h, float* dst_whc, int32_t* spp);
+int adapt_load_accum(adapt_handle* h, const float* src_whc, int32_t spp);   /* checkpoint resume */
+/* Device pointer of the (w,h,3) float sum, for in-place collectives (torch.distributed / NCCL). */
+int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats);
+
+int adapt_get_stats(adapt_handle* h, adapt_stats* out);
+int adapt_reset_stats(adapt_handle* h);
+
+/* Stage-level hooks used by the parity tests: trace a batch of rays through the device BVH.
+ * rays_o/rays_d: [n*3]; tmax: [n] (<=0 means "no limit": min_depth 1e7 as in tracer_base.py:176);
+ * any_hit != 0 runs does_intersect semantics (hit_prim receives 1/0, t/u/v untouched). */
+int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* rays_d, const float* tmax,
+                          int32_t n, int32_t any_hit, int32_t* hit_obj, int32_t* hit_prim,
+                          float* hit_t, float* hit_u, float* hit_v);
+
+/* Host SAH-BVH builder with the signature of the reference's pybind11 module
+ * (tracer/bvh/bvh.cpp:274-285): DFS-linearised nodes with skip offsets.
+ *   primitives [n_prims*9]; obj_info [2*n_objects] = (prim count row, is_sphere row);
+ *   outputs are malloc'ed by the library and released with adapt_free:
+ *   bvh_minmax [n_refs*6], node_minmax [n_nodes*6], bvh_info [n_refs*2] (obj, prim),
+ *   node_info [n_nodes*3] (base, prim_cnt, all_offset). */
+int adapt_bvh_build(const float* primitives, int32_t n_prims, const int32_t* obj_info, int32_t n_objects,
+                    const float* world_min, const float* world_max,
+                    float** bvh_minmax, float** node_minmax, int32_t** bvh_info, int32_t** node_info,
+                    int32_t* n_refs, int32_t* n_nodes);
+void adapt_free(void* p);
+
+const char* adapt_last_error(void);
+const char* adapt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAPT_B200_H */
