@@ -1,0 +1,53 @@
+"""Builds adapt_b200/lib/libadapt_b200.so with nvcc for sm_100a (in-tree, so the .so travels to the GPU box).
+
+    python -m adapt_b200.build [--force] [--verbose]
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libadapt_b200.so")
+SOURCES = ["adapt_abi.cu", "bvh_build.cpp"]
+HEADERS = ["pt_common.cuh", "pt_shade.cuh", "pt_trace.cuh", "bvh_build.h", os.path.join("..", "..", "include", "adapt_b200.h")]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    files = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(f) > t for f in files if os.path.exists(f))
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-ccbin", "g++", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--shared", "-o", LIB]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += list(extra_flags)
+    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-lgomp"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,862 @@
+// adapt_abi.cu -- wavefront kernels, scheduler and the C ABI of libadapt_b200.so (sm_100a).
+//
+// The reference renders with one Taichi megakernel per spp (renderer/vanilla_renderer.py:32-120).
+// Here the same estimator runs as a *persistent path pool*: P path slots live in HBM as SoA float4
+// arrays; one wavefront iteration is three kernels over the pool
+//     k_logic   : emission-MIS weight of the hit just found, Russian roulette, NEE sample + BSDF
+//                 eval/pdf/MIS (-> compacted shadow queue), emission, BSDF sampling, throughput
+//                 update (-> next ray), path termination (NaN scrub + framebuffer RED) and
+//                 *regeneration* of finished slots with the next (pixel, sample) work item
+//     k_shadow  : any-hit traversal of the shadow queue, unoccluded payloads RED-added to the path colour
+//     k_closest : closest-hit traversal of every live slot's ray
+// so the GPU always works on a full pool instead of a shrinking wave, and a path's colour is only
+// splatted once, when it ends (which is what lets the reference's whole-path NaN scrub survive).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "pt_common.cuh"
+#include "pt_shade.cuh"
+#include "pt_trace.cuh"
+
+using namespace adapt;
+
+// ================================================================================================
+// error plumbing
+// ================================================================================================
+static thread_local std::string g_last_error;
+static int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return set_error(ADAPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// ================================================================================================
+// device helpers
+// ================================================================================================
+struct Cursors { unsigned closest, shadow, pad0, pad1; };
+
+#define LOGIC_BLOCK 256
+#define TRACE_BLOCK 128
+
+// Block-wide allocation from a global counter: every thread passes `want` (0/1), gets its index.
+// Two barriers, one atomic per block. Must be called by all threads of the block.
+template <typename CounterT>
+__device__ __forceinline__ CounterT block_alloc(bool want, CounterT* counter, unsigned* s_warp, CounterT* s_base) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned ballot = __ballot_sync(0xffffffffu, want);
+    const unsigned rank = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        #pragma unroll
+        for (int w = 0; w < LOGIC_BLOCK / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        *s_base = tot ? atomicAdd(counter, (CounterT)tot) : (CounterT)0;
+    }
+    __syncthreads();
+    CounterT idx = *s_base + (CounterT)(s_warp[warp] + rank);
+    __syncthreads();       // s_warp / s_base are reused by the next call
+    return idx;
+}
+
+__device__ __forceinline__ void block_count(unsigned v, unsigned long long* counter) {
+    // warp reduce then one atomic per warp (only used for statistics)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
+}
+
+// Shading frame of a hit: geometric + shading normal (tracer_base.py:215-232 / path_tracer.py:372-389)
+__device__ __forceinline__ void load_surface(const SceneView& sv, int prim, float3 o, float3 d, float t, float u, float v,
+                                             Surf& s, int& obj, bool& sphere) {
+    const float4 s0 = __ldg(sv.prim_shade + (size_t)prim * 4);
+    const uint32_t ob = __float_as_uint(s0.w);
+    obj = (int)(ob & 0x7fffffffu);
+    sphere = (ob & 0x80000000u) != 0;
+    s.t = t;
+    if (sphere) {
+        const float4 g0 = __ldg(sv.prim_geom + (size_t)prim * 3);
+        s.n_g = normalized(o + t * d - mk3(g0.x, g0.y, g0.z));
+        s.n_s = s.n_g;
+    } else {
+        s.n_g = mk3(s0.x, s0.y, s0.z);
+        if (sv.has_v_normal) {
+            const float4 a = __ldg(sv.prim_shade + (size_t)prim * 4 + 1), b = __ldg(sv.prim_shade + (size_t)prim * 4 + 2),
+                         c = __ldg(sv.prim_shade + (size_t)prim * 4 + 3);
+            float3 n0 = mk3(a.x, a.y, a.z), n1 = mk3(a.w, b.x, b.y), n2 = mk3(b.z, b.w, c.x);
+            s.n_s = n0 * (1.f - u - v) + u * n1 + v * n2;     // not renormalised, like the reference (quirk 4)
+        } else {
+            s.n_s = s.n_g;
+        }
+    }
+}
+
+// pix2ray (tracer_base.py:136-157)
+__device__ __forceinline__ float3 camera_ray(const SceneView& sv, Rng& g, int i, int j, int cnt) {
+    float vx = 0.5f, vy = 0.5f;
+    if (sv.anti_alias) {
+        if (sv.stratified) {
+            int m = cnt % 16;
+            vx = (float)(m % 4) * 0.25f + g.rand_f() * 0.25f;
+            vy = (float)(m / 4) * 0.25f + g.rand_f() * 0.25f;
+        } else {
+            vx = g.rand_f() * 0.9998f + 1e-4f;
+            vy = g.rand_f() * 0.9998f + 1e-4f;
+        }
+    }
+    float3 cd = mk3((sv.half_w + vx - (float)i) * sv.inv_focal, ((float)j - sv.half_h - vy) * sv.inv_focal, 1.f);
+    return normalized(mul(sv.cam_r, cd));
+}
+
+// ================================================================================================
+// k_logic
+// ================================================================================================
+__global__ void __launch_bounds__(LOGIC_BLOCK)
+k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
+        float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
+        const unsigned long long work_lo, const unsigned long long work_hi, const int cnt_base) {
+    __shared__ unsigned s_warp[LOGIC_BLOCK / 32];
+    __shared__ unsigned s_base32;
+    __shared__ unsigned long long s_base64;
+
+    const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
+    if (slot == 0) { cur->closest = 0; cur->shadow = 0; }
+
+    uint4 misc = pool.misc[slot];
+    bool alive = (misc.z & SLOT_ALIVE) != 0;
+    bool terminate = false;
+    bool shading = false;
+
+    // path registers (valid when shading)
+    float3 ray_o = mk3(0.f), ray_d = mk3(0.f, 0.f, 1.f), contribution = mk3(1.f), color = mk3(0.f);
+    float ray_pdf = 1.f, emission_weight = 1.f;
+    Rng rng; rng.state = 0;
+    Surf sf; sf.n_s = sf.n_g = mk3(1.f, 0.f, 0.f); sf.t = 0.f;
+    Bxdf mat; mat.kind = 0; mat.type = 1; mat.is_delta = 0; mat.k_d = mat.k_s = mat.k_g = mat.mean = mk3(0.f); mat.ior = 1.f;
+    int obj = 0, hit_light = -1, bounce = 0;
+    float3 hit_point = mk3(0.f);
+    bool flip_pending = false;   // brdf_two_sides: normals flip at the first BRDF call of this bounce
+
+    if (alive) {
+        bounce = (int)(misc.z & 0xffffu);
+        const float4 c4 = pool.col[slot];
+        color = mk3(c4.x, c4.y, c4.z);
+        if (misc.z & SLOT_FINISH) {
+            terminate = true;
+        } else {
+            const float4 h4 = pool.hit[slot];
+            const int prim = __float_as_int(h4.w);
+            if (prim < 0) {
+                terminate = true;                                    // "if it.is_ray_not_hit(): break"
+            } else {
+                const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
+                const uint2 r2 = pool.rng[slot];
+                ray_o = mk3(o4.x, o4.y, o4.z); ray_d = mk3(d4.x, d4.y, d4.z);
+                contribution = mk3(t4.x, t4.y, t4.z); ray_pdf = t4.w;
+                rng.state = ((uint64_t)r2.y << 32) | r2.x;
+                bool sphere;
+                load_surface(sv, prim, ray_o, ray_d, h4.x, h4.y, h4.z, sf, obj, sphere);
+                const int4 oi = __ldg(sv.obj_info + obj);
+                hit_light = oi.w;
+                mat = load_bxdf(sv.bxdfs + obj);
+                // emission MIS weight for the hit just found (vanilla_renderer.py:111-117); quirk 1/2:
+                // tests is_delta of the *hit* object and the is_specular flag of the previous sample
+                if (bounce > 0 && sv.use_mis) {
+                    float emitter_pdf = 0.f;
+                    if (hit_light >= 0 && mat.is_delta == 0 && !(misc.z & SLOT_SPECULAR))
+                        emitter_pdf = emitter_solid_angle_pdf(load_emitter(sv.emitters + hit_light), sf, ray_d);
+                    emission_weight = balance(ray_pdf, emitter_pdf);
+                }
+                // Russian roulette / cut-off (:50-57)
+                if (sv.use_rr) {
+                    float mv = vmax(contribution);
+                    if (mv < sv.rr_threshold && bounce >= sv.rr_bounce_th) {
+                        if (rng.rand_f() > mv) terminate = true;
+                        else contribution *= 1.f / (mv + 1e-7f);
+                    }
+                } else if (vmax(contribution) < 1e-4f) {
+                    terminate = true;
+                }
+                shading = !terminate;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- next-event estimation (:67-97)
+    float3 direct_inline = mk3(0.f);      // payloads resolved inside this kernel (two-sided corner case)
+    bool flipped_for_le = false;          // has a BRDF call flipped the normals before eval_le?
+    if (shading) {
+        hit_point = ray_d * sf.t + ray_o;
+        flip_pending = sv.two_sides && mat.kind == 0 && dot(ray_d, sf.n_s) > 0.f;
+    }
+    Surf sfb = sf;                         // normals as the BRDF sees them (flipped when two-sided and back-facing)
+    if (flip_pending) { sfb.n_s = -sf.n_s; sfb.n_g = -sf.n_g; }
+    const bool le_corner = shading && flip_pending && hit_light >= 0;
+    bool break_flag = false;
+    unsigned n_inline = 0;
+    for (int j = 0; j < sv.num_shadow_ray; j++) {
+        bool want = false;
+        float4 q_o = make_float4(0.f, 0.f, 0.f, 0.f), q_d = q_o, q_c = q_o;
+        if (shading && !break_flag) {
+            // sample_light (path_tracer.py:537-554)
+            int idx = floor_mod(rng.rand_i(), sv.n_emitters);
+            float emitter_pdf = 1.f / (float)sv.n_emitters;
+            bool valid = true;
+            if (hit_light >= 0) {
+                if (sv.n_emitters <= 1) valid = false;
+                else {
+                    idx = floor_mod(rng.rand_i(), sv.n_emitters - 1);
+                    if (idx >= hit_light) idx += 1;
+                    emitter_pdf = 1.f / (float)(sv.n_emitters - 1);
+                }
+            }
+            if (!valid) {
+                break_flag = true;
+            } else {
+                const Emitter em = load_emitter(sv.emitters + idx);
+                float3 emit_pos, shadow_int; float direct_pdf;
+                emitter_sample_hit(sv, em, hit_point, rng, emit_pos, shadow_int, direct_pdf);
+                float3 to_emitter = emit_pos - hit_point;
+                float emitter_d = norm(to_emitter);
+                float3 light_dir = to_emitter / emitter_d;
+                float3 direct_spec = mat.kind == 0 ? brdf_eval(mat, sfb, ray_d, light_dir)
+                                                   : bsdf_eval(mat, sf, ray_d, light_dir, sv.world_ior);
+                float mis_w = 1.f;
+                const bool delta_pos = (em.bool_bits & 1) != 0;
+                if (sv.use_mis && !delta_pos) {
+                    float surf_pdf = mat.kind == 0 ? brdf_pdf(mat, sfb, light_dir, ray_d)
+                                                   : bsdf_pdf(mat, sf, light_dir, ray_d, sv.world_ior);
+                    mis_w = balance(emitter_pdf * direct_pdf, surf_pdf);
+                    flipped_for_le = true;             // surface_pdf always runs -> flip happened
+                }
+                float3 payload = sv.use_mis ? direct_spec * shadow_int * mis_w / emitter_pdf
+                                            : direct_spec * shadow_int / emitter_pdf;
+                payload = payload * sv.inv_num_shadow_ray * contribution;
+                const bool nonzero = !is_zero3(payload);
+                if (le_corner && !flipped_for_le) {
+                    // eval() only runs (and flips the normals) when the shadow ray is unoccluded: the
+                    // outcome decides which normal eval_le sees, so resolve it here (rare path)
+                    HitRec hr; unsigned nn = 0, np = 0;
+                    float tmax = emitter_d > 0.f ? emitter_d - 1e-4f : PT_T_INF;
+                    bool occluded = trace<true, false>(sv, hit_point, light_dir, tmax, hr, nn, np);
+                    n_inline++;
+                    if (!occluded) { flipped_for_le = true; direct_inline += payload; }
+                } else if (nonzero) {
+                    want = true;
+                    q_o = make_float4(hit_point.x, hit_point.y, hit_point.z, emitter_d);
+                    q_d = make_float4(light_dir.x, light_dir.y, light_dir.z, __int_as_float(slot));
+                    q_c = make_float4(payload.x, payload.y, payload.z, 0.f);
+                }
+            }
+        }
+        const unsigned qi = block_alloc<unsigned>(want, sq.count, s_warp, &s_base32);
+        if (want) { sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c; }
+    }
+
+    // ---------------------------------------------------------------- emission, BSDF sampling, throughput (:99-109)
+    if (shading) {
+        float3 emit_int = mk3(0.f);
+        if (hit_light >= 0) {
+            const float3 n_le = (flip_pending && flipped_for_le) ? sfb.n_s : sf.n_s;
+            emit_int = emitter_eval_le(load_emitter(sv.emitters + hit_light), hit_point - ray_o, n_le);
+        }
+        float3 new_dir, indirect_spec; float new_pdf; bool is_specular;
+        if (mat.kind == 0) brdf_sample(mat, sfb, ray_d, rng, new_dir, indirect_spec, new_pdf, is_specular);
+        else bsdf_sample(mat, sf, ray_d, sv.world_ior, rng, new_dir, indirect_spec, new_pdf, is_specular);
+        color += (direct_inline + emit_int * emission_weight * contribution);
+        contribution *= indirect_spec / new_pdf;
+        bounce += 1;
+        uint32_t flags = SLOT_ALIVE | (is_specular ? SLOT_SPECULAR : 0u);
+        float tmax = PT_T_INF;
+        if (bounce >= sv.max_bounce) { flags |= SLOT_FINISH; tmax = -1.f; }   // the reference's last trace is never used
+        pool.ray_o[slot] = make_float4(hit_point.x, hit_point.y, hit_point.z, tmax);
+        pool.ray_d[slot] = make_float4(new_dir.x, new_dir.y, new_dir.z, 0.f);
+        pool.thr[slot] = make_float4(contribution.x, contribution.y, contribution.z, new_pdf);
+        pool.col[slot] = make_float4(color.x, color.y, color.z, 0.f);
+        pool.rng[slot] = make_uint2((uint32_t)rng.state, (uint32_t)(rng.state >> 32));
+        misc.z = (uint32_t)bounce | flags;
+        pool.misc[slot] = misc;
+    }
+
+    // ---------------------------------------------------------------- termination: NaN scrub + splat (:119)
+    if (alive && terminate) {
+        float* px = accum + (size_t)misc.x * 3;
+        if (!isnan(color.x) && color.x != 0.f) atomicAdd(px + 0, color.x);
+        if (!isnan(color.y) && color.y != 0.f) atomicAdd(px + 1, color.y);
+        if (!isnan(color.z) && color.z != 0.f) atomicAdd(px + 2, color.z);
+        alive = false;
+    }
+    block_count((alive || !terminate) ? 0u : 1u, &ctr->paths_done);
+    block_count(n_inline, &ctr->shadow_inline);
+
+    // ---------------------------------------------------------------- regeneration
+    // Work item w in [work_lo, work_hi) is sample cnt_base + 1 + (w - work_lo) / n_pixels of pixel
+    // pixel_list[(w - work_lo) % n_pixels]. Once the range is exhausted free slots stop asking.
+    const bool need = !alive && !shading;
+    unsigned long long w;
+    {
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const unsigned ballot = __ballot_sync(0xffffffffu, need);
+        const unsigned rank = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            #pragma unroll
+            for (int k = 0; k < LOGIC_BLOCK / 32; k++) { unsigned c = s_warp[k]; s_warp[k] = tot; tot += c; }
+            unsigned long long base = work_hi;
+            if (tot && *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work) < work_hi)
+                base = atomicAdd(&ctr->next_work, (unsigned long long)tot);
+            s_base64 = base;
+        }
+        __syncthreads();
+        w = s_base64 + (unsigned long long)(s_warp[warp] + rank);
+    }
+    if (need) {
+        if (w >= work_lo && w < work_hi) {
+            const unsigned long long rel = w - work_lo;
+            const unsigned long long s = rel / (unsigned long long)n_pixels;
+            const int k = (int)(rel - s * (unsigned long long)n_pixels);
+            const int pixel = __ldg(pixel_list + k);
+            const int cnt = cnt_base + (int)s + 1;
+            Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
+            const int i = pixel / sv.height, jj = pixel - i * sv.height;
+            float3 d = camera_ray(sv, g, i, jj, cnt);
+            // max_bounce <= 0: the reference still traces the primary ray but never enters the loop
+            const bool no_loop = sv.max_bounce <= 0;
+            pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, no_loop ? -1.f : PT_T_INF);
+            pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+            pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
+            pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
+            pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
+        } else if (misc.z & SLOT_ALIVE) {
+            // out of work: park the slot
+            pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
+            pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
+// ================================================================================================
+// k_closest / k_shadow: persistent warps pull 32 rays at a time from a global cursor
+// ================================================================================================
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur, uint32_t* __restrict__ shadow_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *shadow_count = 0;      // queue is consumed; reset for the next k_logic
+    const unsigned lane = threadIdx.x & 31;
+    unsigned traced = 0, nn = 0, np = 0;
+    const unsigned n = (unsigned)pool.n_slots;
+    while (true) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cur->closest, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const unsigned slot = base + lane;
+        if (slot < n) {
+            const float4 o4 = pool.ray_o[slot];
+            if (o4.w > 0.f) {
+                const float4 d4 = pool.ray_d[slot];
+                HitRec hr;
+                trace<false, COUNT>(sv, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), o4.w, hr, nn, np);
+                pool.hit[slot] = make_float4(hr.t, hr.u, hr.v, __int_as_float(hr.prim));
+                traced++;
+            }
+        }
+    }
+    block_count(traced, &ctr->rays_closest);
+    if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
+}
+
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned n = *sq.count;
+    unsigned traced = 0;
+    while (true) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cur->shadow, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const unsigned i = base + lane;
+        if (i < n) {
+            const float4 o4 = sq.o[i], d4 = sq.d[i];
+            // does_intersect(light_dir, hit_point, emitter_d): t in (1e-4, emitter_d - 1e-4) (tracer_base.py:242)
+            const float tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF;
+            HitRec hr; unsigned nn = 0, np = 0;
+            const bool occluded = trace<true, false>(sv, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), tmax, hr, nn, np);
+            traced++;
+            if (!occluded) {
+                const float4 c4 = sq.c[i];
+                float* dst = reinterpret_cast<float*>(pool.col + __float_as_int(d4.w));
+                atomicAdd(dst + 0, c4.x); atomicAdd(dst + 1, c4.y); atomicAdd(dst + 2, c4.z);
+            }
+        }
+    }
+    block_count(traced, &ctr->rays_shadow);
+}
+
+// stage-level test hook
+__global__ void k_intersect_batch(const SceneView sv, int n, const float* __restrict__ ro, const float* __restrict__ rd,
+                                  const float* __restrict__ tmax_in, int any_hit, int* __restrict__ hit_obj, int* __restrict__ hit_prim,
+                                  float* __restrict__ hit_t, float* __restrict__ hit_u, float* __restrict__ hit_v) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float3 o = ld3(ro + (size_t)k * 3), d = ld3(rd + (size_t)k * 3);
+    float tm = tmax_in ? tmax_in[k] : -1.f;
+    float tmax = tm > 0.f ? tm - 1e-4f : PT_T_INF;
+    HitRec hr; unsigned nn = 0, np = 0;
+    if (any_hit) {
+        bool h = trace<true, false>(sv, o, d, tmax, hr, nn, np);
+        hit_prim[k] = h ? 1 : 0;
+        if (hit_obj) hit_obj[k] = h ? 1 : 0;
+    } else {
+        trace<false, false>(sv, o, d, tmax, hr, nn, np);
+        hit_prim[k] = hr.prim;
+        hit_obj[k] = hr.prim >= 0 ? (hr.obj & 0x7fffffff) : -1;
+        hit_t[k] = hr.t; hit_u[k] = hr.u; hit_v[k] = hr.v;
+    }
+}
+
+// ================================================================================================
+// handle
+// ================================================================================================
+struct adapt_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    SceneView sv{};
+    PathPool pool{};
+    ShadowQueue sq{};
+    DeviceCounters* d_ctr = nullptr;
+    DeviceCounters* h_ctr = nullptr;          // pinned
+    Cursors* d_cur = nullptr;
+    float* d_accum = nullptr;
+    int* d_pixel_list = nullptr;
+    int n_pixels = 0;
+    int width = 0, height = 0;
+    int cnt = 0;                              // spp enqueued so far (the reference's self.cnt)
+    int cnt_base = 0;                         // sample counter at the start of the current work range
+    unsigned long long work_lo = 0, work_hi = 0;   // current work range in next_work units
+    unsigned long long total_paths = 0;       // pixel-samples enqueued since create
+    std::vector<void*> allocs;
+    int trace_grid = 0;
+    bool count_nodes = false;
+    // timing
+    struct IterEvents { cudaEvent_t e[4]; };
+    std::vector<IterEvents> ev_ring;
+    size_t ev_used = 0;
+    cudaEvent_t ev_poll = nullptr;
+    adapt_stats stats{};
+    DeviceCounters ctr_base{};                // counters at the last reset_stats
+};
+
+template <typename T>
+static int dev_alloc(adapt_handle* h, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+template <typename T>
+static int dev_upload(adapt_handle* h, T** p, const T* src, size_t n) {
+    int rc = dev_alloc(h, p, n);
+    if (rc) return rc;
+    if (n) CK(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int drain_events(adapt_handle* h) {
+    if (h->ev_used == 0) return 0;
+    CK(cudaEventSynchronize(h->ev_ring[h->ev_used - 1].e[3]));
+    for (size_t i = 0; i < h->ev_used; i++) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, h->ev_ring[i].e[0], h->ev_ring[i].e[1]);
+        cudaEventElapsedTime(&b, h->ev_ring[i].e[1], h->ev_ring[i].e[2]);
+        cudaEventElapsedTime(&c, h->ev_ring[i].e[2], h->ev_ring[i].e[3]);
+        h->stats.ms_logic += a; h->stats.ms_shadow += b; h->stats.ms_closest += c; h->stats.ms_total += a + b + c;
+    }
+    h->ev_used = 0;
+    return 0;
+}
+
+static int launch_iteration(adapt_handle* h) {
+    if (h->ev_used == h->ev_ring.size()) { int rc = drain_events(h); if (rc) return rc; }
+    adapt_handle::IterEvents& ev = h->ev_ring[h->ev_used++];
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(ev.e[0], st));
+    k_logic<<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, h->d_accum, h->d_pixel_list,
+                                                                    h->n_pixels, h->work_lo, h->work_hi, h->cnt_base);
+    CK(cudaEventRecord(ev.e[1], st));
+    k_shadow<<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur);
+    CK(cudaEventRecord(ev.e[2], st));
+    if (h->count_nodes) k_closest<true><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
+    else k_closest<false><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
+    CK(cudaEventRecord(ev.e[3], st));
+    CK(cudaGetLastError());
+    h->stats.iterations += 1;
+    h->stats.kernel_launches += 3;
+    return 0;
+}
+
+// Run iterations until `done(counters)` holds. Counters are polled with one batch of lag so the
+// stream never drains while we wait.
+template <typename Pred>
+static int run_until(adapt_handle* h, Pred done) {
+    const int batch = 4;
+    CK(cudaSetDevice(h->device));
+    // cheap pre-check
+    CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (done(*h->h_ctr)) return 0;
+    for (int guard = 0; guard < (1 << 26); guard++) {
+        for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
+        CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_poll, h->stream));
+        // overlap: queue the next batch before looking at this one's counters
+        for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
+        CK(cudaEventSynchronize(h->ev_poll));
+        if (done(*h->h_ctr)) return 0;
+    }
+    return set_error(ADAPT_ERR_STATE, "wavefront did not converge");
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* adapt_last_error(void) { return g_last_error.c_str(); }
+const char* adapt_version(void) { return "adapt_b200 0.1.0 (sm_100a)"; }
+void adapt_free(void* p) { std::free(p); }
+
+int adapt_bvh_build(const float* primitives, int32_t n_prims, const int32_t* obj_info, int32_t n_objects,
+                    const float* world_min, const float* world_max,
+                    float** bvh_minmax, float** node_minmax, int32_t** bvh_info, int32_t** node_info,
+                    int32_t* n_refs, int32_t* n_nodes) {
+    if (!primitives || !obj_info || n_prims <= 0 || n_objects <= 0 || !bvh_minmax || !node_minmax || !bvh_info || !node_info || !n_refs || !n_nodes)
+        return set_error(ADAPT_ERR_INVALID, "adapt_bvh_build: null or empty argument");
+    std::vector<uint8_t> sph((size_t)n_prims, 0);
+    std::vector<int32_t> prim_obj((size_t)n_prims, 0);
+    int32_t p = 0;
+    for (int32_t o = 0; o < n_objects; o++)
+        for (int32_t k = 0; k < obj_info[o]; k++, p++) {
+            if (p >= n_prims) return set_error(ADAPT_ERR_INVALID, "adapt_bvh_build: obj_info counts exceed n_prims");
+            sph[p] = obj_info[n_objects + o] > 0; prim_obj[p] = o;
+        }
+    if (p != n_prims) return set_error(ADAPT_ERR_INVALID, "adapt_bvh_build: obj_info counts do not add up to n_prims");
+    BuildParams bp; bp.max_leaf = 1; bp.traverse_cost = 0.1f;       // one primitive per leaf like the reference (bvh.cpp:15-17)
+    BuildResult br;
+    build_bvh(primitives, sph.data(), n_prims, bp, br);
+    RefLayout rl;
+    to_reference_layout(br, prim_obj.data(), world_min, world_max, rl);
+    auto dup = [](const auto& v) { using T = typename std::decay<decltype(v[0])>::type;
+        T* q = (T*)std::malloc(sizeof(T) * std::max<size_t>(v.size(), 1)); std::memcpy(q, v.data(), sizeof(T) * v.size()); return q; };
+    *bvh_minmax = dup(rl.bvh_minmax); *node_minmax = dup(rl.node_minmax);
+    *bvh_info = dup(rl.bvh_info); *node_info = dup(rl.node_info);
+    *n_refs = (int32_t)(rl.bvh_info.size() / 2); *n_nodes = (int32_t)(rl.node_info.size() / 3);
+    return 0;
+}
+
+void adapt_destroy(adapt_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) if (ev.e[k]) cudaEventDestroy(ev.e[k]);
+    if (h->ev_poll) cudaEventDestroy(h->ev_poll);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
+    if (!out || !d) return set_error(ADAPT_ERR_INVALID, "adapt_create: null argument");
+    *out = nullptr;
+    if (d->n_prims <= 0 || d->n_objects <= 0 || !d->primitives || !d->n_g || !d->obj_info || !d->emitter_id || !d->bxdfs)
+        return set_error(ADAPT_ERR_INVALID, "adapt_create: empty scene or missing arrays");
+    if (d->width <= 0 || d->height <= 0) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad film size");
+    if (d->n_emitters < 0 || (d->n_emitters > 0 && !d->emitters)) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad emitters");
+    if (d->n_emitters == 0 && d->num_shadow_ray > 0)
+        return set_error(ADAPT_ERR_INVALID, "adapt_create: num_shadow_ray > 0 needs at least one emitter (sample_light would divide by zero)");
+    if (d->has_v_normal && !d->n_s) return set_error(ADAPT_ERR_INVALID, "adapt_create: has_v_normal set but n_s is NULL");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return set_error(ADAPT_ERR_NO_DEVICE, "no CUDA device visible: libadapt_b200 has no CPU fallback");
+    if (d->device_id < 0 || d->device_id >= n_dev) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad device_id");
+
+    adapt_handle* h = new adapt_handle();
+    h->device = d->device_id;
+    int rc = 0;
+    auto fail = [&](int code) { adapt_destroy(h); return code; };
+#define CKH(x) do { rc = (x); if (rc) return fail(rc); } while (0)
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(set_error(ADAPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    CKC(cudaSetDevice(h->device));
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, h->device));
+
+    const int np = d->n_prims, no = d->n_objects;
+    // ---- per-primitive tables
+    std::vector<uint8_t> sph((size_t)np, 0);
+    std::vector<int32_t> prim_obj((size_t)np, -1);
+    std::vector<int4> obj_info((size_t)no);
+    for (int o = 0; o < no; o++) {
+        int first = d->obj_info[o * 3], cnt = d->obj_info[o * 3 + 1], type = d->obj_info[o * 3 + 2];
+        if (first < 0 || cnt < 0 || first + cnt > np) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: obj_info out of range"));
+        int eid = d->emitter_id[o];
+        if (eid >= d->n_emitters) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: emitter_id out of range"));
+        obj_info[o] = make_int4(first, cnt, type, eid);
+        for (int k = first; k < first + cnt; k++) { prim_obj[k] = o; sph[k] = type != 0; }
+    }
+    for (int k = 0; k < np; k++) if (prim_obj[k] < 0) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: primitive without object"));
+    for (int e = 0; e < d->n_emitters; e++)
+        if (d->emitters[e].type == 1 && (d->emitters[e].obj_ref_id < 0 || d->emitters[e].obj_ref_id >= no))
+            return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: area emitter is not attached to an object"));
+
+    std::vector<float4> prim_geom((size_t)np * 3), prim_shade((size_t)np * 4);
+    for (int k = 0; k < np; k++) {
+        const float* v = d->primitives + (size_t)k * 9;
+        if (sph[k]) {
+            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], v[3]);
+            prim_geom[k * 3 + 1] = make_float4(0, 0, 0, 0);
+            prim_geom[k * 3 + 2] = make_float4(0, 0, 0, 0);
+        } else {
+            float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
+            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], e1[0]);
+            prim_geom[k * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+            prim_geom[k * 3 + 2] = make_float4(e2[2], 0, 0, 0);
+        }
+        const float* ng = d->n_g + (size_t)k * 3;
+        uint32_t ob = (uint32_t)prim_obj[k] | (sph[k] ? 0x80000000u : 0u);
+        float obf; std::memcpy(&obf, &ob, 4);
+        prim_shade[k * 4 + 0] = make_float4(ng[0], ng[1], ng[2], obf);
+        if (d->n_s) {
+            const float* s = d->n_s + (size_t)k * 9;
+            prim_shade[k * 4 + 1] = make_float4(s[0], s[1], s[2], s[3]);
+            prim_shade[k * 4 + 2] = make_float4(s[4], s[5], s[6], s[7]);
+            prim_shade[k * 4 + 3] = make_float4(s[8], 0, 0, 0);
+        } else {
+            prim_shade[k * 4 + 1] = prim_shade[k * 4 + 2] = prim_shade[k * 4 + 3] = make_float4(0, 0, 0, 0);
+        }
+    }
+    // ---- BVH (replaces bvh_process, tracer/path_tracer.py:143-179)
+    BuildParams bp;
+    bp.max_leaf = std::min(8, std::max(1, env_int("ADAPT_BVH_MAX_LEAF", 4)));
+    bp.traverse_cost = (float)env_int("ADAPT_BVH_TRAV_COST_X10", 10) * 0.1f;
+    BuildResult br;
+    build_bvh(d->primitives, sph.data(), np, bp, br);
+    GpuBvh gb;
+    to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), gb);
+    if (gb.depth > PT_STACK_SIZE) return fail(set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack"));
+
+    SceneView& sv = h->sv;
+    float4* tmp4 = nullptr;
+    CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes.data()), gb.nodes.size() * 4)); sv.nodes = tmp4;
+    CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3)); sv.leaf_prims = tmp4;
+    CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4;
+    CKH(dev_upload(h, &tmp4, prim_shade.data(), prim_shade.size())); sv.prim_shade = tmp4;
+    adapt_bxdf* dbx = nullptr; CKH(dev_upload(h, &dbx, d->bxdfs, (size_t)no)); sv.bxdfs = dbx;
+    adapt_emitter* dem = nullptr; CKH(dev_upload(h, &dem, d->emitters, (size_t)d->n_emitters)); sv.emitters = dem;
+    int4* doi = nullptr; CKH(dev_upload(h, &doi, obj_info.data(), obj_info.size())); sv.obj_info = doi;
+    sv.n_objects = no; sv.n_emitters = d->n_emitters; sv.n_prims = np;
+    sv.cam_r.r0 = mk3(d->cam_r[0], d->cam_r[1], d->cam_r[2]);
+    sv.cam_r.r1 = mk3(d->cam_r[3], d->cam_r[4], d->cam_r[5]);
+    sv.cam_r.r2 = mk3(d->cam_r[6], d->cam_r[7], d->cam_r[8]);
+    sv.cam_t = mk3(d->cam_t[0], d->cam_t[1], d->cam_t[2]);
+    sv.inv_focal = d->inv_focal; sv.half_w = d->half_w; sv.half_h = d->half_h;
+    sv.width = d->width; sv.height = d->height;
+    sv.max_bounce = d->max_bounce; sv.num_shadow_ray = d->num_shadow_ray; sv.use_rr = d->use_rr; sv.rr_bounce_th = d->rr_bounce_th;
+    sv.use_mis = d->use_mis; sv.anti_alias = d->anti_alias; sv.stratified = d->stratified_sampling;
+    sv.two_sides = d->brdf_two_sides; sv.has_v_normal = d->has_v_normal;
+    sv.rr_threshold = d->rr_threshold; sv.world_ior = d->world_ior;
+    sv.inv_num_shadow_ray = d->num_shadow_ray > 0 ? 1.f / (float)d->num_shadow_ray : 1.f;
+    sv.seed = d->seed;
+    h->width = d->width; h->height = d->height;
+
+    // ---- pixels owned by this handle
+    std::vector<int> pixels;
+    if (d->pixel_list && d->n_pixels > 0) {
+        pixels.assign(d->pixel_list, d->pixel_list + d->n_pixels);
+        for (int p : pixels) if (p < 0 || p >= d->width * d->height) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: pixel_list entry out of range"));
+    } else {
+        // whole film (or crop window, vanilla_renderer.py:37-38) in 4x8 blocks so one warp covers a compact patch
+        int sx = d->do_crop ? std::max(0, d->start_x) : 0, ex = d->do_crop ? std::min(d->width, d->end_x) : d->width;
+        int sy = d->do_crop ? std::max(0, d->start_y) : 0, ey = d->do_crop ? std::min(d->height, d->end_y) : d->height;
+        for (int bi = sx; bi < ex; bi += 4)
+            for (int bj = sy; bj < ey; bj += 8)
+                for (int i = bi; i < std::min(bi + 4, ex); i++)
+                    for (int j = bj; j < std::min(bj + 8, ey); j++) pixels.push_back(i * d->height + j);
+    }
+    if (pixels.empty()) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: no pixels to render"));
+    h->n_pixels = (int)pixels.size();
+    CKH(dev_upload(h, &h->d_pixel_list, pixels.data(), pixels.size()));
+
+    // ---- path pool
+    int P = d->pool_size > 0 ? d->pool_size : env_int("ADAPT_POOL", 1 << 21);
+    P = std::max(P, LOGIC_BLOCK);
+    P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
+    h->pool.n_slots = P;
+    CKH(dev_alloc(h, &h->pool.ray_o, (size_t)P)); CKH(dev_alloc(h, &h->pool.ray_d, (size_t)P));
+    CKH(dev_alloc(h, &h->pool.hit, (size_t)P)); CKH(dev_alloc(h, &h->pool.thr, (size_t)P));
+    CKH(dev_alloc(h, &h->pool.col, (size_t)P)); CKH(dev_alloc(h, &h->pool.misc, (size_t)P));
+    CKH(dev_alloc(h, &h->pool.rng, (size_t)P));
+    CKC(cudaMemset(h->pool.misc, 0, (size_t)P * sizeof(uint4)));
+    CKC(cudaMemset(h->pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
+    const size_t Q = (size_t)P * (size_t)std::max(1, d->num_shadow_ray);
+    h->sq.capacity = (int)Q;
+    CKH(dev_alloc(h, &h->sq.o, Q)); CKH(dev_alloc(h, &h->sq.d, Q)); CKH(dev_alloc(h, &h->sq.c, Q));
+    CKH(dev_alloc(h, &h->sq.count, (size_t)4));
+    CKC(cudaMemset(h->sq.count, 0, 16));
+    CKH(dev_alloc(h, &h->d_ctr, (size_t)1)); CKC(cudaMemset(h->d_ctr, 0, sizeof(DeviceCounters)));
+    CKH(dev_alloc(h, &h->d_cur, (size_t)1)); CKC(cudaMemset(h->d_cur, 0, sizeof(Cursors)));
+    CKC(cudaHostAlloc((void**)&h->h_ctr, sizeof(DeviceCounters), cudaHostAllocDefault));
+    std::memset(h->h_ctr, 0, sizeof(DeviceCounters));
+    CKH(dev_alloc(h, &h->d_accum, (size_t)d->width * d->height * 3));
+    CKC(cudaMemset(h->d_accum, 0, (size_t)d->width * d->height * 3 * sizeof(float)));
+
+    // ---- launch shape: persistent trace kernels, a multiple of the SM count
+    int per_sm = env_int("ADAPT_TRACE_BLOCKS_PER_SM", 8);
+    h->trace_grid = prop.multiProcessorCount * std::max(1, per_sm);
+    h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
+    h->ev_ring.resize(512);
+    for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
+    CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));
+    CKC(cudaDeviceSynchronize());
+#undef CKH
+#undef CKC
+    *out = h;
+    return 0;
+}
+
+int adapt_render(adapt_handle* h, int32_t n_spp) {
+    if (!h) return set_error(ADAPT_ERR_STATE, "adapt_render: null handle");
+    if (n_spp <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    // the previous range is fully handed out (adapt_render returns only then); free slots may have
+    // bumped next_work past it, so the new range starts wherever the counter stands now
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->h_ctr, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost));
+    h->work_lo = std::max(h->h_ctr->next_work, h->work_hi);
+    if (h->h_ctr->next_work < h->work_lo) {
+        unsigned long long v = h->work_lo;
+        CK(cudaMemcpy(&h->d_ctr->next_work, &v, sizeof(v), cudaMemcpyHostToDevice));
+    }
+    h->work_hi = h->work_lo + (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
+    h->cnt_base = h->cnt;
+    h->cnt += n_spp;
+    h->total_paths += (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
+    const unsigned long long target = h->work_hi;
+    // hand out all work; stragglers keep flowing into the next call (adapt_sync drains them)
+    return run_until(h, [target](const DeviceCounters& c) { return c.next_work >= target; });
+}
+
+int adapt_sync(adapt_handle* h) {
+    if (!h) return set_error(ADAPT_ERR_STATE, "adapt_sync: null handle");
+    const unsigned long long target = h->total_paths;
+    int rc = run_until(h, [target](const DeviceCounters& c) { return c.paths_done >= target; });
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return drain_events(h);
+}
+
+int adapt_read_accum(adapt_handle* h, float* dst, int32_t* spp) {
+    if (!h || !dst) return set_error(ADAPT_ERR_INVALID, "adapt_read_accum: null argument");
+    int rc = adapt_sync(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dst, h->d_accum, (size_t)h->width * h->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (spp) *spp = h->cnt;
+    return 0;
+}
+
+int adapt_load_accum(adapt_handle* h, const float* src, int32_t spp) {
+    if (!h || !src || spp < 0) return set_error(ADAPT_ERR_INVALID, "adapt_load_accum: bad argument");
+    int rc = adapt_sync(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_accum, src, (size_t)h->width * h->height * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->cnt = spp;
+    return 0;
+}
+
+int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats) {
+    if (!h || !dptr) return set_error(ADAPT_ERR_INVALID, "adapt_accum_device_ptr: null argument");
+    *dptr = h->d_accum;
+    if (n_floats) *n_floats = (uint64_t)h->width * h->height * 3;
+    return 0;
+}
+
+int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
+    if (!h || !out) return set_error(ADAPT_ERR_INVALID, "adapt_get_stats: null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    DeviceCounters c;
+    CK(cudaMemcpy(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    *out = h->stats;
+    out->paths = c.paths_done - h->ctr_base.paths_done;
+    out->rays_closest = c.rays_closest - h->ctr_base.rays_closest;
+    out->rays_shadow = (c.rays_shadow - h->ctr_base.rays_shadow) + (c.shadow_inline - h->ctr_base.shadow_inline);
+    out->nodes_visited = c.nodes_visited - h->ctr_base.nodes_visited;
+    out->prims_tested = c.prims_tested - h->ctr_base.prims_tested;
+    return 0;
+}
+
+int adapt_reset_stats(adapt_handle* h) {
+    if (!h) return set_error(ADAPT_ERR_STATE, "adapt_reset_stats: null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    CK(cudaMemcpy(&h->ctr_base, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost));
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    return 0;
+}
+
+int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* rays_d, const float* tmax, int32_t n, int32_t any_hit,
+                          int32_t* hit_obj, int32_t* hit_prim, float* hit_t, float* hit_u, float* hit_v) {
+    if (!h || !rays_o || !rays_d || !hit_prim || n < 0) return set_error(ADAPT_ERR_INVALID, "adapt_intersect_batch: bad argument");
+    if (!any_hit && (!hit_obj || !hit_t || !hit_u || !hit_v)) return set_error(ADAPT_ERR_INVALID, "adapt_intersect_batch: closest-hit needs all outputs");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    float *d_o = nullptr, *d_d = nullptr, *d_tm = nullptr, *d_t = nullptr, *d_u = nullptr, *d_v = nullptr;
+    int *d_obj = nullptr, *d_prim = nullptr;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_tm); cudaFree(d_t); cudaFree(d_u); cudaFree(d_v); cudaFree(d_obj); cudaFree(d_prim); };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return set_error(ADAPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    size_t n3 = (size_t)n * 3 * sizeof(float), n1 = (size_t)n * sizeof(float);
+    CKF(cudaMalloc(&d_o, n3)); CKF(cudaMalloc(&d_d, n3)); CKF(cudaMalloc(&d_t, n1)); CKF(cudaMalloc(&d_u, n1)); CKF(cudaMalloc(&d_v, n1));
+    CKF(cudaMalloc(&d_obj, n1)); CKF(cudaMalloc(&d_prim, n1));
+    CKF(cudaMemcpy(d_o, rays_o, n3, cudaMemcpyHostToDevice)); CKF(cudaMemcpy(d_d, rays_d, n3, cudaMemcpyHostToDevice));
+    if (tmax) { CKF(cudaMalloc(&d_tm, n1)); CKF(cudaMemcpy(d_tm, tmax, n1, cudaMemcpyHostToDevice)); }
+    k_intersect_batch<<<(n + 127) / 128, 128, 0, h->stream>>>(h->sv, n, d_o, d_d, d_tm, any_hit, d_obj, d_prim, d_t, d_u, d_v);
+    CKF(cudaGetLastError());
+    CKF(cudaStreamSynchronize(h->stream));
+    h->stats.kernel_launches += 1;
+    CKF(cudaMemcpy(hit_prim, d_prim, n1, cudaMemcpyDeviceToHost));
+    if (hit_obj) CKF(cudaMemcpy(hit_obj, d_obj, n1, cudaMemcpyDeviceToHost));
+    if (!any_hit) {
+        CKF(cudaMemcpy(hit_t, d_t, n1, cudaMemcpyDeviceToHost)); CKF(cudaMemcpy(hit_u, d_u, n1, cudaMemcpyDeviceToHost));
+        CKF(cudaMemcpy(hit_v, d_v, n1, cudaMemcpyDeviceToHost));
+    }
+#undef CKF
+    cleanup();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// pt_common.cuh -- shared device types, vector maths and the RNG of the wavefront path tracer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/adapt_b200.h"
+
+namespace adapt {
+
+// ------------------------------------------------------------------------------------------------
+// float3 helpers
+// ------------------------------------------------------------------------------------------------
+#define PT_HD __host__ __device__ __forceinline__
+#define PT_D __device__ __forceinline__
+
+PT_HD float3 mk3(float x, float y, float z) { return make_float3(x, y, z); }
+PT_HD float3 mk3(float s) { return make_float3(s, s, s); }
+PT_HD float3 operator+(float3 a, float3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PT_HD float3 operator-(float3 a, float3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PT_HD float3 operator-(float3 a) { return mk3(-a.x, -a.y, -a.z); }
+PT_HD float3 operator*(float3 a, float3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+PT_HD float3 operator/(float3 a, float3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+PT_HD float3 operator*(float3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+PT_HD float3 operator*(float s, float3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+PT_HD float3 operator/(float3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+PT_HD float3 operator+(float3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
+PT_HD float3 operator-(float s, float3 a) { return mk3(s - a.x, s - a.y, s - a.z); }
+PT_HD void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+PT_HD void operator*=(float3& a, float3 b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; }
+PT_HD void operator*=(float3& a, float s) { a.x *= s; a.y *= s; a.z *= s; }
+PT_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+PT_HD float3 cross(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+PT_HD float norm_sqr(float3 a) { return dot(a, a); }
+PT_HD float norm(float3 a) { return sqrtf(dot(a, a)); }
+PT_HD float3 normalized(float3 a) { return a / norm(a); }      // no epsilon: zero vectors give NaN like taichi's .normalized()
+PT_HD float vmax(float3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
+PT_HD float3 vabs(float3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+PT_HD float3 vpow(float b, float3 e) { return mk3(powf(b, e.x), powf(b, e.y), powf(b, e.z)); }
+PT_HD float signf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+PT_HD float3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+PT_HD bool is_zero3(float3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+
+struct Mat3 { float3 r0, r1, r2; };      // rows
+PT_HD float3 mul(const Mat3& A, float3 v) { return mk3(dot(A.r0, v), dot(A.r1, v), dot(A.r2, v)); }
+
+#define PT_PI 3.14159265358979323846f
+#define PT_INV_PI 0.31830988618379067154f
+#define PT_INV_2PI 0.15915494309189533577f
+#define PT_PI2 6.28318530717958647692f
+
+// ------------------------------------------------------------------------------------------------
+// RNG: PCG32 (XSH-RR 64/32), one stream position per (seed, pixel, sample). The spec is shared
+// bit-for-bit with the CPU oracle so parity tests are sample-exact up to fp rounding. Draw order on
+// the path follows the reference's program order.
+// ------------------------------------------------------------------------------------------------
+PT_HD uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct Rng {
+    uint64_t state;
+    PT_HD void init(uint64_t seed, uint32_t pixel, uint32_t sample) {
+        state = mix64(seed ^ mix64(((uint64_t)pixel << 32) | (uint64_t)sample));
+    }
+    PT_HD uint32_t next_u32() {
+        uint64_t old = state;
+        state = old * 6364136223846793005ull + 1442695040888963407ull;
+        uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t)(old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
+    }
+    PT_HD float rand_f() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }   // ti.random(float)
+    PT_HD int32_t rand_i() { return (int32_t)next_u32(); }                              // ti.random(int)
+};
+PT_HD int floor_mod(int32_t a, int32_t n) { int r = a % n; return r < 0 ? r + n : r; }  // taichi `%`
+
+// ------------------------------------------------------------------------------------------------
+// device-side scene view (passed by value to every kernel)
+// ------------------------------------------------------------------------------------------------
+struct SceneView {
+    // BVH (bvh_build.h layouts)
+    const float4* nodes;        // 4 x float4 per node
+    const float4* leaf_prims;   // 3 x float4 per primitive, leaf order
+    // primitives in original order
+    const float4* prim_geom;    // 3 x float4: (v0, e1.x) (e1.yz, e2.xy) (e2.z, -, -, -); sphere: (center, r)
+    const float4* prim_shade;   // 4 x float4: (n_g, obj bits) (vn0, vn1.x) (vn1.yz, vn2.xy) (vn2.z, sphere flag, 0, 0)
+    // objects / emitters
+    const adapt_bxdf* bxdfs;
+    const adapt_emitter* emitters;
+    const int4* obj_info;       // (first_prim, n_prims, type, emitter_id)
+    int n_objects, n_emitters, n_prims;
+    // camera
+    Mat3 cam_r;
+    float3 cam_t;
+    float inv_focal, half_w, half_h;
+    int width, height;
+    // integrator
+    int max_bounce, num_shadow_ray, use_rr, rr_bounce_th, use_mis, anti_alias, stratified, two_sides, has_v_normal;
+    float rr_threshold, world_ior, inv_num_shadow_ray;
+    uint64_t seed;
+};
+
+// Path pool (SoA, one entry per slot) and queues. All float4 / uint4 so every access is one 128-bit
+// load or store, coalesced across a warp.
+struct PathPool {
+    float4* ray_o;     // (o.xyz, tmax)   tmax < 0: nothing to trace for this slot in this iteration
+    float4* ray_d;     // (d.xyz, -)
+    float4* hit;       // (t, u, v, prim_id bits)   prim_id < 0: miss
+    float4* thr;       // (contribution.rgb, ray_pdf)
+    float4* col;       // (color.rgb, -)   shadow kernel adds NEE payloads here
+    uint4* misc;       // (pixel, sample cnt, bounce | flags << 16, -)
+    uint2* rng;        // PCG32 state
+    int n_slots;
+};
+enum : uint32_t { SLOT_ALIVE = 1u << 16, SLOT_SPECULAR = 1u << 17, SLOT_FINISH = 1u << 18 };
+
+struct ShadowQueue {
+    float4* o;         // (o.xyz, distance to the emitter sample)
+    float4* d;         // (d.xyz, slot bits)
+    float4* c;         // (payload.rgb, -)
+    uint32_t* count;
+    int capacity;
+};
+
+struct DeviceCounters {          // all monotonic
+    unsigned long long next_work;       // work items handed out (pixel-samples)
+    unsigned long long paths_done;      // pixel-samples finished and accumulated
+    unsigned long long rays_closest;
+    unsigned long long rays_shadow;
+    unsigned long long nodes_visited;
+    unsigned long long prims_tested;
+    unsigned long long shadow_inline;   // shadow rays traced inside the logic kernel (two-sided corner case)
+    unsigned long long pad;
+};
+
+}  // namespace adapt

@@ -1,0 +1,145 @@
+// pt_trace.cuh -- BVH traversal and primitive tests (device).
+//
+// Replaces the reference's stackless skip-pointer DFS (tracer/path_tracer.py:338-422), which visits
+// the tree in storage order without front-to-back ordering.  Here: a binary BVH whose 64-byte node
+// carries both child boxes (four 128-bit loads per step), near-child-first descent with the far
+// child pushed on a per-thread stack, and early culling against the running closest hit.  The hit
+// that comes out is the same: closest t in (1e-4, t_max) with the reference's acceptance tests
+//   triangle: u >= 0, v >= 0, u + v <= 1           (tracer_base.py:205-208, path_tracer.py:329-335)
+//   sphere:   geometric solve with inside/outside root pick (tracer_base.py:185-197)
+#pragma once
+#include "pt_common.cuh"
+
+namespace adapt {
+
+#define PT_STACK_SIZE 64
+#define PT_T_EPS 1e-4f          // "ray_t > 1e-4" self-intersection guard of the reference
+#define PT_T_INF 1e7f           // min_depth initial value (tracer_base.py:176)
+
+struct HitRec {
+    float t, u, v;
+    int prim;        // original primitive id, -1 = miss
+    int obj;         // object id | sphere flag in bit 31 (valid when prim >= 0)
+};
+
+struct RayPre {      // per-ray precomputation for the slab test: t = lo * idir - o * idir (one FMA per plane)
+    float3 o, d, idir, ood;
+};
+PT_D RayPre make_ray(float3 o, float3 d) {
+    RayPre r; r.o = o; r.d = d;
+    const float eps = 1e-20f;
+    float dx = fabsf(d.x) > eps ? d.x : copysignf(eps, d.x);
+    float dy = fabsf(d.y) > eps ? d.y : copysignf(eps, d.y);
+    float dz = fabsf(d.z) > eps ? d.z : copysignf(eps, d.z);
+    r.idir = mk3(1.f / dx, 1.f / dy, 1.f / dz);
+    r.ood = mk3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
+    return r;
+}
+
+// Primitive test against one 48-byte leaf record. Returns true and updates (t,u,v) when the
+// primitive is hit in (PT_T_EPS, tmax).
+PT_D bool prim_test(const float4 t0, const float4 t1, const float4 t2, const RayPre& r, float tmax, float& t_out, float& u_out, float& v_out) {
+    const uint32_t ob = __float_as_uint(t2.z);
+    if (ob & 0x80000000u) {
+        // sphere: center = t0.xyz, radius = t0.w
+        float3 s2c = mk3(t0.x, t0.y, t0.z) - r.o;
+        float radius2 = t0.w * t0.w;
+        float center_norm2 = norm_sqr(s2c);
+        float proj_norm = dot(r.d, s2c);
+        float c2ray_norm = center_norm2 - proj_norm * proj_norm;
+        if (c2ray_norm >= radius2) return false;
+        float ray_cut = sqrtf(radius2 - c2ray_norm);
+        float ray_t = proj_norm + (center_norm2 > radius2 + 1e-4f ? -ray_cut : ray_cut);
+        if (ray_t > PT_T_EPS && ray_t < tmax) { t_out = ray_t; u_out = 0.f; v_out = 0.f; return true; }
+        return false;
+    }
+    // triangle: solve [e1 e2 -d] (u v t)^T = o - v0 by Cramer's rule (the reference inverts the same matrix)
+    float3 v0 = mk3(t0.x, t0.y, t0.z);
+    float3 e1 = mk3(t0.w, t1.x, t1.y);
+    float3 e2 = mk3(t1.z, t1.w, t2.x);
+    float3 pvec = cross(r.d, e2);
+    float det = dot(e1, pvec);
+    float inv_det = 1.f / det;
+    float3 tvec = r.o - v0;
+    float u = dot(tvec, pvec) * inv_det;
+    float3 qvec = cross(tvec, e1);
+    float v = dot(r.d, qvec) * inv_det;
+    float t = dot(e2, qvec) * inv_det;
+    if (u >= 0.f && v >= 0.f && u + v <= 1.f && t > PT_T_EPS && t < tmax) { t_out = t; u_out = u; v_out = v; return true; }
+    return false;
+}
+
+// slab test of both children of a node; returns entry distances (exit >= entry means hit)
+PT_D void child_slabs(const float4 n0, const float4 n1, const float4 n2, const RayPre& r, float tmax,
+                      float& tmin0, float& tmin1, bool& hit0, bool& hit1) {
+    float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
+    float c0loy = fmaf(n0.z, r.idir.y, -r.ood.y), c0hiy = fmaf(n0.w, r.idir.y, -r.ood.y);
+    float c0loz = fmaf(n2.x, r.idir.z, -r.ood.z), c0hiz = fmaf(n2.y, r.idir.z, -r.ood.z);
+    float c1lox = fmaf(n1.x, r.idir.x, -r.ood.x), c1hix = fmaf(n1.y, r.idir.x, -r.ood.x);
+    float c1loy = fmaf(n1.z, r.idir.y, -r.ood.y), c1hiy = fmaf(n1.w, r.idir.y, -r.ood.y);
+    float c1loz = fmaf(n2.z, r.idir.z, -r.ood.z), c1hiz = fmaf(n2.w, r.idir.z, -r.ood.z);
+    tmin0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
+    float tmax0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
+    tmin1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
+    float tmax1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+    // 1 + 4 ulp slack on the exit distance: the FMA form can round a grazing hit the wrong way
+    hit0 = tmin0 <= tmax0 * 1.0000005f;
+    hit1 = tmin1 <= tmax1 * 1.0000005f;
+}
+
+template <bool ANY_HIT, bool COUNT>
+PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit, unsigned& n_nodes, unsigned& n_prims) {
+    const RayPre r = make_ray(o, d);
+    int stack[PT_STACK_SIZE];
+    int sp = 0;
+    int node = 0;
+    hit.prim = -1; hit.t = tmax; hit.u = 0.f; hit.v = 0.f; hit.obj = 0;
+    const float4* __restrict__ nodes = sc.nodes;
+    const float4* __restrict__ prims = sc.leaf_prims;
+    while (true) {
+        while (node >= 0) {
+            const float4 n0 = __ldg(nodes + node * 4 + 0);
+            const float4 n1 = __ldg(nodes + node * 4 + 1);
+            const float4 n2 = __ldg(nodes + node * 4 + 2);
+            const float4 n3 = __ldg(nodes + node * 4 + 3);
+            if (COUNT) n_nodes++;
+            float tmin0, tmin1; bool h0, h1;
+            child_slabs(n0, n1, n2, r, hit.t, tmin0, tmin1, h0, h1);
+            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                if (tmin1 < tmin0) { int tmp = c0; c0 = c1; c1 = tmp; }
+                if (sp < PT_STACK_SIZE) stack[sp++] = c1;
+                node = c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) return hit.prim >= 0;
+                node = stack[--sp];
+            }
+        }
+        // leaf
+        {
+            const int code = ~node;
+            const int first = code >> 3, cnt = (code & 7) + 1;
+            for (int k = 0; k < cnt; k++) {
+                const float4 t0 = __ldg(prims + (first + k) * 3 + 0);
+                const float4 t1 = __ldg(prims + (first + k) * 3 + 1);
+                const float4 t2 = __ldg(prims + (first + k) * 3 + 2);
+                if (COUNT) n_prims++;
+                float t, u, v;
+                if (prim_test(t0, t1, t2, r, hit.t, t, u, v)) {
+                    hit.t = t; hit.u = u; hit.v = v;
+                    hit.prim = __float_as_int(t2.y);
+                    hit.obj = __float_as_int(t2.z);
+                    if (ANY_HIT) return true;
+                }
+            }
+        }
+        if (sp == 0) return hit.prim >= 0;
+        node = stack[--sp];
+    }
+}
+
+}  // namespace adapt
