@@ -246,7 +246,12 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                                             : direct_spec * shadow_int / emitter_pdf;
                 payload = payload * sv.inv_num_shadow_ray * contribution;
                 const bool nonzero = !is_zero3(payload);
-                if (le_corner && !flipped_for_le) {
+                if (!isfinite(mis_w)) {
+                    // The reference multiplies the (zeroed) shadow intensity by mis_w even when the
+                    // shadow ray is occluded, so a NaN/inf MIS weight poisons the whole path either
+                    // way (0 * NaN): no shadow ray needed, and the NaN scrub later drops the sample.
+                    direct_inline += mk3(nanf(""));
+                } else if (le_corner && !flipped_for_le) {
                     // eval() only runs (and flips the normals) when the shadow ray is unoccluded: the
                     // outcome decides which normal eval_le sees, so resolve it here (rare path)
                     HitRec hr; unsigned nn = 0, np = 0;

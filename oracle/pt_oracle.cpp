@@ -1294,6 +1294,7 @@ inline vec3 pix2ray(const Scene& sc, Rng& rng, int i, int j, int cnt) {
 // ------------------------------------------------------------------------------------------------
 // renderer/vanilla_renderer.py:36-120 -- one pixel-sample
 // ------------------------------------------------------------------------------------------------
+static thread_local bool g_dbg = false;
 vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
     Rng rng;
     rng.init(sc.seed, (uint32_t)(i * sc.h + j), (uint32_t)cnt);
@@ -1351,6 +1352,8 @@ vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
             }
         }
         if (!break_flag) direct_int *= sc.inv_num_shadow_ray;
+        if (g_dbg) std::printf("  b%d obj %d prim %d t %.6f hit (%.5f %.5f %.5f) n_s (%.4f %.4f %.4f) direct (%.5g %.5g %.5g) thr (%.5g %.5g %.5g) ew %.5g hl %d\n", bounce, it.obj_id, it.prim_id,
+            it.min_depth, hit_point.x, hit_point.y, hit_point.z, it.n_s.x, it.n_s.y, it.n_s.z, direct_int.x, direct_int.y, direct_int.z, contribution.x, contribution.y, contribution.z, emission_weight, hit_light);
         vec3 emit_int(0.f);
         if (hit_light >= 0) emit_int = Source(sc.src[hit_light]).eval_le(hit_point - ray_o, it.n_s);
 
@@ -1359,6 +1362,7 @@ vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
         sample_new_ray(sc, rng, it, ray_d, &new_dir, &indirect_spec, &ray_pdf, &is_specular);
         ray_d = new_dir;
         ray_o = hit_point;
+        if (g_dbg) std::printf("     sample dir (%.5f %.5f %.5f) spec (%.5g %.5g %.5g) pdf %.6g specular %d emit (%.4g)\n", ray_d.x, ray_d.y, ray_d.z, indirect_spec.x, indirect_spec.y, indirect_spec.z, ray_pdf, (int)is_specular, emit_int.x);
         color += (direct_int + emit_int * emission_weight) * contribution;
         contribution *= indirect_spec / ray_pdf;
         it = ray_intersect(sc, ray_d, ray_o, cn);
@@ -1653,6 +1657,7 @@ void oracle_render(oracle_scene* os, int cnt_start, int n_spp, float* accum, con
 }
 
 // One pixel-sample, returning colour and the number of RNG draws (for the numpy cross-check).
+void oracle_set_debug(int on) { g_dbg = on != 0; }
 void oracle_render_sample(oracle_scene* os, int i, int j, int cnt, float* rgb, uint64_t* draws) {
     Counters cn;
     vec3 c = render_sample(os->sc, i, j, cnt, cn);
