@@ -85,7 +85,7 @@ class adapt_stats(C.Structure):
 # every symbol include/adapt_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "adapt_create", "adapt_destroy", "adapt_render", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
-    "adapt_accum_device_ptr", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch",
+    "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch",
     "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version",
 ]
 
@@ -118,6 +118,8 @@ def load_library(path: Optional[str] = None):
     lib.adapt_load_accum.restype = C.c_int
     lib.adapt_accum_device_ptr.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.adapt_accum_device_ptr.restype = C.c_int
+    lib.adapt_set_stream.argtypes = [H, C.c_void_p]
+    lib.adapt_set_stream.restype = C.c_int
     lib.adapt_get_stats.argtypes = [H, C.POINTER(adapt_stats)]
     lib.adapt_get_stats.restype = C.c_int
     lib.adapt_reset_stats.argtypes = [H]

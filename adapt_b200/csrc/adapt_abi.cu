@@ -442,7 +442,8 @@ __global__ void k_intersect_batch(const SceneView sv, int n, const float* __rest
 // ================================================================================================
 struct adapt_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;            // stream in use
+    cudaStream_t own_stream = nullptr;        // created by adapt_create
     SceneView sv{};
     PathPool pool{};
     ShadowQueue sq{};
@@ -585,7 +586,7 @@ void adapt_destroy(adapt_handle* h) {
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) if (ev.e[k]) cudaEventDestroy(ev.e[k]);
     if (h->ev_poll) cudaEventDestroy(h->ev_poll);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
@@ -611,7 +612,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
 #define CKH(x) do { rc = (x); if (rc) return fail(rc); } while (0)
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(set_error(ADAPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
     CKC(cudaSetDevice(h->device));
-    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, h->device));
 
@@ -803,6 +805,16 @@ int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats) {
     if (!h || !dptr) return set_error(ADAPT_ERR_INVALID, "adapt_accum_device_ptr: null argument");
     *dptr = h->d_accum;
     if (n_floats) *n_floats = (uint64_t)h->width * h->height * 3;
+    return 0;
+}
+
+int adapt_set_stream(adapt_handle* h, void* cuda_stream) {
+    if (!h) return set_error(ADAPT_ERR_STATE, "adapt_set_stream: null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
     return 0;
 }
 

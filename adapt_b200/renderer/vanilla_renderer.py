@@ -132,6 +132,10 @@ class Renderer:
               "adapt_load_accum")
         self._cnt = int(spp)
 
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on a caller-owned CUDA stream (pass ``torch.cuda.current_stream().cuda_stream``); None restores the own stream."""
+        check(self._lib, self._lib.adapt_set_stream(self._handle, C.c_void_p(cuda_stream) if cuda_stream else None), "adapt_set_stream")
+
     def accum_device_ptr(self):
         """(device pointer, n_floats) of the (w,h,3) sum -- used for the multi-GPU framebuffer reduce."""
         ptr = C.c_void_p()

@@ -121,6 +121,11 @@ int adapt_load_accum(adapt_handle* h, const float* src_whc, int32_t spp);   /* c
 /* Device pointer of the (w,h,3) float sum, for in-place collectives (torch.distributed / NCCL). */
 int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats);
 
+/* Run this handle's kernels and copies on a caller-owned CUDA stream (e.g. torch's current stream, so
+ * torch.cuda.Event timing and NCCL collectives are stream-ordered with the render). NULL restores the
+ * handle's own stream. The handle must be idle (call adapt_sync first). */
+int adapt_set_stream(adapt_handle* h, void* cuda_stream);
+
 int adapt_get_stats(adapt_handle* h, adapt_stats* out);
 int adapt_reset_stats(adapt_handle* h);
 
