@@ -29,12 +29,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in files if os.path.exists(f))
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None) -> str:
+    """out: alternative output path (tuning variants, e.g. -DLOGIC_MIN_BLOCKS=3; pick one at run time with ADAPT_B200_LIB)."""
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
+    out = out or LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-ccbin", "g++", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--shared", "-o", LIB]
+           "-ccbin", "g++", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--shared", "-o", out]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += list(extra_flags)
@@ -46,7 +48,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

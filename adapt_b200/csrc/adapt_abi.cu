@@ -49,8 +49,15 @@ static int env_int(const char* name, int dflt) {
 // ================================================================================================
 struct Cursors { unsigned closest, shadow, pad0, pad1; };
 
+#ifndef LOGIC_BLOCK
 #define LOGIC_BLOCK 256
+#endif
+#ifndef LOGIC_MIN_BLOCKS
+#define LOGIC_MIN_BLOCKS 2
+#endif
+#ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
+#endif
 
 // Block-wide allocation from a global counter: every thread passes `want` (0/1), gets its index.
 // Two barriers, one atomic per block. Must be called by all threads of the block.
@@ -71,6 +78,19 @@ __device__ __forceinline__ CounterT block_alloc(bool want, CounterT* counter, un
     CounterT idx = *s_base + (CounterT)(s_warp[warp] + rank);
     __syncthreads();       // s_warp / s_base are reused by the next call
     return idx;
+}
+
+// Warp-aggregated allocation: one atomic per warp, no block barrier. Must be called by all 32 lanes.
+template <typename CounterT>
+__device__ __forceinline__ CounterT warp_alloc(bool want, CounterT* counter) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned ballot = __ballot_sync(0xffffffffu, want);
+    if (ballot == 0u) return (CounterT)0;
+    const int leader = __ffs(ballot) - 1;
+    CounterT base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (CounterT)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (CounterT)__popc(ballot & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void block_count(unsigned v, unsigned long long* counter) {
@@ -124,19 +144,22 @@ __device__ __forceinline__ float3 camera_ray(const SceneView& sv, Rng& g, int i,
 // ================================================================================================
 // k_logic
 // ================================================================================================
-__global__ void __launch_bounds__(LOGIC_BLOCK)
+__global__ void __launch_bounds__(LOGIC_BLOCK, LOGIC_MIN_BLOCKS)
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
         float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
         const unsigned long long work_lo, const unsigned long long work_hi, const int cnt_base) {
-    __shared__ unsigned s_warp[LOGIC_BLOCK / 32];
-    __shared__ unsigned s_base32;
-    __shared__ unsigned long long s_base64;
-
     const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
     if (slot == 0) { cur->closest = 0; cur->shadow = 0; }
 
     uint4 misc = pool.misc[slot];
     bool alive = (misc.z & SLOT_ALIVE) != 0;
+    // drain phase: a warp with no live path and no work left to hand out has nothing to do
+    if (!__any_sync(0xffffffffu, alive)) {
+        unsigned long long nw = 0;
+        if ((threadIdx.x & 31) == 0) nw = *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work);
+        nw = __shfl_sync(0xffffffffu, nw, 0);
+        if (nw >= work_hi) return;
+    }
     bool terminate = false;
     bool shading = false;
 
@@ -151,47 +174,44 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     bool flip_pending = false;   // brdf_two_sides: normals flip at the first BRDF call of this bounce
 
     if (alive) {
-        bounce = (int)(misc.z & 0xffffu);
+        // all per-slot state in one batch of independent 128-bit loads (one memory round trip)
         const float4 c4 = pool.col[slot];
+        const float4 h4 = pool.hit[slot];
+        const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
+        const uint2 r2 = pool.rng[slot];
+        bounce = (int)(misc.z & 0xffffu);
         color = mk3(c4.x, c4.y, c4.z);
-        if (misc.z & SLOT_FINISH) {
-            terminate = true;
+        const int prim = __float_as_int(h4.w);
+        if ((misc.z & SLOT_FINISH) || prim < 0) {
+            terminate = true;                                        // finished last bounce / "if it.is_ray_not_hit(): break"
         } else {
-            const float4 h4 = pool.hit[slot];
-            const int prim = __float_as_int(h4.w);
-            if (prim < 0) {
-                terminate = true;                                    // "if it.is_ray_not_hit(): break"
-            } else {
-                const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
-                const uint2 r2 = pool.rng[slot];
-                ray_o = mk3(o4.x, o4.y, o4.z); ray_d = mk3(d4.x, d4.y, d4.z);
-                contribution = mk3(t4.x, t4.y, t4.z); ray_pdf = t4.w;
-                rng.state = ((uint64_t)r2.y << 32) | r2.x;
-                bool sphere;
-                load_surface(sv, prim, ray_o, ray_d, h4.x, h4.y, h4.z, sf, obj, sphere);
-                const int4 oi = __ldg(sv.obj_info + obj);
-                hit_light = oi.w;
-                mat = load_bxdf(sv.bxdfs + obj);
-                // emission MIS weight for the hit just found (vanilla_renderer.py:111-117); quirk 1/2:
-                // tests is_delta of the *hit* object and the is_specular flag of the previous sample
-                if (bounce > 0 && sv.use_mis) {
-                    float emitter_pdf = 0.f;
-                    if (hit_light >= 0 && mat.is_delta == 0 && !(misc.z & SLOT_SPECULAR))
-                        emitter_pdf = emitter_solid_angle_pdf(load_emitter(sv.emitters + hit_light), sf, ray_d);
-                    emission_weight = balance(ray_pdf, emitter_pdf);
-                }
-                // Russian roulette / cut-off (:50-57)
-                if (sv.use_rr) {
-                    float mv = vmax(contribution);
-                    if (mv < sv.rr_threshold && bounce >= sv.rr_bounce_th) {
-                        if (rng.rand_f() > mv) terminate = true;
-                        else contribution *= 1.f / (mv + 1e-7f);
-                    }
-                } else if (vmax(contribution) < 1e-4f) {
-                    terminate = true;
-                }
-                shading = !terminate;
+            ray_o = mk3(o4.x, o4.y, o4.z); ray_d = mk3(d4.x, d4.y, d4.z);
+            contribution = mk3(t4.x, t4.y, t4.z); ray_pdf = t4.w;
+            rng.state = ((uint64_t)r2.y << 32) | r2.x;
+            bool sphere;
+            load_surface(sv, prim, ray_o, ray_d, h4.x, h4.y, h4.z, sf, obj, sphere);
+            const int4 oi = __ldg(sv.obj_info + obj);
+            hit_light = oi.w;
+            mat = load_bxdf(sv.bxdfs + obj);
+            // emission MIS weight for the hit just found (vanilla_renderer.py:111-117); quirk 1/2:
+            // tests is_delta of the *hit* object and the is_specular flag of the previous sample
+            if (bounce > 0 && sv.use_mis) {
+                float emitter_pdf = 0.f;
+                if (hit_light >= 0 && mat.is_delta == 0 && !(misc.z & SLOT_SPECULAR))
+                    emitter_pdf = emitter_solid_angle_pdf(load_emitter(sv.emitters + hit_light), sf, ray_d);
+                emission_weight = balance(ray_pdf, emitter_pdf);
             }
+            // Russian roulette / cut-off (:50-57)
+            if (sv.use_rr) {
+                float mv = vmax(contribution);
+                if (mv < sv.rr_threshold && bounce >= sv.rr_bounce_th) {
+                    if (rng.rand_f() > mv) terminate = true;
+                    else contribution *= 1.f / (mv + 1e-7f);
+                }
+            } else if (vmax(contribution) < 1e-4f) {
+                terminate = true;
+            }
+            shading = !terminate;
         }
     }
 
@@ -267,7 +287,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                 }
             }
         }
-        const unsigned qi = block_alloc<unsigned>(want, sq.count, s_warp, &s_base32);
+        const unsigned qi = warp_alloc<unsigned>(want, sq.count);
         if (want) { sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c; }
     }
 
@@ -311,24 +331,18 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // Work item w in [work_lo, work_hi) is sample cnt_base + 1 + (w - work_lo) / n_pixels of pixel
     // pixel_list[(w - work_lo) % n_pixels]. Once the range is exhausted free slots stop asking.
     const bool need = !alive && !shading;
-    unsigned long long w;
+    unsigned long long w = work_hi;
     {
-        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const unsigned lane = threadIdx.x & 31;
         const unsigned ballot = __ballot_sync(0xffffffffu, need);
-        const unsigned rank = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) s_warp[warp] = __popc(ballot);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned tot = 0;
-            #pragma unroll
-            for (int k = 0; k < LOGIC_BLOCK / 32; k++) { unsigned c = s_warp[k]; s_warp[k] = tot; tot += c; }
+        if (ballot) {
+            const int leader = __ffs(ballot) - 1;
             unsigned long long base = work_hi;
-            if (tot && *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work) < work_hi)
-                base = atomicAdd(&ctr->next_work, (unsigned long long)tot);
-            s_base64 = base;
+            if ((int)lane == leader && *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work) < work_hi)
+                base = atomicAdd(&ctr->next_work, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            w = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
         }
-        __syncthreads();
-        w = s_base64 + (unsigned long long)(s_warp[warp] + rank);
     }
     if (need) {
         if (w >= work_lo && w < work_hi) {
@@ -357,28 +371,62 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 }
 
 // ================================================================================================
-// k_closest / k_shadow: persistent warps pull 32 rays at a time from a global cursor
+// k_closest / k_shadow: persistent warps over the ray streams.
+//   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements)
+//   MODE 1: per-lane refill (pt_trace.cuh: trace_stream)
 // ================================================================================================
-template <bool COUNT>
+struct ClosestSource {
+    PathPool pool;
+    PT_D unsigned size() const { return (unsigned)pool.n_slots; }
+    PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
+        const float4 o4 = pool.ray_o[i];
+        if (!(o4.w > 0.f)) return false;             // parked / finishing slot: nothing to trace
+        const float4 d4 = pool.ray_d[i];
+        o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z); tmax = o4.w;
+        return true;
+    }
+    PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim)); }
+};
+struct ShadowSource {
+    PathPool pool; ShadowQueue sq; unsigned n;
+    PT_D unsigned size() const { return n; }
+    PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
+        const float4 o4 = sq.o[i], d4 = sq.d[i];
+        o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z);
+        // does_intersect(light_dir, hit_point, emitter_d): t in (1e-4, emitter_d - 1e-4) (tracer_base.py:242)
+        tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF;
+        return true;
+    }
+    PT_D void store(unsigned i, const HitRec& h) const {
+        if (h.prim >= 0) return;                     // occluded: shadow_int = 0
+        const float4 c4 = sq.c[i];
+        float* dst = reinterpret_cast<float*>(pool.col + __float_as_int(sq.d[i].w));
+        atomicAdd(dst + 0, c4.x); atomicAdd(dst + 1, c4.y); atomicAdd(dst + 2, c4.z);
+    }
+};
+
+template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur, uint32_t* __restrict__ shadow_count) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *shadow_count = 0;      // queue is consumed; reset for the next k_logic
-    const unsigned lane = threadIdx.x & 31;
     unsigned traced = 0, nn = 0, np = 0;
-    const unsigned n = (unsigned)pool.n_slots;
-    while (true) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&cur->closest, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const unsigned slot = base + lane;
-        if (slot < n) {
-            const float4 o4 = pool.ray_o[slot];
-            if (o4.w > 0.f) {
-                const float4 d4 = pool.ray_d[slot];
+    ClosestSource src{pool};
+    if (MODE == 1) {
+        trace_stream<false, COUNT, 8>(sv, src, &cur->closest, traced, nn, np);
+    } else {
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned n = src.size();
+        while (true) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&cur->closest, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            const unsigned slot = base + lane;
+            float3 o, d; float tmax;
+            if (slot < n && src.load(slot, o, d, tmax)) {
                 HitRec hr;
-                trace<false, COUNT>(sv, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), o4.w, hr, nn, np);
-                pool.hit[slot] = make_float4(hr.t, hr.u, hr.v, __int_as_float(hr.prim));
+                trace<false, COUNT>(sv, o, d, tmax, hr, nn, np);
+                src.store(slot, hr);
                 traced++;
             }
         }
@@ -387,28 +435,28 @@ k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ 
     if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned n = *sq.count;
-    unsigned traced = 0;
-    while (true) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&cur->shadow, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const unsigned i = base + lane;
-        if (i < n) {
-            const float4 o4 = sq.o[i], d4 = sq.d[i];
-            // does_intersect(light_dir, hit_point, emitter_d): t in (1e-4, emitter_d - 1e-4) (tracer_base.py:242)
-            const float tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF;
-            HitRec hr; unsigned nn = 0, np = 0;
-            const bool occluded = trace<true, false>(sv, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), tmax, hr, nn, np);
-            traced++;
-            if (!occluded) {
-                const float4 c4 = sq.c[i];
-                float* dst = reinterpret_cast<float*>(pool.col + __float_as_int(d4.w));
-                atomicAdd(dst + 0, c4.x); atomicAdd(dst + 1, c4.y); atomicAdd(dst + 2, c4.z);
+    unsigned traced = 0, nn = 0, np = 0;
+    ShadowSource src{pool, sq, *sq.count};
+    if (MODE == 1) {
+        trace_stream<true, false, 8>(sv, src, &cur->shadow, traced, nn, np);
+    } else {
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned n = src.size();
+        while (true) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&cur->shadow, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            const unsigned i = base + lane;
+            float3 o, d; float tmax;
+            if (i < n && src.load(i, o, d, tmax)) {
+                HitRec hr;
+                trace<true, false>(sv, o, d, tmax, hr, nn, np);
+                src.store(i, hr);
+                traced++;
             }
         }
     }
@@ -460,6 +508,7 @@ struct adapt_handle {
     unsigned long long total_paths = 0;       // pixel-samples enqueued since create
     std::vector<void*> allocs;
     int trace_grid = 0;
+    int trace_mode = 1;
     bool count_nodes = false;
     // timing
     struct IterEvents { cudaEvent_t e[4]; };
@@ -508,10 +557,12 @@ static int launch_iteration(adapt_handle* h) {
     k_logic<<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, h->d_accum, h->d_pixel_list,
                                                                     h->n_pixels, h->work_lo, h->work_hi, h->cnt_base);
     CK(cudaEventRecord(ev.e[1], st));
-    k_shadow<<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur);
+    if (h->trace_mode == 1) k_shadow<1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur);
+    else k_shadow<0><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur);
     CK(cudaEventRecord(ev.e[2], st));
-    if (h->count_nodes) k_closest<true><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
-    else k_closest<false><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
+    if (h->count_nodes) k_closest<true, 0><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
+    else if (h->trace_mode == 1) k_closest<false, 1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
+    else k_closest<false, 0><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
     h->stats.iterations += 1;
@@ -740,6 +791,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     int per_sm = env_int("ADAPT_TRACE_BLOCKS_PER_SM", 8);
     h->trace_grid = prop.multiProcessorCount * std::max(1, per_sm);
     h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
+    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);
     h->ev_ring.resize(512);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
     CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));

@@ -110,17 +110,19 @@ def cpu_reference_leg(args, e, a, o, c, budget_s=15.0, n_threads=0):
     w, h = c["film"]["width"], c["film"]["height"]
     osc = OracleScene(pack_scene(e, a, o, c, seed=args.seed))
     cores = n_threads or (os.cpu_count() or 1)
-    # pilot: one 32x32 tile in the image centre
-    cw, ch = (w // 2) // 32 * 32, (h // 2) // 32 * 32
-    pilot = tile_partition(w, h, 0, 1, window=(cw, min(cw + 32, w), ch, min(ch + 32, h)))
-    t0 = time.time(); _, cn = osc.render(1, pixel_list=pilot, n_threads=cores); dt = max(time.time() - t0, 1e-4)
+    # pilot: a 192x192 block in the image centre (run twice: the first call warms caches / the OpenMP pool)
+    cw, ch = max(0, (w // 2 - 96)) // 32 * 32, max(0, (h // 2 - 96)) // 32 * 32
+    pilot = tile_partition(w, h, 0, 1, window=(cw, min(cw + 192, w), ch, min(ch + 192, h)))
+    osc.render(1, pixel_list=pilot, n_threads=cores)
+    t0 = time.time(); _, cn = osc.render(1, cnt_start=1, pixel_list=pilot, n_threads=cores); dt = max(time.time() - t0, 1e-4)
     rate = len(pilot) / dt
     n_tiles = int(max(1, min((w // 32) * (h // 32), budget_s * rate / 1024)))
     side = int(max(1, np.floor(np.sqrt(n_tiles))))
     x0 = max(0, (w // 2) - side * 16) // 32 * 32; y0 = max(0, (h // 2) - side * 16) // 32 * 32
     window = (x0, min(w, x0 + side * 32), y0, min(h, y0 + side * 32))
     sample = tile_partition(w, h, 0, 1, window=window)
-    return osc, sample, window, cores
+    spp = int(max(1, min(64, budget_s * rate / max(len(sample), 1))))      # whole film is cheap: take several spp
+    return osc, sample, window, cores, spp
 
 
 def run_reference(args):
@@ -129,24 +131,24 @@ def run_reference(args):
     if rank != 0:
         return
     e, a, o, c = load_workload(args.workload, args.width, args.height, args.max_bounce)
-    osc, sample, window, cores = cpu_reference_leg(args, e, a, o, c, budget_s=args.cpu_budget)
+    osc, sample, window, cores, spp = cpu_reference_leg(args, e, a, o, c, budget_s=args.cpu_budget / max(args.steps, 1))
     for _ in range(args.warmup):
         osc.render(1, pixel_list=sample[: max(256, len(sample) // 16)], n_threads=cores)
     rays = 0; paths = 0
     t0 = time.time()
     for k in range(args.steps):
-        _, cn = osc.render(1, cnt_start=k, pixel_list=sample, n_threads=cores)
+        _, cn = osc.render(spp, cnt_start=k * spp, pixel_list=sample, n_threads=cores)
         rays += cn["rays_closest"]; paths += cn["paths"]
     dt = time.time() - t0
     w, h = c["film"]["width"], c["film"]["height"]
     value = rays / dt / 1e6
-    sample_desc = f"{len(sample)} pixels (window x[{window[0]},{window[1]}) y[{window[2]},{window[3]})) x 1 spp per step"
+    sample_desc = f"{len(sample)} pixels (window x[{window[0]},{window[1]}) y[{window[2]},{window[3]})) x {spp} spp per step"
     line = {
         "impl": "reference", "metric": "Mrays/s (closest-hit rays: primary + secondary)", "value": value, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})",
-                   "spp_per_step": 1, "sample": sample_desc},
+                   "spp_per_step": spp, "sample": sample_desc},
         "spp_per_s": paths / dt / (w * h),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,10 +251,10 @@ def run_b200(args):
         # CPU baseline + reference-traversal statistics on a bounded sample (rank 0, N=1 only)
         cpu = None; nbar_node = nbar_prim = None
         if world == 1 and not args.no_cpu:
-            osc, sample, window, cores = cpu_reference_leg(args, e, a, o, c, budget_s=args.cpu_budget)
-            t0 = time.time(); _, cn = osc.render(1, pixel_list=sample, n_threads=cores); dt = time.time() - t0
+            osc, sample, window, cores, cspp = cpu_reference_leg(args, e, a, o, c, budget_s=args.cpu_budget)
+            t0 = time.time(); _, cn = osc.render(cspp, pixel_list=sample, n_threads=cores); dt = time.time() - t0
             cpu = {"value": cn["rays_closest"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                   "sample": f"{len(sample)} pixels (window x[{window[0]},{window[1]}) y[{window[2]},{window[3]})) x 1 spp, {dt:.1f} s"}
+                   "sample": f"{len(sample)} pixels (window x[{window[0]},{window[1]}) y[{window[2]},{window[3]})) x {cspp} spp, {dt:.1f} s"}
             if cn["nodes_visited"]:
                 nbar_node = cn["nodes_visited"] / cn["rays_closest"]; nbar_prim = cn["prims_tested"] / cn["rays_closest"]
         # roofline of the dominant kernel (k_closest), SURVEY 8(d): B_ray = 48 B queue + 36 B * nodes + 104 B * prims under the
@@ -306,13 +308,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="bunny90k", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=8)
+    ap.add_argument("--spp-per-step", type=int, default=32)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--max-bounce", type=int, default=None)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-oracle work for the cpu_baseline sample")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -15,5 +15,8 @@ for tag, scene, name, seed in [('mono','csphere','balls-mono.xml',0), ('all','te
         rdr.render_batch(spp)
         out[f'{tag}_{spp}'] = rdr.pixels.to_numpy()
         rdr.close()
+e,a,o,c = scene_parsing(os.path.join(root, 'test'), 'allbxdf.xml')
+c['film']['width']=96; c['film']['height']=96
+rdr = Renderer(e,a,o,c, seed=3); rdr.render_batch(16); out['all96_16'] = rdr.pixels.to_numpy(); rdr.close()
 np.savez_compressed('gpurun_out/gpu_dump.npz', **out)
 print('saved', list(out))
