@@ -55,6 +55,9 @@ struct Cursors { unsigned closest, shadow, pad0, pad1; };
 #ifndef LOGIC_MIN_BLOCKS
 #define LOGIC_MIN_BLOCKS 2
 #endif
+#ifndef LOGIC_MIN_BLOCKS_SIMPLE
+#define LOGIC_MIN_BLOCKS_SIMPLE 3
+#endif
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif
@@ -144,7 +147,8 @@ __device__ __forceinline__ float3 camera_ray(const SceneView& sv, Rng& g, int i,
 // ================================================================================================
 // k_logic
 // ================================================================================================
-__global__ void __launch_bounds__(LOGIC_BLOCK, LOGIC_MIN_BLOCKS)
+template <int MATS>
+__global__ void __launch_bounds__(LOGIC_BLOCK, (MATS == M_SIMPLE ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
         float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
         const unsigned long long work_lo, const unsigned long long work_hi, const int cnt_base) {
@@ -220,7 +224,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     bool flipped_for_le = false;          // has a BRDF call flipped the normals before eval_le?
     if (shading) {
         hit_point = ray_d * sf.t + ray_o;
-        flip_pending = sv.two_sides && mat.kind == 0 && dot(ray_d, sf.n_s) > 0.f;
+        flip_pending = (MATS & M_TWOSIDED) && sv.two_sides && mat.kind == 0 && dot(ray_d, sf.n_s) > 0.f;
     }
     Surf sfb = sf;                         // normals as the BRDF sees them (flipped when two-sided and back-facing)
     if (flip_pending) { sfb.n_s = -sf.n_s; sfb.n_g = -sf.n_g; }
@@ -252,13 +256,13 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                 float3 to_emitter = emit_pos - hit_point;
                 float emitter_d = norm(to_emitter);
                 float3 light_dir = to_emitter / emitter_d;
-                float3 direct_spec = mat.kind == 0 ? brdf_eval(mat, sfb, ray_d, light_dir)
-                                                   : bsdf_eval(mat, sf, ray_d, light_dir, sv.world_ior);
+                float3 direct_spec = (!(MATS & M_BSDF) || mat.kind == 0) ? brdf_eval<MATS>(mat, sfb, ray_d, light_dir)
+                                                                         : bsdf_eval(mat, sf, ray_d, light_dir, sv.world_ior);
                 float mis_w = 1.f;
                 const bool delta_pos = (em.bool_bits & 1) != 0;
                 if (sv.use_mis && !delta_pos) {
-                    float surf_pdf = mat.kind == 0 ? brdf_pdf(mat, sfb, light_dir, ray_d)
-                                                   : bsdf_pdf(mat, sf, light_dir, ray_d, sv.world_ior);
+                    float surf_pdf = (!(MATS & M_BSDF) || mat.kind == 0) ? brdf_pdf<MATS>(mat, sfb, light_dir, ray_d)
+                                                                         : bsdf_pdf(mat, sf, light_dir, ray_d, sv.world_ior);
                     mis_w = balance(emitter_pdf * direct_pdf, surf_pdf);
                     flipped_for_le = true;             // surface_pdf always runs -> flip happened
                 }
@@ -271,7 +275,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                     // shadow ray is occluded, so a NaN/inf MIS weight poisons the whole path either
                     // way (0 * NaN): no shadow ray needed, and the NaN scrub later drops the sample.
                     direct_inline += mk3(nanf(""));
-                } else if (le_corner && !flipped_for_le) {
+                } else if ((MATS & M_TWOSIDED) && le_corner && !flipped_for_le) {
                     // eval() only runs (and flips the normals) when the shadow ray is unoccluded: the
                     // outcome decides which normal eval_le sees, so resolve it here (rare path)
                     HitRec hr; unsigned nn = 0, np = 0;
@@ -299,7 +303,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
             emit_int = emitter_eval_le(load_emitter(sv.emitters + hit_light), hit_point - ray_o, n_le);
         }
         float3 new_dir, indirect_spec; float new_pdf; bool is_specular;
-        if (mat.kind == 0) brdf_sample(mat, sfb, ray_d, rng, new_dir, indirect_spec, new_pdf, is_specular);
+        if (!(MATS & M_BSDF) || mat.kind == 0) brdf_sample<MATS>(mat, sfb, ray_d, rng, new_dir, indirect_spec, new_pdf, is_specular);
         else bsdf_sample(mat, sf, ray_d, sv.world_ior, rng, new_dir, indirect_spec, new_pdf, is_specular);
         color += (direct_inline + emit_int * emission_weight * contribution);
         contribution *= indirect_spec / new_pdf;
@@ -407,11 +411,14 @@ struct ShadowSource {
 
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
-k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur, uint32_t* __restrict__ shadow_count) {
+k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur, uint32_t* __restrict__ shadow_count,
+          const int refill, const int leaf_t) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *shadow_count = 0;      // queue is consumed; reset for the next k_logic
     unsigned traced = 0, nn = 0, np = 0;
     ClosestSource src{pool};
-    if (MODE == 1) {
+    if (MODE == 2) {
+        trace_stream_vote<false, COUNT>(sv, src, &cur->closest, refill, leaf_t, traced, nn, np);
+    } else if (MODE == 1) {
         trace_stream<false, COUNT, 8>(sv, src, &cur->closest, traced, nn, np);
     } else {
         const unsigned lane = threadIdx.x & 31;
@@ -437,10 +444,13 @@ k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ 
 
 template <int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
-k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur) {
+k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
+         const int refill, const int leaf_t) {
     unsigned traced = 0, nn = 0, np = 0;
     ShadowSource src{pool, sq, *sq.count};
-    if (MODE == 1) {
+    if (MODE == 2) {
+        trace_stream_vote<true, false>(sv, src, &cur->shadow, refill, leaf_t, traced, nn, np);
+    } else if (MODE == 1) {
         trace_stream<true, false, 8>(sv, src, &cur->shadow, traced, nn, np);
     } else {
         const unsigned lane = threadIdx.x & 31;
@@ -508,7 +518,9 @@ struct adapt_handle {
     unsigned long long total_paths = 0;       // pixel-samples enqueued since create
     std::vector<void*> allocs;
     int trace_grid = 0;
-    int trace_mode = 1;
+    int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
+    int trace_mode = 2;
+    int refill = 16, leaf_t = 12;
     bool count_nodes = false;
     // timing
     struct IterEvents { cudaEvent_t e[4]; };
@@ -554,15 +566,25 @@ static int launch_iteration(adapt_handle* h) {
     adapt_handle::IterEvents& ev = h->ev_ring[h->ev_used++];
     cudaStream_t st = h->stream;
     CK(cudaEventRecord(ev.e[0], st));
-    k_logic<<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, h->d_accum, h->d_pixel_list,
-                                                                    h->n_pixels, h->work_lo, h->work_hi, h->cnt_base);
+    {
+        const int lg = h->pool.n_slots / LOGIC_BLOCK;
+#define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, h->d_accum, h->d_pixel_list, \
+                                                               h->n_pixels, h->work_lo, h->work_hi, h->cnt_base)
+        if (h->mats == M_SIMPLE) LAUNCH_LOGIC(M_SIMPLE);
+        else if (h->mats == (M_SIMPLE | M_GLOSSY | M_BSDF)) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
+        else LAUNCH_LOGIC(M_ALL);
+#undef LAUNCH_LOGIC
+    }
     CK(cudaEventRecord(ev.e[1], st));
-    if (h->trace_mode == 1) k_shadow<1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur);
-    else k_shadow<0><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur);
+    const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t;
+    if (h->trace_mode == 2) k_shadow<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
+    else if (h->trace_mode == 1) k_shadow<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
+    else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
     CK(cudaEventRecord(ev.e[2], st));
-    if (h->count_nodes) k_closest<true, 0><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
-    else if (h->trace_mode == 1) k_closest<false, 1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
-    else k_closest<false, 0><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count);
+    if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
+    else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
+    else if (h->trace_mode == 1) k_closest<false, 1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
+    else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
     h->stats.iterations += 1;
@@ -712,6 +734,21 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
             prim_shade[k * 4 + 1] = prim_shade[k * 4 + 2] = prim_shade[k * 4 + 3] = make_float4(0, 0, 0, 0);
         }
     }
+    // ---- which k_logic specialisation covers this scene
+    {
+        int need = M_SIMPLE;
+        for (int o = 0; o < no; o++) {
+            const adapt_bxdf& b = d->bxdfs[o];
+            if (b.kind != 0) need |= M_BSDF;
+            else if (b.type == 4 || b.type == 5) need |= M_GLOSSY;
+            else if (b.type == 7 || b.type == 3) need |= M_COAT_GGX;
+        }
+        if (d->brdf_two_sides) need |= M_TWOSIDED;
+        if (need == M_SIMPLE) h->mats = M_SIMPLE;
+        else if ((need & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) h->mats = M_SIMPLE | M_GLOSSY | M_BSDF;
+        else h->mats = M_ALL;
+        if (env_int("ADAPT_LOGIC_GENERIC", 0)) h->mats = M_ALL;
+    }
     // ---- BVH (replaces bvh_process, tracer/path_tracer.py:143-179)
     BuildParams bp;
     bp.max_leaf = std::min(8, std::max(1, env_int("ADAPT_BVH_MAX_LEAF", 4)));
@@ -791,7 +828,9 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     int per_sm = env_int("ADAPT_TRACE_BLOCKS_PER_SM", 8);
     h->trace_grid = prop.multiProcessorCount * std::max(1, per_sm);
     h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
-    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);
+    h->trace_mode = env_int("ADAPT_TRACE_MODE", 2);
+    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
+    h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 12)));
     h->ev_ring.resize(512);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
     CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));

@@ -15,6 +15,12 @@
 
 namespace adapt {
 
+// Material groups a k_logic instantiation is compiled for (the reference specialises its megakernel the same
+// way: ti.static flags and unused struct methods are compiled out per scene by the Taichi JIT).
+enum : int { M_SIMPLE = 1, M_GLOSSY = 2, M_COAT_GGX = 4, M_BSDF = 8, M_TWOSIDED = 16, M_ALL = 31 };
+// groups: SIMPLE = phong(0) lambertian(1) specular(2) oren-nayar(6); GLOSSY = mod-phong(4) fresnel-blend(5);
+//         COAT_GGX = thin-coat(7) microfacet(3); BSDF = det-refraction / lambertian transmission / null
+
 struct Surf {            // the part of `Interaction` (tracer/interaction.py:15-30) shading needs
     float3 n_s, n_g;
     float t;             // min_depth
@@ -299,25 +305,31 @@ PT_D float3 f_ggx(const Bxdf& m, const Surf& s, float3 in, float3 out) {        
 }
 
 // BRDF.eval :503-526 (mirror has no eval branch: zero)
+template <int MATS>
 PT_D float3 brdf_eval(const Bxdf& m, const Surf& s, float3 in, float3 out) {
     if (!(dot(in, s.n_g) * dot(out, s.n_g) < 0.f)) return mk3(0.f);
-    switch (m.type) {
-        case 0: return f_phong(m, s, in, out);
-        case 1: return f_lambert(m, s.n_s, out);
-        case 4: return f_mod_phong(m, s, in, out);
-        case 5: return f_fresnel_blend(m, s, in, out, frame_from_normal(s.n_s));
-        case 6: return f_oren_nayar(m, s, in, out);
-        case 7: return f_thin_coat(m, s, in, out);
-        case 3: return f_ggx(m, s, in, out);
-        default: return mk3(0.f);
+    if (m.type == 1) return f_lambert(m, s.n_s, out);
+    if (m.type == 0) return f_phong(m, s, in, out);
+    if (m.type == 6) return f_oren_nayar(m, s, in, out);
+    if (MATS & M_GLOSSY) {
+        if (m.type == 4) return f_mod_phong(m, s, in, out);
+        if (m.type == 5) return f_fresnel_blend(m, s, in, out, frame_from_normal(s.n_s));
     }
+    if (MATS & M_COAT_GGX) {
+        if (m.type == 7) return f_thin_coat(m, s, in, out);
+        if (m.type == 3) return f_ggx(m, s, in, out);
+    }
+    return mk3(0.f);
 }
 // BRDF.get_pdf :562-601
+template <int MATS>
 PT_D float brdf_pdf(const Bxdf& m, const Surf& s, float3 outdir, float3 in) {
     float d_out = dot(s.n_s, outdir), d_in = dot(s.n_s, in);
     if (!(d_out * d_in < 0.f)) return 0.f;
+    if (m.type == 0 || m.type == 1 || m.type == 6) return d_out * PT_INV_PI;
+    if (!(MATS & M_GLOSSY) && (m.type == 4 || m.type == 5)) return 0.f;
+    if (!(MATS & M_COAT_GGX) && (m.type == 7 || m.type == 3)) return 0.f;
     switch (m.type) {
-        case 0: case 1: case 6: return d_out * PT_INV_PI;
         case 4: {
             float gl = m.mean.z;
             float3 rv = reflect_about(in, s.n_s);
@@ -348,9 +360,13 @@ PT_D float brdf_pdf(const Bxdf& m, const Surf& s, float3 outdir, float3 in) {
     }
 }
 // BRDF.sample_new_rays :528-560 -> direction, f * cos, pdf, is_specular
+template <int MATS>
 PT_D void brdf_sample(const Bxdf& m, const Surf& s, float3 in, Rng& g, float3& dir, float3& spec, float& pdf, bool& is_specular) {
     dir = mk3(0.f, 1.f, 0.f); spec = mk3(1.f); pdf = 1.f; is_specular = false;
-    switch (m.type) {
+    int type = m.type;
+    if (!(MATS & M_GLOSSY) && (type == 4 || type == 5)) type = -1;        // not compiled into this instantiation (host never picks it then)
+    if (!(MATS & M_COAT_GGX) && (type == 7 || type == 3)) type = -1;
+    switch (type) {
         case 0: {                                                       // sample_phong :184-189
             float3 l = sample_cos_hemisphere(g, pdf);
             dir = to_world(s.n_s, l);

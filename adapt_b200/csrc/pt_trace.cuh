@@ -31,7 +31,7 @@ PT_D RayPre make_ray(float3 o, float3 d) {
     float dx = fabsf(d.x) > eps ? d.x : copysignf(eps, d.x);
     float dy = fabsf(d.y) > eps ? d.y : copysignf(eps, d.y);
     float dz = fabsf(d.z) > eps ? d.z : copysignf(eps, d.z);
-    r.idir = mk3(1.f / dx, 1.f / dy, 1.f / dz);
+    r.idir = mk3(__frcp_rn(dx), __frcp_rn(dy), __frcp_rn(dz));
     r.ood = mk3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
     return r;
 }
@@ -59,7 +59,7 @@ PT_D bool prim_test(const float4 t0, const float4 t1, const float4 t2, const Ray
     float3 e2 = mk3(t1.z, t1.w, t2.x);
     float3 pvec = cross(r.d, e2);
     float det = dot(e1, pvec);
-    float inv_det = 1.f / det;
+    float inv_det = __frcp_rn(det);
     float3 tvec = r.o - v0;
     float u = dot(tvec, pvec) * inv_det;
     float3 qvec = cross(tvec, e1);
@@ -243,6 +243,116 @@ PT_D void trace_stream(const SceneView& sc, Source& src, unsigned* __restrict__ 
             const unsigned act = __ballot_sync(FULL, cur >= 0);
             if (act == 0u) break;
             if (!exhausted && __popc(act) <= 32 - REFILL) break;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Vote-scheduled traversal (mode 2).  ncu on the while-while loop above: the inner-node instructions
+// run with ~5 of 32 lanes, because a lane that has reached a leaf waits until the slowest lane of the
+// warp has finished descending.  Here one loop iteration gives every lane that holds an inner node ONE
+// node step, and the leaf code only runs when at least `leaf_t` lanes are parked on a leaf (or no lane
+// has inner work left), so both code paths execute with well-populated warps.  Finished lanes are
+// refilled from the stream cursor as in trace_stream.
+// ------------------------------------------------------------------------------------------------
+template <bool ANY_HIT, bool COUNT, typename Source>
+PT_D void trace_stream_vote(const SceneView& sc, Source& src, unsigned* __restrict__ cursor, const int refill, const int leaf_t,
+                            unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned n = src.size();
+    const float4* __restrict__ nodes = sc.nodes;
+    const float4* __restrict__ prims = sc.leaf_prims;
+    int stack[PT_STACK_SIZE];
+    int sp = 0, node = PT_NODE_DONE;
+    int cur = -1;
+    bool exhausted = false;
+    RayPre r = make_ray(mk3(0.f), mk3(0.f, 0.f, 1.f));
+    HitRec hit; hit.prim = -1; hit.t = 0.f; hit.u = hit.v = 0.f; hit.obj = 0;
+    while (true) {
+        const unsigned idle = __ballot_sync(FULL, cur < 0);
+        if (idle) {
+            if (exhausted) {
+                if (idle == FULL) break;
+            } else if (__popc(idle) >= refill || idle == FULL) {
+                const int n_idle = __popc(idle);
+                const int leader = __ffs(idle) - 1;
+                unsigned base = 0;
+                if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)n_idle);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + (unsigned)n_idle >= n) exhausted = true;
+                if (cur < 0) {
+                    const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
+                    float3 o, d; float tmax;
+                    if (i < n && src.load(i, o, d, tmax)) {
+                        cur = (int)i;
+                        r = make_ray(o, d);
+                        hit.prim = -1; hit.t = tmax; hit.u = 0.f; hit.v = 0.f; hit.obj = 0;
+                        node = 0; sp = 0;
+                        traced++;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)
+        while (true) {
+            if (node >= 0) {
+                const float4 n0 = __ldg(nodes + node * 4 + 0);
+                const float4 n1 = __ldg(nodes + node * 4 + 1);
+                const float4 n2 = __ldg(nodes + node * 4 + 2);
+                const float4 n3 = __ldg(nodes + node * 4 + 3);
+                if (COUNT) n_nodes++;
+                float tmin0, tmin1; bool h0, h1;
+                child_slabs(n0, n1, n2, r, hit.t, tmin0, tmin1, h0, h1);
+                int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    if (tmin1 < tmin0) { int tmp = c0; c0 = c1; c1 = tmp; }
+                    if (sp < PT_STACK_SIZE) stack[sp++] = c1;
+                    node = c0;
+                } else if (h0) {
+                    node = c0;
+                } else if (h1) {
+                    node = c1;
+                } else {
+                    node = sp ? stack[--sp] : PT_NODE_DONE;
+                }
+            }
+            const bool is_leaf = node < 0 && node != PT_NODE_DONE;
+            const unsigned leaf_mask = __ballot_sync(FULL, is_leaf);
+            if (leaf_mask) {
+                // run the leaf code when enough lanes are parked on a leaf, or nobody has inner work left
+                if (__popc(leaf_mask) >= leaf_t || !__any_sync(FULL, node >= 0)) {
+                    if (is_leaf) {
+                        const int code = ~node;
+                        const int first = code >> 3, cnt = (code & 7) + 1;
+                        bool found = false;
+                        for (int k = 0; k < cnt; k++) {
+                            const float4 t0 = __ldg(prims + (first + k) * 3 + 0);
+                            const float4 t1 = __ldg(prims + (first + k) * 3 + 1);
+                            const float4 t2 = __ldg(prims + (first + k) * 3 + 2);
+                            if (COUNT) n_prims++;
+                            float t, u, v;
+                            if (prim_test(t0, t1, t2, r, hit.t, t, u, v)) {
+                                hit.t = t; hit.u = u; hit.v = v;
+                                hit.prim = __float_as_int(t2.y);
+                                hit.obj = __float_as_int(t2.z);
+                                found = true;
+                                if (ANY_HIT) break;
+                            }
+                        }
+                        node = (ANY_HIT && found) ? PT_NODE_DONE : (sp ? stack[--sp] : PT_NODE_DONE);
+                    }
+                }
+            }
+            // retire finished lanes; only then re-evaluate whether the warp should go and refill
+            const bool fin = node == PT_NODE_DONE && cur >= 0;
+            if (__any_sync(FULL, fin)) {
+                if (fin) { src.store((unsigned)cur, hit); cur = -1; }
+                const unsigned act = __ballot_sync(FULL, cur >= 0);
+                if (act == 0u) break;
+                if (!exhausted && __popc(act) <= 32 - refill) break;
+            }
         }
     }
 }

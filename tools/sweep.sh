@@ -6,7 +6,7 @@ OUT=gpurun_out/sweep.txt
 run() {   # label, env..., -- extra args
   label=$1; shift
   envs=(); while [ "$1" != "--" ] && [ $# -gt 0 ]; do envs+=("$1"); shift; done; shift
-  res=$(env "${envs[@]}" timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --spp-per-step 16 "$@" 2>/dev/null | tail -1)
+  res=$(env "${envs[@]}" timeout 90 python bench.py --steps 3 --warmup 2 --no-cpu --spp-per-step 16 "$@" 2>/dev/null | tail -1)
   python - "$label" "$res" >> $OUT <<'PY'
 import json, sys
 label, res = sys.argv[1], sys.argv[2]
@@ -21,18 +21,13 @@ PY
 }
 L=adapt_b200/lib
 W=${WORKLOAD:-bunny90k}
-run "base(mode1)" -- --workload $W
-run "trace_mode0" ADAPT_TRACE_MODE=0 -- --workload $W
-run "blocks_per_sm=4" ADAPT_TRACE_BLOCKS_PER_SM=4 -- --workload $W
-run "blocks_per_sm=9" ADAPT_TRACE_BLOCKS_PER_SM=9 -- --workload $W
-run "pool=1M" ADAPT_POOL=1048576 -- --workload $W
-run "pool=4M" ADAPT_POOL=4194304 -- --workload $W
-run "leaf=2" ADAPT_BVH_MAX_LEAF=2 -- --workload $W
-run "leaf=8" ADAPT_BVH_MAX_LEAF=8 -- --workload $W
-run "logic lb3" ADAPT_B200_LIB=$L/libadapt_b200_lb3.so -- --workload $W
-run "logic 128x4" ADAPT_B200_LIB=$L/libadapt_b200_lb128x4.so -- --workload $W
-run "logic 128x5" ADAPT_B200_LIB=$L/libadapt_b200_lb128x5.so -- --workload $W
+run "default (mode2 r16 l12, spec)" -- --workload $W
+run "generic logic" ADAPT_LOGIC_GENERIC=1 -- --workload $W
+run "mode0" ADAPT_TRACE_MODE=0 -- --workload $W
+for lt in 6 8 16; do run "leaf_t=$lt" ADAPT_LEAF_T=$lt -- --workload $W; done
+for rf in 8 12 20; do run "refill=$rf" ADAPT_REFILL=$rf -- --workload $W; done
+run "bps=9" ADAPT_TRACE_BLOCKS_PER_SM=9 -- --workload $W
 if [ "$1" == "big" ]; then
-run "orb500k base" -- --workload orb500k
-run "orb500k mode0" ADAPT_TRACE_MODE=0 -- --workload orb500k
+run "orb500k default" -- --workload orb500k
+run "balls-mono 1024 default" -- --workload balls-mono --width 1024 --height 1024
 fi
