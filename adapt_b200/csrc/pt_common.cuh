@@ -22,7 +22,9 @@ PT_HD float3 operator*(float3 a, float3 b) { return mk3(a.x * b.x, a.y * b.y, a.
 PT_HD float3 operator/(float3 a, float3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 PT_HD float3 operator*(float3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 PT_HD float3 operator*(float s, float3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
-PT_HD float3 operator/(float3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+// vector / scalar as one reciprocal and three multiplies: what LLVM's fast-math (the reference's Taichi JIT runs
+// with fast_math on) makes of x/n, y/n, z/n -- and a third of the instructions of three IEEE divisions.
+PT_HD float3 operator/(float3 a, float s) { const float r = 1.f / s; return mk3(a.x * r, a.y * r, a.z * r); }
 PT_HD float3 operator+(float3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
 PT_HD float3 operator-(float s, float3 a) { return mk3(s - a.x, s - a.y, s - a.z); }
 PT_HD void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
@@ -32,10 +34,26 @@ PT_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; 
 PT_HD float3 cross(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 PT_HD float norm_sqr(float3 a) { return dot(a, a); }
 PT_HD float norm(float3 a) { return sqrtf(dot(a, a)); }
-PT_HD float3 normalized(float3 a) { return a / norm(a); }      // no epsilon: zero vectors give NaN like taichi's .normalized()
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ float3 normalized(float3 a) { return a / norm(a); }      // no epsilon: zero vectors give NaN like taichi's .normalized()
+#else
+inline float3 normalized(float3 a) { return a / norm(a); }
+#endif
 PT_HD float vmax(float3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
 PT_HD float3 vabs(float3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
-PT_HD float3 vpow(float b, float3 e) { return mk3(powf(b, e.x), powf(b, e.y), powf(b, e.z)); }
+// Out-of-line transcendental wrappers: powf / sincosf / tanf expand to 100-250 instructions each (with their
+// slow paths). Inlined at every call site they blew k_logic up to >200 KB of SASS and the kernel stalled on
+// instruction fetch (ncu: stall_no_instruction dominant). One shared copy each keeps the hot code in the I-cache.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ float pt_powf(float a, float b) { return powf(a, b); }
+__device__ __noinline__ float2 pt_sincosf(float x) { float s, c; sincosf(x, &s, &c); return make_float2(s, c); }
+__device__ __noinline__ float pt_tanf(float x) { return tanf(x); }
+#else
+inline float pt_powf(float a, float b) { return powf(a, b); }
+inline float2 pt_sincosf(float x) { return make_float2(sinf(x), cosf(x)); }
+inline float pt_tanf(float x) { return tanf(x); }
+#endif
+PT_HD float3 vpow(float b, float3 e) { return mk3(pt_powf(b, e.x), pt_powf(b, e.y), pt_powf(b, e.z)); }
 PT_HD float signf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 PT_HD float3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
 PT_HD bool is_zero3(float3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }

@@ -75,14 +75,15 @@ PT_D Mat3 rotation_between(float3 a, float3 b) {
     return R;
 }
 PT_D Mat3 frame_from_normal(float3 n) { return rotation_between(mk3(0.f, 1.f, 0.f), n); }
-PT_D float3 to_world(float3 n, float3 local) { return mul(frame_from_normal(n), local); }          // delocalize_rotate :91-95
-PT_D float3 to_local(float3 n, float3 g) { return mul(rotation_between(n, mk3(0.f, 1.f, 0.f)), g); } // localize_rotate :97-101
+// out of line on purpose (one copy each): every BxDF uses them, inlining them ~40 times made k_logic I-cache bound
+__device__ __noinline__ float3 to_world(float3 n, float3 local) { return mul(frame_from_normal(n), local); }          // delocalize_rotate :91-95
+__device__ __noinline__ float3 to_local(float3 n, float3 g) { return mul(rotation_between(n, mk3(0.f, 1.f, 0.f)), g); } // localize_rotate :97-101
 // (cos_theta, sin_theta, cos_phi, sin_phi) of a direction in the y-up local frame (:70-89)
 PT_D float4 raw_angles_local(float3 l) {
     float ct = l.y;
     float st = sqrtf(fmaxf(0.f, 1.f - ct * ct));
     float cp = 1.f, sp = 0.f;
-    if (st > 1e-5f) { cp = l.x / st; sp = l.z / st; }
+    if (st > 1e-5f) { const float r = 1.f / st; cp = l.x * r; sp = l.z * r; }
     return make_float4(ct, st, cp, sp);
 }
 PT_D float4 raw_angles(float3 d, float3 n) { return raw_angles_local(to_local(n, d)); }
@@ -121,7 +122,7 @@ PT_D float3 snell(float3 incid, float3 n, float dot_n, float ni, float nr, float
 }
 
 // ---------------------------------------------------------------- direction samplers (sampler/general_sampling.py)
-PT_D float3 sph_dir(float ct, float st, float phi) { float s, c; sincosf(phi, &s, &c); return mk3(c * st, ct, s * st); }
+PT_D float3 sph_dir(float ct, float st, float phi) { const float2 sc = pt_sincosf(phi); return mk3(sc.y * st, ct, sc.x * st); }
 PT_D float3 sample_cos_hemisphere(Rng& g, float& pdf) {               // :29-41
     float e = g.rand_f();
     float ct = sqrtf(e), st = sqrtf(1.f - e);
@@ -130,10 +131,10 @@ PT_D float3 sample_cos_hemisphere(Rng& g, float& pdf) {               // :29-41
     return sph_dir(ct, st, phi);
 }
 PT_D float3 sample_phong_lobe(Rng& g, float alpha, float& pdf) {      // mod_phong_hemisphere :43-53
-    float ct = powf(g.rand_f(), 1.f / (alpha + 1.f));
+    float ct = pt_powf(g.rand_f(), 1.f / (alpha + 1.f));
     float st = sqrtf(1.f - ct * ct);
     float phi = PT_PI2 * g.rand_f();
-    pdf = 0.5f * (1.f + alpha) * powf(ct, alpha) * PT_INV_PI;
+    pdf = 0.5f * (1.f + alpha) * pt_powf(ct, alpha) * PT_INV_PI;
     return sph_dir(ct, st, phi);
 }
 PT_D float3 sample_uniform_sphere(Rng& g, float& pdf) {               // :63-69
@@ -146,14 +147,14 @@ PT_D float3 sample_uniform_sphere(Rng& g, float& pdf) {               // :63-69
 PT_D float3 sample_as_half(Rng& g, float nu, float nv, float& power) { // fresnel_hemisphere :95-109
     float e1 = g.rand_f() * 4.f;
     float inner = e1 - floorf(e1);
-    float tan_phi = sqrtf((nu + 1.f) / (nv + 1.f)) * tanf(PT_PI / 2.f * inner);
+    float tan_phi = sqrtf((nu + 1.f) / (nv + 1.f)) * pt_tanf(PT_PI / 2.f * inner);
     float cp2 = 1.f / (1.f + tan_phi * tan_phi);
     float sp2 = 1.f - cp2;
     float cp = sqrtf(cp2);
     if (e1 > 1.f && e1 <= 3.f) cp = -cp;
     float sp = sqrtf(sp2) * signf(2.f - e1);
     power = nu * cp2 + nv * sp2;
-    float ct = powf(1.f - g.rand_f(), 1.f / (power + 1.f));
+    float ct = pt_powf(1.f - g.rand_f(), 1.f / (power + 1.f));
     float st = sqrtf(1.f - ct * ct);
     return mk3(cp * st, ct, sp * st);
 }
@@ -183,8 +184,8 @@ PT_D void ggx_sample11(Rng& g, float ct, float& sx, float& sy) {        // __tro
     if (ct > 1.f - 1e-5f) {
         float r = sqrtf(u1 / (1.f - u1));
         float phi = 6.28318530718f * u2;
-        float s, c; sincosf(phi, &s, &c);
-        sx = r * c; sy = r * s;
+        const float2 sc = pt_sincosf(phi);
+        sx = r * sc.y; sy = r * sc.x;
         return;
     }
     float st = sqrtf(fmaxf(0.f, 1.f - ct * ct));
@@ -257,13 +258,13 @@ PT_D float3 f_fresnel_blend(const Bxdf& m, const Surf& s, float3 in, float3 out,
         float d_in = -dot(s.n_s, in);
         float d_half = fabsf(dot(s.n_s, h));
         float d_hk = fabsf(dot(h, out));
-        float3 F = m.k_s + (1.f - m.k_s) * powf(1.f - d_hk, 5.f);      // schlick_fresnel, geo_optics.py:24-27
+        float3 F = m.k_s + (1.f - m.k_s) * pt_powf(1.f - d_hk, 5.f);      // schlick_fresnel, geo_optics.py:24-27
         float c2, s2;
         as_cos2_sin2(h, s.n_s, R, d_half, c2, s2);
         float denom = d_hk * fmaxf(d_in, d_out);
-        float3 specular = m.k_g.z * powf(d_half, m.k_g.x * c2 + m.k_g.y * s2) * F / denom;
+        float3 specular = m.k_g.z * pt_powf(d_half, m.k_g.x * c2 + m.k_g.y * s2) * F / denom;
         float3 diffuse = 0.38750768885463377f * m.k_d * (1.f - m.k_s);   // 28 / (23 pi)
-        float p_in = powf(1.f - d_in / 2.f, 5.f), p_out = powf(1.f - d_out / 2.f, 5.f);
+        float p_in = pt_powf(1.f - d_in / 2.f, 5.f), p_out = pt_powf(1.f - d_out / 2.f, 5.f);
         diffuse *= (1.f - p_in) * (1.f - p_out);
         spec = (specular + diffuse) * d_out;
     }
@@ -335,7 +336,7 @@ PT_D float brdf_pdf(const Bxdf& m, const Surf& s, float3 outdir, float3 in) {
             float3 rv = reflect_about(in, s.n_s);
             float dro = fmaxf(0.f, dot(rv, outdir));
             float dp = d_out * PT_INV_PI;
-            float sp = 0.5f * (gl + 1.f) * PT_INV_PI * powf(dro, gl);
+            float sp = 0.5f * (gl + 1.f) * PT_INV_PI * pt_powf(dro, gl);
             return vmax(m.k_d) * dp + vmax(m.k_s) * sp;
         }
         case 7: {
@@ -349,7 +350,7 @@ PT_D float brdf_pdf(const Bxdf& m, const Surf& s, float3 outdir, float3 in) {
             float dh = dot(h, s.n_s);
             float c2, s2;
             as_cos2_sin2(h, s.n_s, frame_from_normal(s.n_s), dh, c2, s2);
-            float p = m.k_g.z * powf(dh, m.k_g.x * c2 + m.k_g.y * s2) / fabsf(dot(in, h));
+            float p = m.k_g.z * pt_powf(dh, m.k_g.x * c2 + m.k_g.y * s2) / fabsf(dot(in, h));
             return 0.5f * (p + d_out * PT_INV_PI);
         }
         case 3: {
@@ -433,7 +434,7 @@ PT_D void brdf_sample(const Bxdf& m, const Surf& s, float3 in, Rng& g, float3& d
             float3 h = mul(R, l);
             float d_inc;
             dir = reflect_about(in, h, d_inc);                          // fresnel_blend_dir :237-244
-            float hp = m.k_g.z * powf(dot(h, s.n_s), power);
+            float hp = m.k_g.z * pt_powf(dot(h, s.n_s), power);
             pdf = hp / fmaxf(fabsf(d_inc), 1e-7f);
             bool valid = dot(s.n_s, dir) > 0.f;
             if (g.rand_f() > 0.5f) {

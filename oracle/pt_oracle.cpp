@@ -64,7 +64,9 @@ inline vec3 operator*(vec3 a, vec3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}
 inline vec3 operator/(vec3 a, vec3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
 inline vec3 operator*(vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 inline vec3 operator*(float s, vec3 a) { return {a.x * s, a.y * s, a.z * s}; }
-inline vec3 operator/(vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+// vector / scalar as reciprocal + multiplies: LLVM fast-math (Taichi's default) applies the same `arcp` rewrite,
+// and the CUDA kernels do it explicitly, so both sides round identically here.
+inline vec3 operator/(vec3 a, float s) { const float r = 1.f / s; return {a.x * r, a.y * r, a.z * r}; }
 inline vec3 operator+(vec3 a, float s) { return {a.x + s, a.y + s, a.z + s}; }
 inline vec3 operator-(vec3 a, float s) { return {a.x - s, a.y - s, a.z - s}; }
 inline vec3 operator-(float s, vec3 a) { return {s - a.x, s - a.y, s - a.z}; }
@@ -250,8 +252,9 @@ inline vec4 convert_to_raw(vec3 d_in, vec3 normal, bool localize = true) {
     float sin_theta = std::sqrt(std::fmax(0.f, 1.f - cos_theta * cos_theta));
     float cos_phi = 1.f, sin_phi = 0.f;
     if (sin_theta > 1e-5f) {
-        cos_phi = local_dir.x / sin_theta;
-        sin_phi = local_dir.z / sin_theta;
+        const float r = 1.f / sin_theta;
+        cos_phi = local_dir.x * r;
+        sin_phi = local_dir.z * r;
     }
     return {cos_theta, sin_theta, cos_phi, sin_phi};
 }

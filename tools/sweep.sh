@@ -21,13 +21,9 @@ PY
 }
 L=adapt_b200/lib
 W=${WORKLOAD:-bunny90k}
-run "default (mode2 r16 l12, spec)" -- --workload $W
-run "generic logic" ADAPT_LOGIC_GENERIC=1 -- --workload $W
-run "mode0" ADAPT_TRACE_MODE=0 -- --workload $W
-for lt in 6 8 16; do run "leaf_t=$lt" ADAPT_LEAF_T=$lt -- --workload $W; done
-for rf in 8 12 20; do run "refill=$rf" ADAPT_REFILL=$rf -- --workload $W; done
-run "bps=9" ADAPT_TRACE_BLOCKS_PER_SM=9 -- --workload $W
+run "bunny default" -- --workload $W
 if [ "$1" == "big" ]; then
 run "orb500k default" -- --workload orb500k
 run "balls-mono 1024 default" -- --workload balls-mono --width 1024 --height 1024
+run "car290k default" -- --workload car290k --spp-per-step 4
 fi
