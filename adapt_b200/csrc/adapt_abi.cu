@@ -144,6 +144,17 @@ __device__ __forceinline__ float3 camera_ray(const SceneView& sv, Rng& g, int i,
     return normalized(mul(sv.cam_r, cd));
 }
 
+// conservative ray / box test (same slab arithmetic as the traversal, with slack): false only if the ray cannot hit anything inside
+__device__ __forceinline__ bool ray_hits_box(float3 o, float3 d, float3 lo, float3 hi) {
+    const RayPre r = make_ray(o, d);
+    float t0x = fmaf(lo.x, r.idir.x, -r.ood.x), t1x = fmaf(hi.x, r.idir.x, -r.ood.x);
+    float t0y = fmaf(lo.y, r.idir.y, -r.ood.y), t1y = fmaf(hi.y, r.idir.y, -r.ood.y);
+    float t0z = fmaf(lo.z, r.idir.z, -r.ood.z), t1z = fmaf(hi.z, r.idir.z, -r.ood.z);
+    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), PT_T_INF));
+    return tmin <= tmax * 1.00001f;
+}
+
 // ================================================================================================
 // k_logic
 // ================================================================================================
@@ -334,44 +345,55 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // ---------------------------------------------------------------- regeneration
     // Work item w in [work_lo, work_hi) is sample cnt_base + 1 + (w - work_lo) / n_pixels of pixel
     // pixel_list[(w - work_lo) % n_pixels]. Once the range is exhausted free slots stop asking.
-    const bool need = !alive && !shading;
-    unsigned long long w = work_hi;
-    {
+    // A camera ray that misses the scene's bounding box ends its path on the spot (colour 0, nothing to splat):
+    // the slot immediately takes the next work item instead of spending a whole wavefront iteration on it.
+    bool need = !alive && !shading;
+    unsigned culled = 0;
+    const bool may_cull = sv.cull_primary && sv.max_bounce > 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
         const unsigned lane = threadIdx.x & 31;
         const unsigned ballot = __ballot_sync(0xffffffffu, need);
-        if (ballot) {
-            const int leader = __ffs(ballot) - 1;
-            unsigned long long base = work_hi;
-            if ((int)lane == leader && *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work) < work_hi)
-                base = atomicAdd(&ctr->next_work, (unsigned long long)__popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            w = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
+        if (ballot == 0u) break;
+        const int leader = __ffs(ballot) - 1;
+        unsigned long long base = work_hi;
+        if ((int)lane == leader && *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work) < work_hi)
+            base = atomicAdd(&ctr->next_work, (unsigned long long)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const unsigned long long w = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
+        if (need) {
+            if (w >= work_lo && w < work_hi) {
+                const unsigned long long rel = w - work_lo;
+                const unsigned long long s = rel / (unsigned long long)n_pixels;
+                const int k = (int)(rel - s * (unsigned long long)n_pixels);
+                const int pixel = __ldg(pixel_list + k);
+                const int cnt = cnt_base + (int)s + 1;
+                Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
+                const int i = pixel / sv.height, jj = pixel - i * sv.height;
+                float3 d = camera_ray(sv, g, i, jj, cnt);
+                if (may_cull && attempt < 3 && !ray_hits_box(sv.cam_t, d, sv.world_lo, sv.world_hi)) {
+                    culled++;                       // path over: ray_intersect would return a miss
+                } else {
+                    // max_bounce <= 0: the reference still traces the primary ray but never enters the loop
+                    const bool no_loop = sv.max_bounce <= 0;
+                    pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, no_loop ? -1.f : PT_T_INF);
+                    pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+                    pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
+                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
+                    need = false;
+                }
+            } else {
+                if (misc.z & SLOT_ALIVE) {
+                    // out of work: park the slot
+                    pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
+                    pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                need = false;
+            }
         }
     }
-    if (need) {
-        if (w >= work_lo && w < work_hi) {
-            const unsigned long long rel = w - work_lo;
-            const unsigned long long s = rel / (unsigned long long)n_pixels;
-            const int k = (int)(rel - s * (unsigned long long)n_pixels);
-            const int pixel = __ldg(pixel_list + k);
-            const int cnt = cnt_base + (int)s + 1;
-            Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
-            const int i = pixel / sv.height, jj = pixel - i * sv.height;
-            float3 d = camera_ray(sv, g, i, jj, cnt);
-            // max_bounce <= 0: the reference still traces the primary ray but never enters the loop
-            const bool no_loop = sv.max_bounce <= 0;
-            pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, no_loop ? -1.f : PT_T_INF);
-            pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
-            pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
-            pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-            pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-            pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
-        } else if (misc.z & SLOT_ALIVE) {
-            // out of work: park the slot
-            pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
-            pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
+    if (may_cull) { block_count(culled, &ctr->paths_done); block_count(culled, &ctr->rays_culled); }
 }
 
 // ================================================================================================
@@ -781,6 +803,14 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     sv.rr_threshold = d->rr_threshold; sv.world_ior = d->world_ior;
     sv.inv_num_shadow_ray = d->num_shadow_ray > 0 ? 1.f / (float)d->num_shadow_ray : 1.f;
     sv.seed = d->seed;
+    {
+        // scene bounds (root of the BVH), padded: used to finish camera rays that cannot hit anything
+        const Aabb& rb = br.nodes[0].box;
+        const float pad = 1e-3f;
+        sv.world_lo = mk3(rb.lo[0] - pad, rb.lo[1] - pad, rb.lo[2] - pad);
+        sv.world_hi = mk3(rb.hi[0] + pad, rb.hi[1] + pad, rb.hi[2] + pad);
+        sv.cull_primary = env_int("ADAPT_CULL_PRIMARY", 0);
+    }
     h->width = d->width; h->height = d->height;
 
     // ---- pixels owned by this handle
@@ -919,7 +949,10 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     CK(cudaMemcpy(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
     *out = h->stats;
     out->paths = c.paths_done - h->ctr_base.paths_done;
-    out->rays_closest = c.rays_closest - h->ctr_base.rays_closest;
+    // camera rays rejected against the scene box in k_logic are ray_intersect calls too (they are answered by the
+    // same root-box test the traversal kernel would have done)
+    out->rays_closest = (c.rays_closest - h->ctr_base.rays_closest) + (c.rays_culled - h->ctr_base.rays_culled);
+    out->reserved[0] = c.rays_culled - h->ctr_base.rays_culled;
     out->rays_shadow = (c.rays_shadow - h->ctr_base.rays_shadow) + (c.shadow_inline - h->ctr_base.shadow_inline);
     out->nodes_visited = c.nodes_visited - h->ctr_base.nodes_visited;
     out->prims_tested = c.prims_tested - h->ctr_base.prims_tested;

@@ -118,6 +118,8 @@ struct SceneView {
     int max_bounce, num_shadow_ray, use_rr, rr_bounce_th, use_mis, anti_alias, stratified, two_sides, has_v_normal;
     float rr_threshold, world_ior, inv_num_shadow_ray;
     uint64_t seed;
+    float3 world_lo, world_hi;   // padded scene bounds
+    int cull_primary;
 };
 
 // Path pool (SoA, one entry per slot) and queues. All float4 / uint4 so every access is one 128-bit
@@ -150,7 +152,7 @@ struct DeviceCounters {          // all monotonic
     unsigned long long nodes_visited;
     unsigned long long prims_tested;
     unsigned long long shadow_inline;   // shadow rays traced inside the logic kernel (two-sided corner case)
-    unsigned long long pad;
+    unsigned long long rays_culled;     // camera rays finished by the scene-box test in k_logic
 };
 
 }  // namespace adapt

@@ -22,10 +22,11 @@ PY
 L=adapt_b200/lib
 W=${WORKLOAD:-bunny90k}
 run "bunny default" -- --workload $W
-run "bunny inline-mats" ADAPT_B200_LIB=$L/libadapt_b200_inl.so -- --workload $W
+run "bunny no-cull" ADAPT_CULL_PRIMARY=0 -- --workload $W
+run "bunny mode1 (no vote, no popcull)" ADAPT_TRACE_MODE=1 -- --workload $W
 if [ "$1" == "big" ]; then
 run "orb500k default" -- --workload orb500k
-run "orb500k inline-mats" ADAPT_B200_LIB=$L/libadapt_b200_inl.so -- --workload orb500k
+run "orb500k no-cull" ADAPT_CULL_PRIMARY=0 -- --workload orb500k
 run "balls-mono 1024 default" -- --workload balls-mono --width 1024 --height 1024
-run "balls-mono 1024 inline-mats" ADAPT_B200_LIB=$L/libadapt_b200_inl.so -- --workload balls-mono --width 1024 --height 1024
+run "car290k default" -- --workload car290k --spp-per-step 4
 fi
