@@ -47,7 +47,6 @@ static int env_int(const char* name, int dflt) {
 // ================================================================================================
 // device helpers
 // ================================================================================================
-struct Cursors { unsigned closest, shadow, pad0, pad1; };
 
 #ifndef LOGIC_BLOCK
 #define LOGIC_BLOCK 256
@@ -160,20 +159,27 @@ __device__ __forceinline__ bool ray_hits_box(float3 o, float3 d, float3 lo, floa
 // ================================================================================================
 template <int MATS>
 __global__ void __launch_bounds__(LOGIC_BLOCK, (MATS == M_SIMPLE ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
-k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
-        float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_lo, const unsigned long long work_hi, const int cnt_base) {
+k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
+        Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
+        const unsigned long long work_hi, const long long cnt_origin) {
     const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
-    if (slot == 0) { cur->closest = 0; cur->shadow = 0; }
+    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; }
+    // work stripe of this warp (pt_common.cuh: WorkStripe) and how many ids it may hand out in total
+    const int home = (int)((unsigned)(slot >> 5) % PT_NSTRIPE);
 
     uint4 misc = pool.misc[slot];
     bool alive = (misc.z & SLOT_ALIVE) != 0;
-    // drain phase: a warp with no live path and no work left to hand out has nothing to do
+    // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
     if (!__any_sync(0xffffffffu, alive)) {
-        unsigned long long nw = 0;
-        if ((threadIdx.x & 31) == 0) nw = *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work);
-        nw = __shfl_sync(0xffffffffu, nw, 0);
-        if (nw >= work_hi) return;
+        bool dry = true;
+        if ((threadIdx.x & 31) < 4) {
+            const int c = (home + (int)(threadIdx.x & 31)) % PT_NSTRIPE;
+            dry = *reinterpret_cast<volatile unsigned long long*>(&work[c].claimed) >= stripe_limit(work_hi, c);
+        }
+        if (__all_sync(0xffffffffu, dry)) {
+            if ((threadIdx.x & 31) == 0) sq.warp_count[slot >> 5] = 0u;
+            return;
+        }
     }
     bool terminate = false;
     bool shading = false;
@@ -242,6 +248,8 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     const bool le_corner = shading && flip_pending && hit_light >= 0;
     bool break_flag = false;
     unsigned n_inline = 0;
+    const unsigned q_base = (unsigned)(slot >> 5) * (unsigned)sq.per_warp;     // this warp's region of the shadow queue
+    unsigned q_n = 0;                                                           // entries written so far (warp-uniform)
     for (int j = 0; j < sv.num_shadow_ray; j++) {
         bool want = false;
         float4 q_o = make_float4(0.f, 0.f, 0.f, 0.f), q_d = q_o, q_c = q_o;
@@ -302,9 +310,14 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                 }
             }
         }
-        const unsigned qi = warp_alloc<unsigned>(want, sq.count);
-        if (want) { sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c; }
+        const unsigned q_ballot = __ballot_sync(0xffffffffu, want);
+        if (want) {
+            const unsigned qi = q_base + q_n + (unsigned)__popc(q_ballot & ((1u << (threadIdx.x & 31)) - 1u));
+            sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c;
+        }
+        q_n += (unsigned)__popc(q_ballot);
     }
+    if ((threadIdx.x & 31) == 0) sq.warp_count[slot >> 5] = q_n;
 
     // ---------------------------------------------------------------- emission, BSDF sampling, throughput (:99-109)
     if (shading) {
@@ -339,12 +352,14 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         if (!isnan(color.z) && color.z != 0.f) atomicAdd(px + 2, color.z);
         alive = false;
     }
-    block_count((alive || !terminate) ? 0u : 1u, &ctr->paths_done);
+    unsigned finished = (alive || !terminate) ? 0u : 1u;
     block_count(n_inline, &ctr->shadow_inline);
 
     // ---------------------------------------------------------------- regeneration
-    // Work item w in [work_lo, work_hi) is sample cnt_base + 1 + (w - work_lo) / n_pixels of pixel
-    // pixel_list[(w - work_lo) % n_pixels]. Once the range is exhausted free slots stop asking.
+    // A free slot takes the next work id of the warp's stripe: id -> sample cnt_origin + id / n_pixels + 1 of pixel
+    // pixel_list[id % n_pixels].  A stripe never hands out more than stripe_limit(work_hi): a claim that overshoots
+    // gives the excess back, so between launches `claimed` is exact and ids stay gap-free across adapt_render calls.
+    // If the home stripe is dry the warp tries its neighbours (tail of a work range only).
     // A camera ray that misses the scene's bounding box ends its path on the spot (colour 0, nothing to splat):
     // the slot immediately takes the next work item instead of spending a whole wavefront iteration on it.
     bool need = !alive && !shading;
@@ -355,18 +370,36 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         const unsigned ballot = __ballot_sync(0xffffffffu, need);
         if (ballot == 0u) break;
         const int leader = __ffs(ballot) - 1;
-        unsigned long long base = work_hi;
-        if ((int)lane == leader && *reinterpret_cast<volatile unsigned long long*>(&ctr->next_work) < work_hi)
-            base = atomicAdd(&ctr->next_work, (unsigned long long)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        const unsigned long long w = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
+        const unsigned want = (unsigned)__popc(ballot);
+        // pick a stripe with work left: lanes 0..3 look at home, home+1, home+2, home+3 (one round trip)
+        const int c_probe = (home + (int)(lane & 3u)) % PT_NSTRIPE;
+        const unsigned long long lim_probe = stripe_limit(work_hi, c_probe);
+        bool has = false;
+        if (lane < 4u) has = *reinterpret_cast<volatile unsigned long long*>(&work[c_probe].claimed) < lim_probe;
+        const unsigned live = __ballot_sync(0xffffffffu, has) & 0xfu;
+        unsigned long long base = 0, limit = 0;
+        int c = home;
+        if (live) {
+            const int pick = __ffs(live) - 1;
+            c = (home + pick) % PT_NSTRIPE;
+            limit = __shfl_sync(0xffffffffu, lim_probe, pick);
+            if ((int)lane == leader) {
+                base = atomicAdd(&work[c].claimed, (unsigned long long)want);
+                if (base + want > limit) {                        // overshoot: hand the excess back
+                    const unsigned long long ok = base < limit ? limit - base : 0ull;
+                    atomicAdd(&work[c].claimed, (unsigned long long)(0ull - ((unsigned long long)want - ok)));
+                }
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+        }
+        const unsigned long long v = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
         if (need) {
-            if (w >= work_lo && w < work_hi) {
-                const unsigned long long rel = w - work_lo;
-                const unsigned long long s = rel / (unsigned long long)n_pixels;
-                const int k = (int)(rel - s * (unsigned long long)n_pixels);
+            if (live && v < limit) {
+                const unsigned long long id = stripe_item_id(v, c);
+                const unsigned long long s = id / (unsigned long long)n_pixels;
+                const int k = (int)(id - s * (unsigned long long)n_pixels);
                 const int pixel = __ldg(pixel_list + k);
-                const int cnt = cnt_base + (int)s + 1;
+                const int cnt = (int)(cnt_origin + (long long)s + 1);
                 Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
                 const int i = pixel / sv.height, jj = pixel - i * sv.height;
                 float3 d = camera_ray(sv, g, i, jj, cnt);
@@ -383,23 +416,26 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                     pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
                     need = false;
                 }
-            } else {
+            } else if (!live || attempt == 3) {
                 if (misc.z & SLOT_ALIVE) {
-                    // out of work: park the slot
+                    // out of work (for now): park the slot
                     pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
                     pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 need = false;
             }
+            // else: the stripe ran dry under this claim -- try again (next attempt probes the neighbours)
         }
     }
-    if (may_cull) { block_count(culled, &ctr->paths_done); block_count(culled, &ctr->rays_culled); }
+    finished += culled;
+    block_count(finished, &work[home].done);
+    if (may_cull) block_count(culled, &ctr->rays_culled);
 }
 
 // ================================================================================================
 // k_closest / k_shadow: persistent warps over the ray streams.
-//   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements)
-//   MODE 1: per-lane refill (pt_trace.cuh: trace_stream)
+//   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements and node counting)
+//   MODE 2: per-lane refill + vote-scheduled traversal (pt_trace.cuh: trace_stream_vote)
 // ================================================================================================
 struct ClosestSource {
     PathPool pool;
@@ -414,9 +450,11 @@ struct ClosestSource {
     PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim)); }
 };
 struct ShadowSource {
-    PathPool pool; ShadowQueue sq; unsigned n;
-    PT_D unsigned size() const { return n; }
+    PathPool pool; ShadowQueue sq;
+    PT_D unsigned size() const { return (unsigned)sq.capacity; }
     PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
+        const unsigned region = i / (unsigned)sq.per_warp;
+        if (i - region * (unsigned)sq.per_warp >= __ldg(sq.warp_count + region)) return false;      // unused queue space
         const float4 o4 = sq.o[i], d4 = sq.d[i];
         o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z);
         // does_intersect(light_dir, hit_point, emitter_d): t in (1e-4, emitter_d - 1e-4) (tracer_base.py:242)
@@ -433,21 +471,18 @@ struct ShadowSource {
 
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
-k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur, uint32_t* __restrict__ shadow_count,
+k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
           const int refill, const int leaf_t) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *shadow_count = 0;      // queue is consumed; reset for the next k_logic
     unsigned traced = 0, nn = 0, np = 0;
     ClosestSource src{pool};
     if (MODE == 2) {
-        trace_stream_vote<false, COUNT>(sv, src, &cur->closest, refill, leaf_t, traced, nn, np);
-    } else if (MODE == 1) {
-        trace_stream<false, COUNT, 8>(sv, src, &cur->closest, traced, nn, np);
+        trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
     } else {
         const unsigned lane = threadIdx.x & 31;
         const unsigned n = src.size();
         while (true) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&cur->closest, 32u);
+            if (lane == 0) base = atomicAdd(&cur->closest[0].v, 32u);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= n) break;
             const unsigned slot = base + lane;
@@ -469,17 +504,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK)
 k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
          const int refill, const int leaf_t) {
     unsigned traced = 0, nn = 0, np = 0;
-    ShadowSource src{pool, sq, *sq.count};
+    ShadowSource src{pool, sq};
     if (MODE == 2) {
-        trace_stream_vote<true, false>(sv, src, &cur->shadow, refill, leaf_t, traced, nn, np);
-    } else if (MODE == 1) {
-        trace_stream<true, false, 8>(sv, src, &cur->shadow, traced, nn, np);
+        trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
     } else {
         const unsigned lane = threadIdx.x & 31;
         const unsigned n = src.size();
         while (true) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&cur->shadow, 32u);
+            if (lane == 0) base = atomicAdd(&cur->shadow[0].v, 32u);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= n) break;
             const unsigned i = base + lane;
@@ -528,16 +561,16 @@ struct adapt_handle {
     PathPool pool{};
     ShadowQueue sq{};
     DeviceCounters* d_ctr = nullptr;
-    DeviceCounters* h_ctr = nullptr;          // pinned
+    WorkStripe* d_work = nullptr;
+    WorkStripe* h_work = nullptr;             // pinned copy the host polls
     Cursors* d_cur = nullptr;
     float* d_accum = nullptr;
     int* d_pixel_list = nullptr;
     int n_pixels = 0;
     int width = 0, height = 0;
     int cnt = 0;                              // spp enqueued so far (the reference's self.cnt)
-    int cnt_base = 0;                         // sample counter at the start of the current work range
-    unsigned long long work_lo = 0, work_hi = 0;   // current work range in next_work units
-    unsigned long long total_paths = 0;       // pixel-samples enqueued since create
+    long long cnt_origin = 0;                 // work id -> sample number: cnt_origin + id / n_pixels + 1
+    unsigned long long work_hi = 0;           // work ids [0, work_hi) have been enqueued since create (== pixel-samples)
     std::vector<void*> allocs;
     int trace_grid = 0;
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
@@ -551,6 +584,7 @@ struct adapt_handle {
     cudaEvent_t ev_poll = nullptr;
     adapt_stats stats{};
     DeviceCounters ctr_base{};                // counters at the last reset_stats
+    unsigned long long done_base = 0;
 };
 
 template <typename T>
@@ -590,8 +624,8 @@ static int launch_iteration(adapt_handle* h) {
     CK(cudaEventRecord(ev.e[0], st));
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
-#define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, h->d_accum, h->d_pixel_list, \
-                                                               h->n_pixels, h->work_lo, h->work_hi, h->cnt_base)
+#define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, \
+                                                               h->n_pixels, h->work_hi, h->cnt_origin)
         if (h->mats == M_SIMPLE) LAUNCH_LOGIC(M_SIMPLE);
         else if (h->mats == (M_SIMPLE | M_GLOSSY | M_BSDF)) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
         else LAUNCH_LOGIC(M_ALL);
@@ -600,13 +634,11 @@ static int launch_iteration(adapt_handle* h) {
     CK(cudaEventRecord(ev.e[1], st));
     const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t;
     if (h->trace_mode == 2) k_shadow<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
-    else if (h->trace_mode == 1) k_shadow<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
     else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
     CK(cudaEventRecord(ev.e[2], st));
-    if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
-    else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
-    else if (h->trace_mode == 1) k_closest<false, 1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
-    else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->sq.count, rf, lt);
+    if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+    else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+    else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
     h->stats.iterations += 1;
@@ -614,24 +646,31 @@ static int launch_iteration(adapt_handle* h) {
     return 0;
 }
 
-// Run iterations until `done(counters)` holds. Counters are polled with one batch of lag so the
-// stream never drains while we wait.
+// Run iterations until `done(claimed, finished)` holds (sums over the work stripes). Counters are polled with one
+// batch of lag so the stream never drains while we wait.
+struct WorkTotals { unsigned long long claimed, done; };
+static WorkTotals work_totals(const WorkStripe* w) {
+    WorkTotals t{0, 0};
+    for (int c = 0; c < PT_NSTRIPE; c++) { t.claimed += w[c].claimed; t.done += w[c].done; }
+    return t;
+}
 template <typename Pred>
 static int run_until(adapt_handle* h, Pred done) {
     const int batch = 4;
+    const size_t wbytes = sizeof(WorkStripe) * PT_NSTRIPE;
     CK(cudaSetDevice(h->device));
     // cheap pre-check
-    CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (done(*h->h_ctr)) return 0;
+    if (done(work_totals(h->h_work))) return 0;
     for (int guard = 0; guard < (1 << 26); guard++) {
         for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
-        CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev_poll, h->stream));
         // overlap: queue the next batch before looking at this one's counters
         for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
         CK(cudaEventSynchronize(h->ev_poll));
-        if (done(*h->h_ctr)) return 0;
+        if (done(work_totals(h->h_work))) return 0;
     }
     return set_error(ADAPT_ERR_STATE, "wavefront did not converge");
 }
@@ -680,7 +719,7 @@ void adapt_destroy(adapt_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) if (ev.e[k]) cudaEventDestroy(ev.e[k]);
     if (h->ev_poll) cudaEventDestroy(h->ev_poll);
-    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_work) cudaFreeHost(h->h_work);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -845,12 +884,14 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     const size_t Q = (size_t)P * (size_t)std::max(1, d->num_shadow_ray);
     h->sq.capacity = (int)Q;
     CKH(dev_alloc(h, &h->sq.o, Q)); CKH(dev_alloc(h, &h->sq.d, Q)); CKH(dev_alloc(h, &h->sq.c, Q));
-    CKH(dev_alloc(h, &h->sq.count, (size_t)4));
-    CKC(cudaMemset(h->sq.count, 0, 16));
+    h->sq.per_warp = 32 * std::max(1, d->num_shadow_ray);
+    CKH(dev_alloc(h, &h->sq.warp_count, (size_t)P / 32));
+    CKC(cudaMemset(h->sq.warp_count, 0, (size_t)P / 32 * sizeof(uint32_t)));
     CKH(dev_alloc(h, &h->d_ctr, (size_t)1)); CKC(cudaMemset(h->d_ctr, 0, sizeof(DeviceCounters)));
+    CKH(dev_alloc(h, &h->d_work, (size_t)PT_NSTRIPE)); CKC(cudaMemset(h->d_work, 0, sizeof(WorkStripe) * PT_NSTRIPE));
     CKH(dev_alloc(h, &h->d_cur, (size_t)1)); CKC(cudaMemset(h->d_cur, 0, sizeof(Cursors)));
-    CKC(cudaHostAlloc((void**)&h->h_ctr, sizeof(DeviceCounters), cudaHostAllocDefault));
-    std::memset(h->h_ctr, 0, sizeof(DeviceCounters));
+    CKC(cudaHostAlloc((void**)&h->h_work, sizeof(WorkStripe) * PT_NSTRIPE, cudaHostAllocDefault));
+    std::memset(h->h_work, 0, sizeof(WorkStripe) * PT_NSTRIPE);
     CKH(dev_alloc(h, &h->d_accum, (size_t)d->width * d->height * 3));
     CKC(cudaMemset(h->d_accum, 0, (size_t)d->width * d->height * 3 * sizeof(float)));
 
@@ -875,28 +916,18 @@ int adapt_render(adapt_handle* h, int32_t n_spp) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_render: null handle");
     if (n_spp <= 0) return 0;
     CK(cudaSetDevice(h->device));
-    // the previous range is fully handed out (adapt_render returns only then); free slots may have
-    // bumped next_work past it, so the new range starts wherever the counter stands now
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(h->h_ctr, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost));
-    h->work_lo = std::max(h->h_ctr->next_work, h->work_hi);
-    if (h->h_ctr->next_work < h->work_lo) {
-        unsigned long long v = h->work_lo;
-        CK(cudaMemcpy(&h->d_ctr->next_work, &v, sizeof(v), cudaMemcpyHostToDevice));
-    }
-    h->work_hi = h->work_lo + (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
-    h->cnt_base = h->cnt;
+    // work ids are absolute and gap-free (pt_common.cuh: WorkStripe): a new batch just raises the limit
+    h->work_hi += (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
     h->cnt += n_spp;
-    h->total_paths += (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
     const unsigned long long target = h->work_hi;
     // hand out all work; stragglers keep flowing into the next call (adapt_sync drains them)
-    return run_until(h, [target](const DeviceCounters& c) { return c.next_work >= target; });
+    return run_until(h, [target](const WorkTotals& t) { return t.claimed >= target; });
 }
 
 int adapt_sync(adapt_handle* h) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_sync: null handle");
-    const unsigned long long target = h->total_paths;
-    int rc = run_until(h, [target](const DeviceCounters& c) { return c.paths_done >= target; });
+    const unsigned long long target = h->work_hi;
+    int rc = run_until(h, [target](const WorkTotals& t) { return t.done >= target; });
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return drain_events(h);
@@ -918,7 +949,9 @@ int adapt_load_accum(adapt_handle* h, const float* src, int32_t spp) {
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_accum, src, (size_t)h->width * h->height * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    // everything enqueued so far is finished (adapt_sync above): the next work id, work_hi, becomes sample spp + 1
     h->cnt = spp;
+    h->cnt_origin = (long long)spp - (long long)(h->work_hi / (unsigned long long)h->n_pixels);
     return 0;
 }
 
@@ -947,8 +980,9 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     if (rc) return rc;
     DeviceCounters c;
     CK(cudaMemcpy(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h->h_work, h->d_work, sizeof(WorkStripe) * PT_NSTRIPE, cudaMemcpyDeviceToHost));
     *out = h->stats;
-    out->paths = c.paths_done - h->ctr_base.paths_done;
+    out->paths = work_totals(h->h_work).done - h->done_base;
     // camera rays rejected against the scene box in k_logic are ray_intersect calls too (they are answered by the
     // same root-box test the traversal kernel would have done)
     out->rays_closest = (c.rays_closest - h->ctr_base.rays_closest) + (c.rays_culled - h->ctr_base.rays_culled);
@@ -966,6 +1000,8 @@ int adapt_reset_stats(adapt_handle* h) {
     int rc = drain_events(h);
     if (rc) return rc;
     CK(cudaMemcpy(&h->ctr_base, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h->h_work, h->d_work, sizeof(WorkStripe) * PT_NSTRIPE, cudaMemcpyDeviceToHost));
+    h->done_base = work_totals(h->h_work).done;
     std::memset(&h->stats, 0, sizeof(h->stats));
     return 0;
 }

@@ -136,23 +136,58 @@ struct PathPool {
 };
 enum : uint32_t { SLOT_ALIVE = 1u << 16, SLOT_SPECULAR = 1u << 17, SLOT_FINISH = 1u << 18 };
 
+// Shadow-ray queue.  Warp w of k_logic owns the entries [w * per_warp, (w + 1) * per_warp), per_warp = 32 * num_shadow_ray,
+// writes its rays compacted at the front of that region and their number into warp_count[w]: no global append counter
+// (65 536 same-address atomics per launch would cost ~2 cycles each in one L2 slice, i.e. as much as the kernel's whole
+// HBM traffic).  k_shadow walks all P * num_shadow_ray indices; an index past its region's count costs one cached 4-byte load.
 struct ShadowQueue {
     float4* o;         // (o.xyz, distance to the emitter sample)
     float4* d;         // (d.xyz, slot bits)
     float4* c;         // (payload.rgb, -)
-    uint32_t* count;
+    uint32_t* warp_count;
+    int per_warp;
     int capacity;
 };
 
-struct DeviceCounters {          // all monotonic
-    unsigned long long next_work;       // work items handed out (pixel-samples)
-    unsigned long long paths_done;      // pixel-samples finished and accumulated
+// Work distribution and completion counters are STRIPED over PT_NSTRIPE cache lines.  ncu on the first version
+// (one 64-bit `next_work` counter bumped once per warp per iteration) showed 56 % of k_logic's stall samples on
+// that atomic: 65 536 same-address atomics per launch serialise in one L2 slice (~12 cycles each = the whole kernel).
+// Stripe c hands out the work ids  ((g * PT_NSTRIPE + c) << 5) + j  for its own running index v = 32 g + j, i.e. whole
+// 32-item groups (one 4x8 pixel patch) round-robin over the stripes, so ids stay absolute and gap-free:
+//     id -> sample = id / n_pixels, pixel = pixel_list[id % n_pixels].
+// Up to `work_hi` ids are valid; stripe c may hand out limit_c(work_hi) of them (stripe_limit below).
+#define PT_NSTRIPE 64
+struct alignas(128) WorkStripe {
+    unsigned long long claimed;         // items handed out by this stripe (== its running index v)
+    unsigned long long pad0[15];
+    unsigned long long done;            // pixel-samples finished and accumulated, counted by this stripe's warps
+    unsigned long long pad1[15];
+};
+PT_HD unsigned long long stripe_limit(unsigned long long work_hi, int c) {
+    const unsigned long long per_round = (unsigned long long)PT_NSTRIPE * 32ull;
+    const unsigned long long q = work_hi / per_round, r = work_hi - q * per_round;
+    const unsigned long long lo = 32ull * (unsigned long long)c;
+    const unsigned long long extra = r > lo ? (r - lo < 32ull ? r - lo : 32ull) : 0ull;
+    return q * 32ull + extra;
+}
+PT_HD unsigned long long stripe_item_id(unsigned long long v, int c) {
+    return (((v >> 5) * (unsigned long long)PT_NSTRIPE + (unsigned long long)c) << 5) + (v & 31ull);
+}
+
+// Ray-stream cursors of the persistent trace kernels, striped the same way: stripe k serves the contiguous index range
+// [k * n / PT_NCURSOR, (k + 1) * n / PT_NCURSOR); a warp starts on its home stripe and moves on when that one runs dry.
+#define PT_NCURSOR 16
+struct alignas(128) CursorStripe { unsigned v; unsigned pad[31]; };
+struct Cursors { CursorStripe closest[PT_NCURSOR]; CursorStripe shadow[PT_NCURSOR]; };
+
+struct DeviceCounters {          // statistics, all monotonic (one RED per warp at the end of a persistent kernel)
     unsigned long long rays_closest;
     unsigned long long rays_shadow;
     unsigned long long nodes_visited;
     unsigned long long prims_tested;
     unsigned long long shadow_inline;   // shadow rays traced inside the logic kernel (two-sided corner case)
     unsigned long long rays_culled;     // camera rays finished by the scene-box test in k_logic
+    unsigned long long pad[2];
 };
 
 }  // namespace adapt

@@ -143,121 +143,26 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 }
 
 
+#define PT_NODE_DONE ((int)0x80000000)
+
 // ------------------------------------------------------------------------------------------------
-// Persistent-warp ray stream with per-lane refill.
+// Persistent-warp ray stream with per-lane refill and vote-scheduled traversal.
 //
-// Path lengths in one warp differ wildly (a camera ray that leaves the box next to a ray bouncing
-// inside the mesh), so "32 rays in, wait for the slowest" leaves most lanes idle (ncu: ~6 of 32 lanes
-// active per instruction). Here every lane keeps its own traversal state; as soon as REFILL or more
-// lanes have finished, the warp grabs that many new rays from the global cursor with ONE atomic and
-// the idle lanes start over, so the warp stays populated until the stream runs dry.
+// Path lengths in one warp differ wildly (a camera ray that leaves the box next to a ray bouncing inside the mesh),
+// so "32 rays in, wait for the slowest" leaves most lanes idle (ncu: ~6 of 32 lanes active per instruction).  Here
+// every lane keeps its own traversal state; as soon as `refill` or more lanes have finished, the warp grabs that many
+// new rays from a stream cursor with ONE atomic and the idle lanes start over, so the warp stays populated until the
+// stream runs dry.  Inside the loop one iteration gives every lane that holds an inner node ONE node step, and the
+// leaf code only runs when at least `leaf_t` lanes are parked on a leaf (or no lane has inner work left), so both
+// code paths execute with well-populated warps (ncu on the plain while-while loop: ~5 of 32 lanes in the node code).
+// The cursor is striped (pt_common.cuh: CursorStripe): one cursor for the whole stream cost 15 % of k_shadow's
+// stall samples (131 k same-address atomics per launch).
 //
 // Source concept:  unsigned size() const;  bool load(unsigned i, float3& o, float3& d, float& tmax);
 //                  void store(unsigned i, const HitRec& h);   (closest hit: the record; any hit: h.prim >= 0 means occluded)
 // ------------------------------------------------------------------------------------------------
-#define PT_NODE_DONE ((int)0x80000000)
-
-template <bool ANY_HIT, bool COUNT, int REFILL, typename Source>
-PT_D void trace_stream(const SceneView& sc, Source& src, unsigned* __restrict__ cursor, unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned n = src.size();
-    const float4* __restrict__ nodes = sc.nodes;
-    const float4* __restrict__ prims = sc.leaf_prims;
-    int stack[PT_STACK_SIZE];
-    int sp = 0, node = PT_NODE_DONE;
-    int cur = -1;                    // stream index this lane is working on
-    bool exhausted = false;          // warp-uniform: the cursor has passed the end of the stream
-    RayPre r = make_ray(mk3(0.f), mk3(0.f, 0.f, 1.f));
-    HitRec hit; hit.prim = -1; hit.t = 0.f; hit.u = hit.v = 0.f; hit.obj = 0;
-    while (true) {
-        // ---------------------------------------------------------------- refill idle lanes
-        const unsigned idle = __ballot_sync(FULL, cur < 0);
-        if (idle) {
-            if (exhausted) {
-                if (idle == FULL) break;
-            } else if (__popc(idle) >= REFILL || idle == FULL) {
-                const int n_idle = __popc(idle);
-                const int leader = __ffs(idle) - 1;
-                unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)n_idle);
-                base = __shfl_sync(FULL, base, leader);
-                if (base + (unsigned)n_idle >= n) exhausted = true;
-                if (cur < 0) {
-                    const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
-                    float3 o, d; float tmax;
-                    if (i < n && src.load(i, o, d, tmax)) {
-                        cur = (int)i;
-                        r = make_ray(o, d);
-                        hit.prim = -1; hit.t = tmax; hit.u = 0.f; hit.v = 0.f; hit.obj = 0;
-                        node = 0; sp = 0;
-                        traced++;
-                    }
-                }
-            }
-        }
-        // ---------------------------------------------------------------- traverse until enough lanes retire
-        while (true) {
-            while (node >= 0) {
-                const float4 n0 = __ldg(nodes + node * 4 + 0);
-                const float4 n1 = __ldg(nodes + node * 4 + 1);
-                const float4 n2 = __ldg(nodes + node * 4 + 2);
-                const float4 n3 = __ldg(nodes + node * 4 + 3);
-                if (COUNT) n_nodes++;
-                float tmin0, tmin1; bool h0, h1;
-                child_slabs(n0, n1, n2, r, hit.t, tmin0, tmin1, h0, h1);
-                int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    if (tmin1 < tmin0) { int tmp = c0; c0 = c1; c1 = tmp; }
-                    if (sp < PT_STACK_SIZE) stack[sp++] = c1;
-                    node = c0;
-                } else if (h0) {
-                    node = c0;
-                } else if (h1) {
-                    node = c1;
-                } else {
-                    node = sp ? stack[--sp] : PT_NODE_DONE;
-                }
-            }
-            if (node != PT_NODE_DONE) {          // leaf
-                const int code = ~node;
-                const int first = code >> 3, cnt = (code & 7) + 1;
-                bool found = false;
-                for (int k = 0; k < cnt; k++) {
-                    const float4 t0 = __ldg(prims + (first + k) * 3 + 0);
-                    const float4 t1 = __ldg(prims + (first + k) * 3 + 1);
-                    const float4 t2 = __ldg(prims + (first + k) * 3 + 2);
-                    if (COUNT) n_prims++;
-                    float t, u, v;
-                    if (prim_test(t0, t1, t2, r, hit.t, t, u, v)) {
-                        hit.t = t; hit.u = u; hit.v = v;
-                        hit.prim = __float_as_int(t2.y);
-                        hit.obj = __float_as_int(t2.z);
-                        found = true;
-                        if (ANY_HIT) break;
-                    }
-                }
-                node = (ANY_HIT && found) ? PT_NODE_DONE : (sp ? stack[--sp] : PT_NODE_DONE);
-            }
-            if (node == PT_NODE_DONE && cur >= 0) { src.store((unsigned)cur, hit); cur = -1; }
-            const unsigned act = __ballot_sync(FULL, cur >= 0);
-            if (act == 0u) break;
-            if (!exhausted && __popc(act) <= 32 - REFILL) break;
-        }
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Vote-scheduled traversal (mode 2).  ncu on the while-while loop above: the inner-node instructions
-// run with ~5 of 32 lanes, because a lane that has reached a leaf waits until the slowest lane of the
-// warp has finished descending.  Here one loop iteration gives every lane that holds an inner node ONE
-// node step, and the leaf code only runs when at least `leaf_t` lanes are parked on a leaf (or no lane
-// has inner work left), so both code paths execute with well-populated warps.  Finished lanes are
-// refilled from the stream cursor as in trace_stream.
-// ------------------------------------------------------------------------------------------------
 template <bool ANY_HIT, bool COUNT, typename Source>
-PT_D void trace_stream_vote(const SceneView& sc, Source& src, unsigned* __restrict__ cursor, const int refill, const int leaf_t,
+PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, const int refill, const int leaf_t,
                             unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
@@ -267,7 +172,11 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, unsigned* __restri
     int stack[PT_STACK_SIZE];
     int sp = 0, node = PT_NODE_DONE;
     int cur = -1;
-    bool exhausted = false;
+    // cursor stripe this warp is drawing from (warp-uniform)
+    int stripe = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % PT_NCURSOR);
+    unsigned s_lo = (unsigned)(((unsigned long long)n * (unsigned)stripe) / PT_NCURSOR);
+    unsigned s_hi = (unsigned)(((unsigned long long)n * (unsigned)(stripe + 1)) / PT_NCURSOR);
+    bool exhausted = n == 0u;        // warp-uniform: every stripe has been handed out
     RayPre r = make_ray(mk3(0.f), mk3(0.f, 0.f, 1.f));
     HitRec hit; hit.prim = -1; hit.t = 0.f; hit.u = hit.v = 0.f; hit.obj = 0;
     while (true) {
@@ -279,13 +188,32 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, unsigned* __restri
                 const int n_idle = __popc(idle);
                 const int leader = __ffs(idle) - 1;
                 unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)n_idle);
-                base = __shfl_sync(FULL, base, leader);
-                if (base + (unsigned)n_idle >= n) exhausted = true;
+                if ((int)lane == leader) base = atomicAdd(&cursors[stripe].v, (unsigned)n_idle);
+                base = __shfl_sync(FULL, base, leader) + s_lo;
+                const unsigned end = s_hi;
+                if (base + (unsigned)n_idle >= end) {
+                    // this claim drains the stripe: look at all cursors at once (one round trip) and move to the next
+                    // stripe that still has rays; a stripe seen dry stays dry, one seen live may dry before we get there
+                    bool live = false;
+                    if (lane < PT_NCURSOR) {
+                        const unsigned lo_k = (unsigned)(((unsigned long long)n * lane) / PT_NCURSOR);
+                        const unsigned hi_k = (unsigned)(((unsigned long long)n * (lane + 1u)) / PT_NCURSOR);
+                        live = (int)lane != stripe && *reinterpret_cast<volatile unsigned*>(&cursors[lane].v) < hi_k - lo_k;
+                    }
+                    const unsigned avail = __ballot_sync(FULL, live);
+                    if (avail == 0u) {
+                        exhausted = true;
+                    } else {
+                        const unsigned above = avail & ~((2u << stripe) - 1u);          // stripes after the current one first
+                        stripe = __ffs(above ? above : avail) - 1;
+                        s_lo = (unsigned)(((unsigned long long)n * (unsigned)stripe) / PT_NCURSOR);
+                        s_hi = (unsigned)(((unsigned long long)n * (unsigned)(stripe + 1)) / PT_NCURSOR);
+                    }
+                }
                 if (cur < 0) {
                     const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
                     float3 o, d; float tmax;
-                    if (i < n && src.load(i, o, d, tmax)) {
+                    if (i < end && src.load(i, o, d, tmax)) {
                         cur = (int)i;
                         r = make_ray(o, d);
                         hit.prim = -1; hit.t = tmax; hit.u = 0.f; hit.v = 0.f; hit.obj = 0;
@@ -293,6 +221,8 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, unsigned* __restri
                         traced++;
                     }
                 }
+                // stream entries can be empty (parked slots, unused queue space): keep fetching until the warp is populated
+                if (!exhausted && __popc(__ballot_sync(FULL, cur < 0)) >= refill) continue;
             }
         }
         if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)

@@ -5,10 +5,14 @@
 // only so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
 // can check and time the CUDA path against it; nothing under adapt_b200/ may link or call it.
 //
-// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and cannot run
-// here (Taichi is not installable offline), so this oracle is pinned only by (i) closed-form
-// known-answer tests (tests/test_oracle_kat.py) and (ii) an independent pure-numpy single-path
-// restatement on a handful of pixels (oracle/np_path.py).  See DESIGN.md "Oracle".
+// PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCE: Taichi cannot be installed offline, so the reference's unmodified
+// Python modules are imported on top of a pure-Python stand-in for the Taichi API (tests/golden/ti_shim/) and its
+// render kernel and BxDF functions are executed as Python (tests/golden/make_reference_golden.py, run in the development
+// container).  The resulting golden vectors -- whole renders of 10 scene / flag combinations covering every BxDF,
+// emitter type, the brute-force and the BVH intersectors, and per-function eval / pdf / sample tables -- are committed
+// under tests/golden/ and checked by tests/test_reference_golden.py (this oracle, CPU) and its -m gpu half (CUDA path).
+// Further pins: closed-form known answers (tests/test_oracle_kat.py).  What stays unpinned is Taichi's LLVM fast-math
+// rounding, which only shows as ~1e-6 noise and rare threshold "flips" (DESIGN.md "Oracle").
 //
 // Reference files followed (paths relative to the reference root, commit f590925):
 //   renderer/vanilla_renderer.py:32-120   render()                  -> render_sample()
@@ -23,7 +27,7 @@
 //
 // RNG: Taichi's per-thread xorshift is not reproducible (no seed, dynamic thread pool), so draws
 // come from a counter-keyed PCG32 stream per (seed, pixel, sample) shared bit-for-bit with the CUDA
-// kernels (adapt_b200/csrc/pt_rng.cuh); draw ORDER follows SURVEY.md Appendix A.
+// kernels (adapt_b200/csrc/pt_common.cuh); draw ORDER follows SURVEY.md Appendix A.
 //
 // All arithmetic is fp32 like the reference (ti.init(default_fp=ti.f32), render.py:69).
 
@@ -1740,6 +1744,25 @@ void oracle_bxdf_eval(const adapt_bxdf* b, const float* normal, const float* inc
     vec3 s = eval_bxdf(sc, it, vec3(incid), vec3(out));
     spec3[0] = s.x; spec3[1] = s.y; spec3[2] = s.z;
     *pdf = surface_pdf(sc, it, vec3(out), vec3(incid));
+}
+// same as oracle_bxdf_eval with separate (possibly non-unit, quirk 4) shading and geometric normals and brdf_two_sides
+void oracle_bxdf_eval2(const adapt_bxdf* b, const float* n_s, const float* n_g, const float* incid, const float* out, float world_ior,
+                       int two_sides, float* spec3, float* pdf) {
+    Scene sc; sc.world_ior = world_ior; sc.two_sides = two_sides != 0; sc.bxdfs.push_back(*b);
+    Interaction it; it.obj_id = 0; it.n_s = vec3(n_s); it.n_g = vec3(n_g); it.tex = vec3(-1.f, -1.f, -1.f);
+    vec3 s = eval_bxdf(sc, it, vec3(incid), vec3(out));
+    spec3[0] = s.x; spec3[1] = s.y; spec3[2] = s.z;
+    Interaction it2; it2.obj_id = 0; it2.n_s = vec3(n_s); it2.n_g = vec3(n_g); it2.tex = vec3(-1.f, -1.f, -1.f);
+    *pdf = surface_pdf(sc, it2, vec3(out), vec3(incid));
+}
+void oracle_bxdf_sample2(const adapt_bxdf* b, const float* n_s, const float* n_g, const float* incid, float world_ior, int two_sides,
+                         uint64_t seed, uint32_t idx, float* dir3, float* spec3, float* pdf, int32_t* is_specular) {
+    Scene sc; sc.world_ior = world_ior; sc.two_sides = two_sides != 0; sc.bxdfs.push_back(*b);
+    Interaction it; it.obj_id = 0; it.n_s = vec3(n_s); it.n_g = vec3(n_g); it.tex = vec3(-1.f, -1.f, -1.f);
+    Rng rng; rng.init(seed, idx, 0);
+    vec3 d, s; float p; bool sp;
+    sample_new_ray(sc, rng, it, vec3(incid), &d, &s, &p, &sp);
+    dir3[0] = d.x; dir3[1] = d.y; dir3[2] = d.z; spec3[0] = s.x; spec3[1] = s.y; spec3[2] = s.z; *pdf = p; *is_specular = sp ? 1 : 0;
 }
 void oracle_bxdf_sample(const adapt_bxdf* b, const float* normal, const float* incid, float world_ior, uint64_t seed, uint32_t idx,
                         float* dir3, float* spec3, float* pdf, int32_t* is_specular) {
