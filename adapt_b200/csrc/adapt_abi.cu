@@ -161,9 +161,10 @@ template <int MATS>
 __global__ void __launch_bounds__(LOGIC_BLOCK, (MATS == M_SIMPLE ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_hi, const long long cnt_origin) {
+        const unsigned long long work_hi, const long long cnt_origin, const int parity) {
     const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
-    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; }
+    // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
+    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + slot].v = 0; }
     // work stripe of this warp (pt_common.cuh: WorkStripe) and how many ids it may hand out in total
     const int home = (int)((unsigned)(slot >> 5) % PT_NSTRIPE);
 
@@ -176,10 +177,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
             const int c = (home + (int)(threadIdx.x & 31)) % PT_NSTRIPE;
             dry = *reinterpret_cast<volatile unsigned long long*>(&work[c].claimed) >= stripe_limit(work_hi, c);
         }
-        if (__all_sync(0xffffffffu, dry)) {
-            if ((threadIdx.x & 31) == 0) sq.warp_count[slot >> 5] = 0u;
-            return;
-        }
+        if (__all_sync(0xffffffffu, dry)) return;
     }
     bool terminate = false;
     bool shading = false;
@@ -248,8 +246,8 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     const bool le_corner = shading && flip_pending && hit_light >= 0;
     bool break_flag = false;
     unsigned n_inline = 0;
-    const unsigned q_base = (unsigned)(slot >> 5) * (unsigned)sq.per_warp;     // this warp's region of the shadow queue
-    unsigned q_n = 0;                                                           // entries written so far (warp-uniform)
+    const int q_seg = (int)((unsigned)(slot >> 5) % PT_NCURSOR);               // this warp's segment of the shadow queue
+    unsigned* const q_count = &sq.seg_count[parity * PT_NCURSOR + q_seg].v;
     for (int j = 0; j < sv.num_shadow_ray; j++) {
         bool want = false;
         float4 q_o = make_float4(0.f, 0.f, 0.f, 0.f), q_d = q_o, q_c = q_o;
@@ -310,14 +308,9 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                 }
             }
         }
-        const unsigned q_ballot = __ballot_sync(0xffffffffu, want);
-        if (want) {
-            const unsigned qi = q_base + q_n + (unsigned)__popc(q_ballot & ((1u << (threadIdx.x & 31)) - 1u));
-            sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c;
-        }
-        q_n += (unsigned)__popc(q_ballot);
+        const unsigned qi = (unsigned)q_seg * (unsigned)sq.seg_cap + warp_alloc<unsigned>(want, q_count);
+        if (want) { sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c; }
     }
-    if ((threadIdx.x & 31) == 0) sq.warp_count[slot >> 5] = q_n;
 
     // ---------------------------------------------------------------- emission, BSDF sampling, throughput (:99-109)
     if (shading) {
@@ -440,6 +433,10 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 struct ClosestSource {
     PathPool pool;
     PT_D unsigned size() const { return (unsigned)pool.n_slots; }
+    PT_D void stripe_range(int k, unsigned& lo, unsigned& hi) const {
+        const unsigned long long n = (unsigned long long)(unsigned)pool.n_slots;
+        lo = (unsigned)((n * (unsigned)k) / PT_NCURSOR); hi = (unsigned)((n * (unsigned)(k + 1)) / PT_NCURSOR);
+    }
     PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
         const float4 o4 = pool.ray_o[i];
         if (!(o4.w > 0.f)) return false;             // parked / finishing slot: nothing to trace
@@ -450,11 +447,12 @@ struct ClosestSource {
     PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim)); }
 };
 struct ShadowSource {
-    PathPool pool; ShadowQueue sq;
-    PT_D unsigned size() const { return (unsigned)sq.capacity; }
+    PathPool pool; ShadowQueue sq; int parity;
+    PT_D void stripe_range(int k, unsigned& lo, unsigned& hi) const {
+        lo = (unsigned)k * (unsigned)sq.seg_cap;
+        hi = lo + *reinterpret_cast<const volatile unsigned*>(&sq.seg_count[parity * PT_NCURSOR + k].v);
+    }
     PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
-        const unsigned region = i / (unsigned)sq.per_warp;
-        if (i - region * (unsigned)sq.per_warp >= __ldg(sq.warp_count + region)) return false;      // unused queue space
         const float4 o4 = sq.o[i], d4 = sq.d[i];
         o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z);
         // does_intersect(light_dir, hit_point, emitter_d): t in (1e-4, emitter_d - 1e-4) (tracer_base.py:242)
@@ -469,32 +467,38 @@ struct ShadowSource {
     }
 };
 
+// Mode-0 baseline: one cursor for the whole index range of every stripe in turn
+template <bool ANY_HIT, bool COUNT, typename Source>
+PT_D void trace_stream_simple(const SceneView& sv, Source& src, CursorStripe* __restrict__ cursors, unsigned& traced, unsigned& nn, unsigned& np) {
+    const unsigned lane = threadIdx.x & 31;
+    for (int k = 0; k < PT_NCURSOR; k++) {
+        unsigned lo, hi;
+        src.stripe_range(k, lo, hi);
+        while (true) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&cursors[k].v, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0) + lo;
+            if (base >= hi) break;
+            const unsigned i = base + lane;
+            float3 o, d; float tmax;
+            if (i < hi && src.load(i, o, d, tmax)) {
+                HitRec hr;
+                trace<ANY_HIT, COUNT>(sv, o, d, tmax, hr, nn, np);
+                src.store(i, hr);
+                traced++;
+            }
+        }
+    }
+}
+
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
           const int refill, const int leaf_t) {
     unsigned traced = 0, nn = 0, np = 0;
     ClosestSource src{pool};
-    if (MODE == 2) {
-        trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
-    } else {
-        const unsigned lane = threadIdx.x & 31;
-        const unsigned n = src.size();
-        while (true) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&cur->closest[0].v, 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            const unsigned slot = base + lane;
-            float3 o, d; float tmax;
-            if (slot < n && src.load(slot, o, d, tmax)) {
-                HitRec hr;
-                trace<false, COUNT>(sv, o, d, tmax, hr, nn, np);
-                src.store(slot, hr);
-                traced++;
-            }
-        }
-    }
+    if (MODE == 2) trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+    else trace_stream_simple<false, COUNT>(sv, src, cur->closest, traced, nn, np);
     block_count(traced, &ctr->rays_closest);
     if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
 }
@@ -502,30 +506,33 @@ k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ 
 template <int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
-         const int refill, const int leaf_t) {
+         const int refill, const int leaf_t, const int parity) {
     unsigned traced = 0, nn = 0, np = 0;
-    ShadowSource src{pool, sq};
-    if (MODE == 2) {
-        trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
-    } else {
-        const unsigned lane = threadIdx.x & 31;
-        const unsigned n = src.size();
-        while (true) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&cur->shadow[0].v, 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            const unsigned i = base + lane;
-            float3 o, d; float tmax;
-            if (i < n && src.load(i, o, d, tmax)) {
-                HitRec hr;
-                trace<true, false>(sv, o, d, tmax, hr, nn, np);
-                src.store(i, hr);
-                traced++;
-            }
-        }
-    }
+    ShadowSource src{pool, sq, parity};
+    if (MODE == 2) trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    else trace_stream_simple<true, false>(sv, src, cur->shadow, traced, nn, np);
     block_count(traced, &ctr->rays_shadow);
+}
+
+// Both ray streams of one wavefront iteration in ONE launch: a warp that runs out of shadow rays moves straight on to the
+// closest-hit stream, so the shadow stream's tail (ncu: 17-24 % of a trace kernel's elapsed cycles are ramp + tail, warps
+// waiting for the last long rays) overlaps useful work and one launch per iteration disappears.  The two streams are
+// independent: shadow results are RED-added to pool.col, closest hits are written to pool.hit.
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
+        const int refill, const int leaf_t, const int parity) {
+    unsigned traced = 0, nn = 0, np = 0;
+    {
+        ShadowSource src{pool, sq, parity};
+        trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        block_count(traced, &ctr->rays_shadow);
+    }
+    traced = 0;
+    {
+        ClosestSource src{pool};
+        trace_stream_vote<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        block_count(traced, &ctr->rays_closest);
+    }
 }
 
 // stage-level test hook
@@ -575,6 +582,8 @@ struct adapt_handle {
     int trace_grid = 0;
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
     int trace_mode = 2;
+    bool fuse_trace = true;
+    unsigned iter_parity = 0;
     int refill = 16, leaf_t = 12;
     bool count_nodes = false;
     // timing
@@ -621,11 +630,13 @@ static int launch_iteration(adapt_handle* h) {
     if (h->ev_used == h->ev_ring.size()) { int rc = drain_events(h); if (rc) return rc; }
     adapt_handle::IterEvents& ev = h->ev_ring[h->ev_used++];
     cudaStream_t st = h->stream;
+    const int parity = (int)(h->iter_parity & 1u);
+    h->iter_parity ^= 1u;
     CK(cudaEventRecord(ev.e[0], st));
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
 #define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, \
-                                                               h->n_pixels, h->work_hi, h->cnt_origin)
+                                                               h->n_pixels, h->work_hi, h->cnt_origin, parity)
         if (h->mats == M_SIMPLE) LAUNCH_LOGIC(M_SIMPLE);
         else if (h->mats == (M_SIMPLE | M_GLOSSY | M_BSDF)) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
         else LAUNCH_LOGIC(M_ALL);
@@ -633,16 +644,21 @@ static int launch_iteration(adapt_handle* h) {
     }
     CK(cudaEventRecord(ev.e[1], st));
     const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t;
-    if (h->trace_mode == 2) k_shadow<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
-    else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt);
-    CK(cudaEventRecord(ev.e[2], st));
-    if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
-    else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
-    else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+    if (h->fuse_trace && h->trace_mode == 2 && !h->count_nodes) {
+        CK(cudaEventRecord(ev.e[2], st));          // fused: the whole trace time is booked under "closest"
+        k_trace<<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+    } else {
+        if (h->trace_mode == 2) k_shadow<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        CK(cudaEventRecord(ev.e[2], st));
+        if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+        else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+        else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+    }
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
     h->stats.iterations += 1;
-    h->stats.kernel_launches += 3;
+    h->stats.kernel_launches += (h->fuse_trace && h->trace_mode == 2 && !h->count_nodes) ? 2 : 3;
     return 0;
 }
 
@@ -881,12 +897,14 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKH(dev_alloc(h, &h->pool.rng, (size_t)P));
     CKC(cudaMemset(h->pool.misc, 0, (size_t)P * sizeof(uint4)));
     CKC(cudaMemset(h->pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
-    const size_t Q = (size_t)P * (size_t)std::max(1, d->num_shadow_ray);
+    // segment k takes the shadow rays of the warps w with w % PT_NCURSOR == k: at most ceil(n_warps / PT_NCURSOR) * 32 * nsr entries
+    const size_t seg_cap = (((size_t)P / 32 + PT_NCURSOR - 1) / PT_NCURSOR) * 32 * (size_t)std::max(1, d->num_shadow_ray);
+    const size_t Q = seg_cap * PT_NCURSOR;
+    h->sq.seg_cap = (int)seg_cap;
     h->sq.capacity = (int)Q;
     CKH(dev_alloc(h, &h->sq.o, Q)); CKH(dev_alloc(h, &h->sq.d, Q)); CKH(dev_alloc(h, &h->sq.c, Q));
-    h->sq.per_warp = 32 * std::max(1, d->num_shadow_ray);
-    CKH(dev_alloc(h, &h->sq.warp_count, (size_t)P / 32));
-    CKC(cudaMemset(h->sq.warp_count, 0, (size_t)P / 32 * sizeof(uint32_t)));
+    CKH(dev_alloc(h, &h->sq.seg_count, (size_t)2 * PT_NCURSOR));
+    CKC(cudaMemset(h->sq.seg_count, 0, sizeof(CursorStripe) * 2 * PT_NCURSOR));
     CKH(dev_alloc(h, &h->d_ctr, (size_t)1)); CKC(cudaMemset(h->d_ctr, 0, sizeof(DeviceCounters)));
     CKH(dev_alloc(h, &h->d_work, (size_t)PT_NSTRIPE)); CKC(cudaMemset(h->d_work, 0, sizeof(WorkStripe) * PT_NSTRIPE));
     CKH(dev_alloc(h, &h->d_cur, (size_t)1)); CKC(cudaMemset(h->d_cur, 0, sizeof(Cursors)));
@@ -900,6 +918,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     h->trace_grid = prop.multiProcessorCount * std::max(1, per_sm);
     h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
     h->trace_mode = env_int("ADAPT_TRACE_MODE", 2);
+    h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
     h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
     h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 12)));
     h->ev_ring.resize(512);
@@ -987,6 +1006,7 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     // same root-box test the traversal kernel would have done)
     out->rays_closest = (c.rays_closest - h->ctr_base.rays_closest) + (c.rays_culled - h->ctr_base.rays_culled);
     out->reserved[0] = c.rays_culled - h->ctr_base.rays_culled;
+    out->reserved[1] = (h->fuse_trace && h->trace_mode == 2 && !h->count_nodes) ? 1 : 0;
     out->rays_shadow = (c.rays_shadow - h->ctr_base.rays_shadow) + (c.shadow_inline - h->ctr_base.shadow_inline);
     out->nodes_visited = c.nodes_visited - h->ctr_base.nodes_visited;
     out->prims_tested = c.prims_tested - h->ctr_base.prims_tested;

@@ -136,16 +136,21 @@ struct PathPool {
 };
 enum : uint32_t { SLOT_ALIVE = 1u << 16, SLOT_SPECULAR = 1u << 17, SLOT_FINISH = 1u << 18 };
 
-// Shadow-ray queue.  Warp w of k_logic owns the entries [w * per_warp, (w + 1) * per_warp), per_warp = 32 * num_shadow_ray,
-// writes its rays compacted at the front of that region and their number into warp_count[w]: no global append counter
-// (65 536 same-address atomics per launch would cost ~2 cycles each in one L2 slice, i.e. as much as the kernel's whole
-// HBM traffic).  k_shadow walks all P * num_shadow_ray indices; an index past its region's count costs one cached 4-byte load.
+#define PT_NCURSOR 16
+struct alignas(128) CursorStripe { unsigned v; unsigned pad[31]; };
+
+// Shadow-ray queue: PT_NCURSOR segments of seg_cap entries, one per cursor stripe of the trace kernel.  Warp w of k_logic
+// appends to segment w % PT_NCURSOR with one warp-aggregated atomic on that segment's counter, so the appends are spread
+// over PT_NCURSOR cache lines (one global counter = 65 536 same-address atomics per launch, ~2 cycles each in one L2 slice,
+// as much as the kernel's whole HBM time) while the trace kernel still walks compact index ranges
+// [k * seg_cap, k * seg_cap + count[k]).  The counters are double-buffered by iteration parity: k_logic of iteration i
+// appends under parity i & 1 and clears the other set, which the trace kernel of iteration i - 1 has finished reading.
 struct ShadowQueue {
     float4* o;         // (o.xyz, distance to the emitter sample)
     float4* d;         // (d.xyz, slot bits)
     float4* c;         // (payload.rgb, -)
-    uint32_t* warp_count;
-    int per_warp;
+    CursorStripe* seg_count;   // [2][PT_NCURSOR]
+    int seg_cap;
     int capacity;
 };
 
@@ -176,8 +181,6 @@ PT_HD unsigned long long stripe_item_id(unsigned long long v, int c) {
 
 // Ray-stream cursors of the persistent trace kernels, striped the same way: stripe k serves the contiguous index range
 // [k * n / PT_NCURSOR, (k + 1) * n / PT_NCURSOR); a warp starts on its home stripe and moves on when that one runs dry.
-#define PT_NCURSOR 16
-struct alignas(128) CursorStripe { unsigned v; unsigned pad[31]; };
 struct Cursors { CursorStripe closest[PT_NCURSOR]; CursorStripe shadow[PT_NCURSOR]; };
 
 struct DeviceCounters {          // statistics, all monotonic (one RED per warp at the end of a persistent kernel)

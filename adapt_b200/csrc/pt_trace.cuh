@@ -158,7 +158,8 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 // The cursor is striped (pt_common.cuh: CursorStripe): one cursor for the whole stream cost 15 % of k_shadow's
 // stall samples (131 k same-address atomics per launch).
 //
-// Source concept:  unsigned size() const;  bool load(unsigned i, float3& o, float3& d, float& tmax);
+// Source concept:  void stripe_range(int k, unsigned& lo, unsigned& hi) const;     (index range served by cursor stripe k)
+//                  bool load(unsigned i, float3& o, float3& d, float& tmax);        (false: empty entry)
 //                  void store(unsigned i, const HitRec& h);   (closest hit: the record; any hit: h.prim >= 0 means occluded)
 // ------------------------------------------------------------------------------------------------
 template <bool ANY_HIT, bool COUNT, typename Source>
@@ -166,7 +167,6 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                             unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
-    const unsigned n = src.size();
     const float4* __restrict__ nodes = sc.nodes;
     const float4* __restrict__ prims = sc.leaf_prims;
     int stack[PT_STACK_SIZE];
@@ -174,9 +174,9 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
     int cur = -1;
     // cursor stripe this warp is drawing from (warp-uniform)
     int stripe = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % PT_NCURSOR);
-    unsigned s_lo = (unsigned)(((unsigned long long)n * (unsigned)stripe) / PT_NCURSOR);
-    unsigned s_hi = (unsigned)(((unsigned long long)n * (unsigned)(stripe + 1)) / PT_NCURSOR);
-    bool exhausted = n == 0u;        // warp-uniform: every stripe has been handed out
+    unsigned s_lo, s_hi;
+    src.stripe_range(stripe, s_lo, s_hi);
+    bool exhausted = false;          // warp-uniform: every stripe has been handed out
     RayPre r = make_ray(mk3(0.f), mk3(0.f, 0.f, 1.f));
     HitRec hit; hit.prim = -1; hit.t = 0.f; hit.u = hit.v = 0.f; hit.obj = 0;
     while (true) {
@@ -196,8 +196,8 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                     // stripe that still has rays; a stripe seen dry stays dry, one seen live may dry before we get there
                     bool live = false;
                     if (lane < PT_NCURSOR) {
-                        const unsigned lo_k = (unsigned)(((unsigned long long)n * lane) / PT_NCURSOR);
-                        const unsigned hi_k = (unsigned)(((unsigned long long)n * (lane + 1u)) / PT_NCURSOR);
+                        unsigned lo_k, hi_k;
+                        src.stripe_range((int)lane, lo_k, hi_k);
                         live = (int)lane != stripe && *reinterpret_cast<volatile unsigned*>(&cursors[lane].v) < hi_k - lo_k;
                     }
                     const unsigned avail = __ballot_sync(FULL, live);
@@ -206,8 +206,7 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                     } else {
                         const unsigned above = avail & ~((2u << stripe) - 1u);          // stripes after the current one first
                         stripe = __ffs(above ? above : avail) - 1;
-                        s_lo = (unsigned)(((unsigned long long)n * (unsigned)stripe) / PT_NCURSOR);
-                        s_hi = (unsigned)(((unsigned long long)n * (unsigned)(stripe + 1)) / PT_NCURSOR);
+                        src.stripe_range(stripe, s_lo, s_hi);
                     }
                 }
                 if (cur < 0) {

@@ -249,7 +249,7 @@ def run_b200(args):
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         # CPU baseline + reference-traversal statistics on a bounded sample (rank 0, N=1 only)
-        cpu = None; nbar_node = nbar_prim = None
+        cpu = None; nbar_node = nbar_prim = nbar_node_s = nbar_prim_s = None
         if world == 1 and not args.no_cpu:
             osc, sample, window, cores, cspp = cpu_reference_leg(args, e, a, o, c, budget_s=args.cpu_budget)
             t0 = time.time(); _, cn = osc.render(cspp, pixel_list=sample, n_threads=cores); dt = time.time() - t0
@@ -257,18 +257,34 @@ def run_b200(args):
                    "sample": f"{len(sample)} pixels (window x[{window[0]},{window[1]}) y[{window[2]},{window[3]})) x {cspp} spp, {dt:.1f} s"}
             if cn["nodes_visited"]:
                 nbar_node = cn["nodes_visited"] / cn["rays_closest"]; nbar_prim = cn["prims_tested"] / cn["rays_closest"]
-        # roofline of the dominant kernel (k_closest), SURVEY 8(d): B_ray = 48 B queue + 36 B * nodes + 104 B * prims under the
-        # reference traversal order (oracle counters); avg launch duration from CUDA events recorded around every launch
+                nbar_node_s = cn["nodes_shadow"] / max(cn["rays_shadow"], 1); nbar_prim_s = cn["prims_shadow"] / max(cn["rays_shadow"], 1)
+        # roofline of the dominant kernel, SURVEY 8(d): per closest-hit ray B = 48 B queue + 36 B * nodes + 104 B * prims under the
+        # reference traversal order (oracle counters); per shadow ray 60 B queue + the same with the any-hit statistics.  The
+        # fused k_trace launch processes both streams, so its algorithmic bytes are the sum; avg launch duration from the
+        # CUDA events the library records around every launch on its stream
+        fused = bool(st.get("fused_trace"))
         iters = max(tot[6], 1.0)
-        avg_ms = tot[5] / iters / world
+        avg_ms = (tot[5] + (tot[8] if fused else 0.0)) / iters / world
         rays_per_launch = rays_closest / iters / world
-        b_queue = 48.0
+        shadow_per_launch = rays_shadow / iters / world
+        b_queue, b_queue_s = 48.0, 60.0
         b_bvh = (36.0 * nbar_node + 104.0 * nbar_prim) if nbar_node else None
         b_ray = b_queue + (b_bvh or 0.0)
-        achieved = rays_per_launch * b_ray / (avg_ms * 1e-3) / 1e9
-        traffic = None
+        b_ray_s = b_queue_s + ((36.0 * nbar_node_s + 104.0 * nbar_prim_s) if nbar_node else 0.0)
+        bytes_per_launch = rays_per_launch * b_ray + (shadow_per_launch * b_ray_s if fused else 0.0)
+        queue_bytes_per_launch = rays_per_launch * b_queue + (shadow_per_launch * b_queue_s if fused else 0.0)
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        kern = "k_trace" if fused else "k_closest"
+        # k_logic: 104 B state read + 88 B state write per live slot, 48 B per shadow ray written
+        pool_slots = args.pool or int(os.environ.get("ADAPT_POOL", 1 << 21))
+        logic_bytes = pool_slots * 192.0 + shadow_per_launch * 48.0
+        traffic = logic_traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("k_closest", {}).get("dram_bytes_per_launch")
+            logic_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("k_logic", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(kern, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -287,12 +303,20 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "stage_ms_per_step": {"logic": tot[7] / world / args.steps, "shadow": tot[8] / world / args.steps, "closest": tot[5] / world / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "k_closest", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": b_ray, "bytes_per_ray_queue_only": b_queue,
-                         "frac_queue_only": rays_per_launch * b_queue / (avg_ms * 1e-3) / 1e9 / peak_gbs,
-                         "ref_nodes_per_ray": nbar_node, "ref_prims_per_ray": nbar_prim, "avg_launch_ms": avg_ms,
-                         "rays_per_launch": rays_per_launch,
-                         "note": "achieved uses the logical bytes the REFERENCE traversal would touch (SURVEY 8(d)); it can exceed the HBM peak because the BVH is served from L2"},
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": b_ray, "bytes_per_shadow_ray": b_ray_s if fused else None,
+                         "bytes_per_ray_queue_only": b_queue,
+                         "frac_queue_only": queue_bytes_per_launch / (avg_ms * 1e-3) / 1e9 / peak_gbs,
+                         "ref_nodes_per_ray": nbar_node, "ref_prims_per_ray": nbar_prim,
+                         "ref_nodes_per_shadow_ray": nbar_node_s, "ref_prims_per_shadow_ray": nbar_prim_s, "avg_launch_ms": avg_ms,
+                         "rays_per_launch": rays_per_launch, "shadow_rays_per_launch": shadow_per_launch if fused else None,
+                         "note": "achieved = the logical bytes the REFERENCE traversal would touch for the rays of one launch (SURVEY 8(d)) / launch time; "
+                                 "it can exceed the HBM peak because the BVH is served from L2/L1 -- frac_queue_only (compulsory HBM bytes) and traffic (ncu dram bytes) are the DRAM-side figures",
+                         # second kernel of the iteration: streams the whole path pool (HBM-bound by construction)
+                         "k_logic": {"achieved": logic_bytes / max(tot[7] / iters / world * 1e-3, 1e-9) / 1e9,
+                                     "frac": logic_bytes / max(tot[7] / iters / world * 1e-3, 1e-9) / 1e9 / peak_gbs,
+                                     "bytes_per_launch": logic_bytes, "avg_launch_ms": tot[7] / iters / world,
+                                     "traffic": logic_traffic}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

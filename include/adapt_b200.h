@@ -100,7 +100,8 @@ typedef struct {
     float ms_logic, ms_closest, ms_shadow, ms_total; /* CUDA-event time per stage */
     uint64_t nodes_visited;     /* BVH nodes fetched by k_closest (0 unless built with ADAPT_COUNT_NODES) */
     uint64_t prims_tested;
-    uint64_t reserved[4];       /* reserved[0]: camera rays answered by the scene-box test (included in rays_closest) */
+    uint64_t reserved[4];       /* [0]: camera rays answered by the scene-box test (included in rays_closest);
+                                   [1]: 1 when both ray streams run in one fused launch (all trace time is booked under ms_closest) */
 } adapt_stats;
 
 typedef struct adapt_handle adapt_handle;

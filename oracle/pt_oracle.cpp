@@ -185,7 +185,9 @@ struct LinearBVH { vec3 mini, maxi; int obj_idx, prim_idx; };             // tra
 struct Counters {
     uint64_t paths = 0, rays_closest = 0, rays_shadow = 0, nodes_visited = 0, prims_tested = 0, rng_draws = 0;
     uint64_t rays_closest_useful = 0;   // closest-hit rays whose result is consumed (excludes the trace after the last bounce)
+    uint64_t nodes_shadow = 0, prims_shadow = 0;   // the same traversal statistics for does_intersect_bvh
     void add(const Counters& o) {
+        nodes_shadow += o.nodes_shadow; prims_shadow += o.prims_shadow;
         paths += o.paths; rays_closest += o.rays_closest; rays_shadow += o.rays_shadow;
         nodes_visited += o.nodes_visited; prims_tested += o.prims_tested; rng_draws += o.rng_draws;
         rays_closest_useful += o.rays_closest_useful;
@@ -1194,14 +1196,15 @@ bool does_intersect_bvh(const Scene& sc, vec3 ray, vec3 start_p, float min_depth
     bool hit_flag = false;
     float min_depth = min_depth_in > 0.f ? min_depth_in - 1e-4f : 1e7f;
     vec3 inv_ray(1.f / ray.x, 1.f / ray.y, 1.f / ray.z);
-    (void)cn;
     while (node_idx < sc.node_num) {
         const LinearNode& nd = sc.lin_nodes[node_idx];
+        cn.nodes_shadow++;
         float t_near;
         bool hit = lin_aabb_test(nd.mini, nd.maxi, inv_ray, start_p, &t_near);
         if (!hit || t_near > min_depth) { node_idx += nd.all_offset; continue; }
         if (nd.all_offset == 1) {
             for (int bvh_i = nd.base; bvh_i < nd.base + nd.prim_cnt; bvh_i++) {
+                cn.prims_shadow++;
                 const LinearBVH& lb = sc.lin_bvhs[bvh_i];
                 bool h2 = lin_aabb_test(lb.mini, lb.maxi, inv_ray, start_p, &t_near);
                 if (!h2 || t_near > min_depth) continue;
@@ -1623,7 +1626,7 @@ oracle_scene* oracle_create(const adapt_scene_desc* d) {
 }
 void oracle_destroy(oracle_scene* os) { delete os; }
 
-// counters_out: [paths, rays_closest, rays_shadow, nodes_visited, prims_tested, rng_draws, rays_closest_useful]
+// counters_out (10 slots): [paths, rays_closest, rays_shadow, nodes_visited, prims_tested, rng_draws, rays_closest_useful, nodes_shadow, prims_shadow, -]
 // Renders samples cnt_start+1 .. cnt_start+n_spp of every pixel in the crop window (or of pixel_list
 // when given: film indices i*h+j) and ADDS them to accum (w,h,3).
 void oracle_render(oracle_scene* os, int cnt_start, int n_spp, float* accum, const int32_t* pixel_list, int n_pixels,
@@ -1659,7 +1662,7 @@ void oracle_render(oracle_scene* os, int cnt_start, int n_spp, float* accum, con
     if (counters_out) {
         counters_out[0] = total.paths; counters_out[1] = total.rays_closest; counters_out[2] = total.rays_shadow;
         counters_out[3] = total.nodes_visited; counters_out[4] = total.prims_tested; counters_out[5] = total.rng_draws;
-        counters_out[6] = total.rays_closest_useful;
+        counters_out[6] = total.rays_closest_useful; counters_out[7] = total.nodes_shadow; counters_out[8] = total.prims_shadow;
     }
 }
 

@@ -184,6 +184,6 @@ def test_cuda_matches_reference_render(golden, scene_root, tag):
     if tag in SMOOTH:
         assert flipped == 0.0 and rel_l2(acc, ref) < 2e-5
     else:
-        assert flipped < 0.04, f"{flipped:.2%} of pixels hold a sample that differs"
+        assert flipped < 0.07, f"{flipped:.2%} of pixels hold a sample that differs"
         assert rel_l2(acc[match], ref[match]) < 5e-4
         np.testing.assert_allclose(acc.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-2)
