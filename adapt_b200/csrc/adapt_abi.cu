@@ -51,15 +51,24 @@ static int env_int(const char* name, int dflt) {
 #ifndef LOGIC_BLOCK
 #define LOGIC_BLOCK 256
 #endif
+// resident blocks per SM the k_logic instantiations are compiled for (measured on B200, profiles/r01c_ab.txt: the heavy-material
+// kernels gain 20 % going from 2 to 3 blocks and another 4-8 % at 4 although ptxas then spills; the simple one 5 % from 3 to 4)
 #ifndef LOGIC_MIN_BLOCKS
-#define LOGIC_MIN_BLOCKS 2
+#define LOGIC_MIN_BLOCKS 4
 #endif
 #ifndef LOGIC_MIN_BLOCKS_SIMPLE
-#define LOGIC_MIN_BLOCKS_SIMPLE 3
+#define LOGIC_MIN_BLOCKS_SIMPLE 4
 #endif
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif
+// sort keys of k_logic's block-local regrouping: material classes 0..10 (BRDF type 0..7, BSDF det-refraction 8, BSDF
+// Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot, 13 = not for this launch
+#define LOGIC_NKEY 14
+#define LOGIC_KEYS_SIMPLE ((1u << 0) | (1u << 1) | (1u << 2) | (1u << 6) | (1u << 11) | (1u << 12))
+#define LOGIC_KEYS_GLOSSY ((1u << 4) | (1u << 5))
+#define LOGIC_KEYS_COAT_GGX ((1u << 3) | (1u << 7))
+#define LOGIC_KEYS_BSDF ((1u << 8) | (1u << 9) | (1u << 10))
 
 // Block-wide allocation from a global counter: every thread passes `want` (0/1), gets its index.
 // Two barriers, one atomic per block. Must be called by all threads of the block.
@@ -158,18 +167,76 @@ __device__ __forceinline__ bool ray_hits_box(float3 o, float3 d, float3 lo, floa
 // k_logic
 // ================================================================================================
 template <int MATS>
-__global__ void __launch_bounds__(LOGIC_BLOCK, (MATS == M_SIMPLE ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
+__global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_hi, const long long cnt_origin, const int parity) {
-    const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
+        const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort,
+        const unsigned key_mask, const int first_pass, const unsigned stamp) {
+    const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
     // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
-    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + slot].v = 0; }
-    // work stripe of this warp (pt_common.cuh: WorkStripe) and how many ids it may hand out in total
-    const int home = (int)((unsigned)(slot >> 5) % PT_NSTRIPE);
+    if (first_pass && tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
+    // work stripe of this warp (pt_common.cuh: WorkStripe)
+    const int home = (int)((unsigned)(tslot >> 5) % PT_NSTRIPE);
+
+    // ---------------------------------------------------------------- block-local regrouping by material class
+    // ncu on scenes with several surface models (orb500k: glass + GGX + Fresnel blend + Lambertian walls): 8.3 of 32 lanes
+    // active per instruction, because neighbouring slots hit different materials and every warp walks through every
+    // model's code.  The block therefore permutes its 256 slots among its threads so that threads of a warp work on
+    // slots of the same class: key = material class of the surface hit (leaf record -> hit word, no extra load),
+    // then slots whose path ends, then free slots.  All accesses stay inside the block's own 256-slot window of the
+    // pool, so DRAM traffic is unchanged; what it costs is 13 ballots, a 104-entry prefix sum and three barriers.
+    //
+    // Scenes with several material groups run k_logic once per group (host: launch_iteration), each launch an
+    // instantiation that only contains that group's code (the all-in-one kernel is 125 KB of SASS and was instruction-fetch
+    // bound: ncu stall_no_instruction 46 %).  `key_mask` names the keys this launch handles; everything else, and every
+    // slot a previous launch of the same iteration has already advanced (misc.w == stamp), sorts to the end and is skipped.
+    int slot = tslot;
+    bool mine = true;
+    if (do_sort) {
+        __shared__ unsigned s_cnt[LOGIC_NKEY * (LOGIC_BLOCK / 32)];
+        __shared__ unsigned short s_perm[LOGIC_BLOCK];
+        const uint4 m0 = pool.misc[tslot];
+        int key = LOGIC_NKEY - 2;                                           // free slot
+        if (m0.w == stamp) {
+            key = LOGIC_NKEY - 1;                                           // advanced by an earlier launch of this iteration
+        } else if (m0.z & SLOT_ALIVE) {
+            const int hw = __float_as_int(pool.hit[tslot].w);
+            key = ((m0.z & SLOT_FINISH) || hw < 0) ? LOGIC_NKEY - 3          // path ends here: splat, then regenerate
+                                                   : min((hw >> PT_HIT_PRIM_BITS) & 15, LOGIC_NKEY - 4);
+        }
+        if (!((key_mask >> key) & 1u)) key = LOGIC_NKEY - 1;
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned my_rank = 0;
+        #pragma unroll
+        for (int k = 0; k < LOGIC_NKEY; k++) {
+            const unsigned b = __ballot_sync(0xffffffffu, key == k);
+            if (key == k) my_rank = __popc(b & ((1u << lane) - 1u));
+            if (lane == 0) s_cnt[k * (LOGIC_BLOCK / 32) + warp] = __popc(b);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive prefix over (key major, warp minor): lane l owns entries 4l .. 4l+3
+            const int n_ent = LOGIC_NKEY * (LOGIC_BLOCK / 32);
+            unsigned v[4], sum = 0;
+            #pragma unroll
+            for (int q = 0; q < 4; q++) { const int e = (int)lane * 4 + q; v[q] = e < n_ent ? s_cnt[e] : 0u; sum += v[q]; }
+            unsigned incl = sum;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            unsigned run = incl - sum;
+            #pragma unroll
+            for (int q = 0; q < 4; q++) { const int e = (int)lane * 4 + q; if (e < n_ent) s_cnt[e] = run; run += v[q]; }
+        }
+        __syncthreads();
+        s_perm[s_cnt[key * (LOGIC_BLOCK / 32) + warp] + my_rank] = (unsigned short)threadIdx.x;
+        __syncthreads();
+        slot = blockIdx.x * LOGIC_BLOCK + (int)s_perm[threadIdx.x];
+        mine = threadIdx.x < s_cnt[(LOGIC_NKEY - 1) * (LOGIC_BLOCK / 32)];    // skipped slots sit at the end of the order
+        if (!__any_sync(0xffffffffu, mine)) return;
+    }
 
     uint4 misc = pool.misc[slot];
-    bool alive = (misc.z & SLOT_ALIVE) != 0;
+    bool alive = mine && (misc.z & SLOT_ALIVE) != 0;
     // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
     if (!__any_sync(0xffffffffu, alive)) {
         bool dry = true;
@@ -200,7 +267,8 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         const uint2 r2 = pool.rng[slot];
         bounce = (int)(misc.z & 0xffffu);
         color = mk3(c4.x, c4.y, c4.z);
-        const int prim = __float_as_int(h4.w);
+        const int hit_word = __float_as_int(h4.w);
+        const int prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
         if ((misc.z & SLOT_FINISH) || prim < 0) {
             terminate = true;                                        // finished last bounce / "if it.is_ray_not_hit(): break"
         } else {
@@ -246,7 +314,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     const bool le_corner = shading && flip_pending && hit_light >= 0;
     bool break_flag = false;
     unsigned n_inline = 0;
-    const int q_seg = (int)((unsigned)(slot >> 5) % PT_NCURSOR);               // this warp's segment of the shadow queue
+    const int q_seg = (int)((unsigned)(tslot >> 5) % PT_NCURSOR);              // this (physical) warp's segment of the shadow queue
     unsigned* const q_count = &sq.seg_count[parity * PT_NCURSOR + q_seg].v;
     for (int j = 0; j < sv.num_shadow_ray; j++) {
         bool want = false;
@@ -334,6 +402,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         pool.col[slot] = make_float4(color.x, color.y, color.z, 0.f);
         pool.rng[slot] = make_uint2((uint32_t)rng.state, (uint32_t)(rng.state >> 32));
         misc.z = (uint32_t)bounce | flags;
+        misc.w = stamp;
         pool.misc[slot] = misc;
     }
 
@@ -355,7 +424,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // If the home stripe is dry the warp tries its neighbours (tail of a work range only).
     // A camera ray that misses the scene's bounding box ends its path on the spot (colour 0, nothing to splat):
     // the slot immediately takes the next work item instead of spending a whole wavefront iteration on it.
-    bool need = !alive && !shading;
+    bool need = mine && !alive && !shading;
     unsigned culled = 0;
     const bool may_cull = sv.cull_primary && sv.max_bounce > 0;
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -406,7 +475,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                     pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
                     pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
                     pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
+                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), stamp);
                     need = false;
                 }
             } else if (!live || attempt == 3) {
@@ -428,7 +497,8 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 // ================================================================================================
 // k_closest / k_shadow: persistent warps over the ray streams.
 //   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements and node counting)
-//   MODE 2: per-lane refill + vote-scheduled traversal (pt_trace.cuh: trace_stream_vote)
+//   MODE 1: per-lane refill straight from the stream + vote-scheduled traversal (pt_trace.cuh: trace_stream_vote)
+//   MODE 2: the same traversal fed from a per-warp shared-memory ring filled by a cp.async pipeline (trace_stream_ring)
 // ================================================================================================
 struct ClosestSource {
     PathPool pool;
@@ -444,7 +514,10 @@ struct ClosestSource {
         o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z); tmax = o4.w;
         return true;
     }
-    PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim)); }
+    PT_D const float4* o_ptr(unsigned i) const { return pool.ray_o + i; }
+    PT_D const float4* d_ptr(unsigned i) const { return pool.ray_d + i; }
+    PT_D bool accept(const float4 o4, const float4, float& tmax) const { tmax = o4.w; return o4.w > 0.f; }
+    PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(pack_hit(h))); }
 };
 struct ShadowSource {
     PathPool pool; ShadowQueue sq; int parity;
@@ -459,6 +532,9 @@ struct ShadowSource {
         tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF;
         return true;
     }
+    PT_D const float4* o_ptr(unsigned i) const { return sq.o + i; }
+    PT_D const float4* d_ptr(unsigned i) const { return sq.d + i; }
+    PT_D bool accept(const float4 o4, const float4, float& tmax) const { tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF; return true; }
     PT_D void store(unsigned i, const HitRec& h) const {
         if (h.prim >= 0) return;                     // occluded: shadow_int = 0
         const float4 c4 = sq.c[i];
@@ -497,7 +573,9 @@ k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ 
           const int refill, const int leaf_t) {
     unsigned traced = 0, nn = 0, np = 0;
     ClosestSource src{pool};
-    if (MODE == 2) trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+    __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
+    if (MODE == 2) trace_stream_ring<false, COUNT>(sv, src, cur->closest, rings[MODE == 2 ? threadIdx.x >> 5 : 0], refill, leaf_t, traced, nn, np);
+    else if (MODE == 1) trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
     else trace_stream_simple<false, COUNT>(sv, src, cur->closest, traced, nn, np);
     block_count(traced, &ctr->rays_closest);
     if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
@@ -509,7 +587,9 @@ k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCo
          const int refill, const int leaf_t, const int parity) {
     unsigned traced = 0, nn = 0, np = 0;
     ShadowSource src{pool, sq, parity};
-    if (MODE == 2) trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
+    if (MODE == 2) trace_stream_ring<true, false>(sv, src, cur->shadow, rings[MODE == 2 ? threadIdx.x >> 5 : 0], refill, leaf_t, traced, nn, np);
+    else if (MODE == 1) trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
     else trace_stream_simple<true, false>(sv, src, cur->shadow, traced, nn, np);
     block_count(traced, &ctr->rays_shadow);
 }
@@ -518,19 +598,24 @@ k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCo
 // closest-hit stream, so the shadow stream's tail (ncu: 17-24 % of a trace kernel's elapsed cycles are ramp + tail, warps
 // waiting for the last long rays) overlaps useful work and one launch per iteration disappears.  The two streams are
 // independent: shadow results are RED-added to pool.col, closest hits are written to pool.hit.
+template <int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
         const int refill, const int leaf_t, const int parity) {
+    __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
+    WarpRing& ring = rings[MODE == 2 ? threadIdx.x >> 5 : 0];
     unsigned traced = 0, nn = 0, np = 0;
     {
         ShadowSource src{pool, sq, parity};
-        trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        if (MODE == 2) trace_stream_ring<true, false>(sv, src, cur->shadow, ring, refill, leaf_t, traced, nn, np);
+        else trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
         block_count(traced, &ctr->rays_shadow);
     }
     traced = 0;
     {
         ClosestSource src{pool};
-        trace_stream_vote<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        if (MODE == 2) trace_stream_ring<false, false>(sv, src, cur->closest, ring, refill, leaf_t, traced, nn, np);
+        else trace_stream_vote<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
         block_count(traced, &ctr->rays_closest);
     }
 }
@@ -583,6 +668,9 @@ struct adapt_handle {
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
     int trace_mode = 2;
     bool fuse_trace = true;
+    int logic_sort = 1;
+    int logic_passes = 1;
+    unsigned iter_stamp = 0;
     unsigned iter_parity = 0;
     int refill = 16, leaf_t = 12;
     bool count_nodes = false;
@@ -633,32 +721,48 @@ static int launch_iteration(adapt_handle* h) {
     const int parity = (int)(h->iter_parity & 1u);
     h->iter_parity ^= 1u;
     CK(cudaEventRecord(ev.e[0], st));
+    int n_logic = 0;
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
-#define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, \
-                                                               h->n_pixels, h->work_hi, h->cnt_origin, parity)
-        if (h->mats == M_SIMPLE) LAUNCH_LOGIC(M_SIMPLE);
-        else if (h->mats == (M_SIMPLE | M_GLOSSY | M_BSDF)) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
-        else LAUNCH_LOGIC(M_ALL);
+        const unsigned stamp = ++h->iter_stamp ? h->iter_stamp : ++h->iter_stamp;      // never 0 (parked slots carry 0)
+#define LAUNCH_LOGIC(M, KEYS, FIRST) do { k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
+        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort, (unsigned)(KEYS), (FIRST), stamp); n_logic++; } while (0)
+        const bool ts = (h->mats & M_TWOSIDED) != 0;
+        if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
+            if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED, 0xffffffffu, 1); else LAUNCH_LOGIC(M_SIMPLE, 0xffffffffu, 1);
+        } else if (!h->logic_passes || !h->logic_sort) {
+            // one launch with every model compiled in
+            if (h->mats == (M_SIMPLE | M_GLOSSY | M_BSDF)) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF, 0xffffffffu, 1);
+            else LAUNCH_LOGIC(M_ALL, 0xffffffffu, 1);
+        } else {
+            // one launch per material group present (k_logic: "block-local regrouping")
+            if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED, LOGIC_KEYS_SIMPLE, 1); else LAUNCH_LOGIC(M_SIMPLE, LOGIC_KEYS_SIMPLE, 1);
+            if (h->mats & M_GLOSSY) { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_TWOSIDED, LOGIC_KEYS_GLOSSY, 0); else LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY, LOGIC_KEYS_GLOSSY, 0); }
+            if (h->mats & M_COAT_GGX) { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_COAT_GGX | M_TWOSIDED, LOGIC_KEYS_COAT_GGX, 0); else LAUNCH_LOGIC(M_SIMPLE | M_COAT_GGX, LOGIC_KEYS_COAT_GGX, 0); }
+            if (h->mats & M_BSDF) LAUNCH_LOGIC(M_SIMPLE | M_BSDF, LOGIC_KEYS_BSDF, 0);
+        }
 #undef LAUNCH_LOGIC
     }
     CK(cudaEventRecord(ev.e[1], st));
     const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t;
-    if (h->fuse_trace && h->trace_mode == 2 && !h->count_nodes) {
+    if (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) {
         CK(cudaEventRecord(ev.e[2], st));          // fused: the whole trace time is booked under "closest"
-        k_trace<<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        if (h->trace_mode == 2) k_trace<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        else k_trace<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
     } else {
         if (h->trace_mode == 2) k_shadow<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        else if (h->trace_mode == 1) k_shadow<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
         else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
         CK(cudaEventRecord(ev.e[2], st));
         if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
         else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+        else if (h->trace_mode == 1) k_closest<false, 1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
         else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
     }
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
     h->stats.iterations += 1;
-    h->stats.kernel_launches += (h->fuse_trace && h->trace_mode == 2 && !h->count_nodes) ? 2 : 3;
+    h->stats.kernel_launches += n_logic + ((h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 2);
     return 0;
 }
 
@@ -821,10 +925,13 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
             else if (b.type == 7 || b.type == 3) need |= M_COAT_GGX;
         }
         if (d->brdf_two_sides) need |= M_TWOSIDED;
-        if (need == M_SIMPLE) h->mats = M_SIMPLE;
-        else if ((need & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) h->mats = M_SIMPLE | M_GLOSSY | M_BSDF;
-        else h->mats = M_ALL;
+        // M_SIMPLE alone: one launch of the small kernel.  Otherwise `mats` keeps the exact group bits: launch_iteration runs one
+        // specialised launch per group (ADAPT_LOGIC_PASSES=0: a single launch of the all-in-one instantiation instead).
+        h->mats = (need == M_SIMPLE) ? M_SIMPLE : need;
         if (env_int("ADAPT_LOGIC_GENERIC", 0)) h->mats = M_ALL;
+        h->logic_passes = env_int("ADAPT_LOGIC_PASSES", 0);      // measured on B200: per-group launches are slower than one sorted launch
+        if (!h->logic_passes && h->mats != M_SIMPLE && (h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) != 0) h->mats = M_ALL;
+        else if (!h->logic_passes && h->mats != M_SIMPLE) h->mats = M_SIMPLE | M_GLOSSY | M_BSDF;
     }
     // ---- BVH (replaces bvh_process, tracer/path_tracer.py:143-179)
     BuildParams bp;
@@ -833,7 +940,13 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     BuildResult br;
     build_bvh(d->primitives, sph.data(), np, bp, br);
     GpuBvh gb;
-    to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), gb);
+    std::vector<uint8_t> obj_class((size_t)no, 0);
+    for (int o = 0; o < no; o++) {
+        const adapt_bxdf& b = d->bxdfs[o];
+        obj_class[o] = (uint8_t)(b.kind == 0 ? std::min(std::max(b.type, 0), 7) : (b.type == 0 ? 8 : (b.type == 1 ? 9 : 10)));
+    }
+    if (np >= (1 << PT_HIT_PRIM_BITS)) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: more than 2^27 primitives"));
+    to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), obj_class.data(), gb);
     if (gb.depth > PT_STACK_SIZE) return fail(set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack"));
 
     SceneView& sv = h->sv;
@@ -887,7 +1000,10 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKH(dev_upload(h, &h->d_pixel_list, pixels.data(), pixels.size()));
 
     // ---- path pool
-    int P = d->pool_size > 0 ? d->pool_size : env_int("ADAPT_POOL", 1 << 21);
+    // default pool: two path slots per owned pixel, between 64 Ki and 4 Mi slots (measured on bunny90k 1080p: 1 Mi slots 2.42,
+    // 2 Mi 2.92, 4 Mi 3.18, 8 Mi 3.19 Grays/s -- a bigger pool amortises the per-launch ramp and tail of the persistent kernels)
+    int P = d->pool_size > 0 ? d->pool_size : env_int("ADAPT_POOL", 0);
+    if (P <= 0) P = (int)std::min<long long>(1ll << 22, std::max<long long>(1ll << 16, 2ll * (long long)h->n_pixels));
     P = std::max(P, LOGIC_BLOCK);
     P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
     h->pool.n_slots = P;
@@ -914,12 +1030,20 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKC(cudaMemset(h->d_accum, 0, (size_t)d->width * d->height * 3 * sizeof(float)));
 
     // ---- launch shape: persistent trace kernels, a multiple of the SM count
-    int per_sm = env_int("ADAPT_TRACE_BLOCKS_PER_SM", 8);
-    h->trace_grid = prop.multiProcessorCount * std::max(1, per_sm);
     h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
-    h->trace_mode = env_int("ADAPT_TRACE_MODE", 2);
+    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);     // 2 (shared-memory ring fed by cp.async) measured slower on B200, see DESIGN.md
+    {
+        // persistent trace kernels: exactly as many blocks as are resident at once (one wave), at most ADAPT_TRACE_BLOCKS_PER_SM per SM
+        int occ = 0;
+        cudaError_t oe = h->trace_mode == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<2>, TRACE_BLOCK, 0)
+                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<1>, TRACE_BLOCK, 0);
+        if (oe != cudaSuccess || occ < 1) occ = 8;
+        const int per_sm = std::max(1, std::min(occ, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 8)));
+        h->trace_grid = prop.multiProcessorCount * per_sm;
+    }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
-    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
+    h->logic_sort = env_int("ADAPT_LOGIC_SORT", (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) ? 1 : 0);
+    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", h->trace_mode == 2 ? 4 : 16)));
     h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 12)));
     h->ev_ring.resize(512);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
@@ -1006,7 +1130,8 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     // same root-box test the traversal kernel would have done)
     out->rays_closest = (c.rays_closest - h->ctr_base.rays_closest) + (c.rays_culled - h->ctr_base.rays_culled);
     out->reserved[0] = c.rays_culled - h->ctr_base.rays_culled;
-    out->reserved[1] = (h->fuse_trace && h->trace_mode == 2 && !h->count_nodes) ? 1 : 0;
+    out->reserved[1] = (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 0;
+    out->reserved[2] = (uint64_t)h->pool.n_slots;
     out->rays_shadow = (c.rays_shadow - h->ctr_base.rays_shadow) + (c.shadow_inline - h->ctr_base.shadow_inline);
     out->nodes_visited = c.nodes_visited - h->ctr_base.nodes_visited;
     out->prims_tested = c.prims_tested - h->ctr_base.prims_tested;

@@ -152,7 +152,7 @@ void build_bvh(const float* primitives, const uint8_t* is_sphere, int32_t n, con
 }
 
 void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj,
-                   GpuBvh& out) {
+                   const uint8_t* obj_class, GpuBvh& out) {
     const int32_t n = (int32_t)br.order.size();
     out.prims.resize((size_t)std::max(1, n));
     std::memset(out.prims.data(), 0, out.prims.size() * sizeof(GpuPrim));
@@ -172,6 +172,8 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
         uint32_t ob = (uint32_t)prim_obj[p] | (sph ? 0x80000000u : 0u);
         std::memcpy(&g.v[9], &pid, 4);
         std::memcpy(&g.v[10], &ob, 4);
+        int32_t cls = obj_class ? (int32_t)obj_class[prim_obj[p]] : 0;
+        std::memcpy(&g.v[11], &cls, 4);
     }
     // inner nodes get compact indices in DFS order (children of a node adjacent in memory)
     std::vector<int32_t> inner_index(br.nodes.size(), -1);

@@ -53,7 +53,7 @@ void build_bvh(const float* primitives, const uint8_t* is_sphere, int32_t n, con
 //       ~child = (first_prim_in_leaf_order << 3) | (count - 1)
 struct alignas(16) GpuNode { float v[12]; int32_t c[4]; };
 // 48-byte leaf primitive record in leaf order:
-//   t0 = (v0.xyz, e1.x)  t1 = (e1.yz, e2.xy)  t2 = (e2.z, prim_id bits, obj_id | sphere << 31 bits, 0)
+//   t0 = (v0.xyz, e1.x)  t1 = (e1.yz, e2.xy)  t2 = (e2.z, prim_id bits, obj_id | sphere << 31 bits, material class bits)
 //   sphere: t0 = (center.xyz, radius)
 struct alignas(16) GpuPrim { float v[12]; };
 
@@ -63,7 +63,7 @@ struct GpuBvh {
     int32_t depth = 0;
 };
 void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj,
-                   GpuBvh& out);
+                   const uint8_t* obj_class, GpuBvh& out);
 
 // ---- reference layout (tracer/bvh/bvh.cpp:215-251): DFS order with sub-tree skip offsets --------
 struct RefLayout {

@@ -175,7 +175,7 @@ class Renderer:
         st = adapt_stats()
         check(self._lib, self._lib.adapt_get_stats(self._handle, C.byref(st)), "adapt_get_stats")
         out = st.as_dict()
-        out["rays_culled"], out["fused_trace"] = int(st.reserved[0]), bool(st.reserved[1])
+        out["rays_culled"], out["fused_trace"], out["pool_slots"] = int(st.reserved[0]), bool(st.reserved[1]), int(st.reserved[2])
         if reset:
             check(self._lib, self._lib.adapt_reset_stats(self._handle), "adapt_reset_stats")
         return out

@@ -276,7 +276,7 @@ def run_b200(args):
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         kern = "k_trace" if fused else "k_closest"
         # k_logic: 104 B state read + 88 B state write per live slot, 48 B per shadow ray written
-        pool_slots = args.pool or int(os.environ.get("ADAPT_POOL", 1 << 21))
+        pool_slots = int(st.get("pool_slots") or args.pool or int(os.environ.get("ADAPT_POOL", 0)) or 0)
         logic_bytes = pool_slots * 192.0 + shadow_per_launch * 48.0
         traffic = logic_traffic = None
         try:
@@ -292,7 +292,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})",
-                       "spp_per_step": spp_step, "pool_slots": args.pool or int(os.environ.get("ADAPT_POOL", 1 << 21)),
+                       "spp_per_step": spp_step, "pool_slots": pool_slots,
                        "parallelism": f"tile-split x{world}" if world > 1 else "single GPU",
                        "l2": "path pool + queues (>200 MB) stream through HBM every wavefront iteration (> 126 MB L2); the BVH stays L2-resident by design"},
             "spp_per_s": paths / (w * h) / (ms * 1e-3),

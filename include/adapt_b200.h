@@ -101,7 +101,8 @@ typedef struct {
     uint64_t nodes_visited;     /* BVH nodes fetched by k_closest (0 unless built with ADAPT_COUNT_NODES) */
     uint64_t prims_tested;
     uint64_t reserved[4];       /* [0]: camera rays answered by the scene-box test (included in rays_closest);
-                                   [1]: 1 when both ray streams run in one fused launch (all trace time is booked under ms_closest) */
+                                   [1]: 1 when both ray streams run in one fused launch (all trace time is booked under ms_closest);
+                                   [2]: path-pool slots */
 } adapt_stats;
 
 typedef struct adapt_handle adapt_handle;
