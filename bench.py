@@ -181,11 +181,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the reduce works on a copy: the renderer's own buffer keeps accumulating across steps, and summing it in place on
+    # rank 0 would count the other ranks' pixels once per step
+    fb_out = torch.empty_like(fb) if world > 1 else None
+
     def step():
         rdr.render_batch(spp_step)
         rdr.synchronize()
         if world > 1:
-            reduce_framebuffer(fb, dst=0)
+            fb_out.copy_(fb)
+            reduce_framebuffer(fb_out, dst=0)
 
     for _ in range(args.warmup):
         step()
@@ -227,8 +232,10 @@ def run_b200(args):
         rdr.load_check_point(ck)                       # H2D of the pinned accumulation buffer
         rdr.render_batch(spp_step)
         if world > 1:
-            rdr.synchronize(); reduce_framebuffer(fb, dst=0)
-        out = rdr.pixels.to_numpy()                    # D2H of the mean buffer (sync point)
+            rdr.synchronize(); fb_out.copy_(fb); reduce_framebuffer(fb_out, dst=0)
+            out = (fb_out.cpu().numpy() if rank == 0 else rdr.pixels.to_numpy())   # D2H of the reduced film (sync point)
+        else:
+            out = rdr.pixels.to_numpy()                # D2H of the mean buffer (sync point)
     ev1.record(stream)
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
