@@ -1000,10 +1000,10 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKH(dev_upload(h, &h->d_pixel_list, pixels.data(), pixels.size()));
 
     // ---- path pool
-    // default pool: two path slots per owned pixel, between 64 Ki and 4 Mi slots (measured on bunny90k 1080p: 1 Mi slots 2.42,
+    // default pool: 4 Mi slots (fewer only for films under 128 Ki owned pixels: 32 per pixel, at least 64 Ki) (measured on bunny90k 1080p: 1 Mi slots 2.42,
     // 2 Mi 2.92, 4 Mi 3.18, 8 Mi 3.19 Grays/s -- a bigger pool amortises the per-launch ramp and tail of the persistent kernels)
     int P = d->pool_size > 0 ? d->pool_size : env_int("ADAPT_POOL", 0);
-    if (P <= 0) P = (int)std::min<long long>(1ll << 22, std::max<long long>(1ll << 16, 2ll * (long long)h->n_pixels));
+    if (P <= 0) P = (int)std::min<long long>(1ll << 22, std::max<long long>(1ll << 16, 32ll * (long long)h->n_pixels));
     P = std::max(P, LOGIC_BLOCK);
     P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
     h->pool.n_slots = P;
