@@ -62,6 +62,9 @@ static int env_int(const char* name, int dflt) {
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 9
+#endif
 // sort keys of k_logic's block-local regrouping: material classes 0..10 (BRDF type 0..7, BSDF det-refraction 8, BSDF
 // Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot, 13 = not for this launch
 #define LOGIC_NKEY 14
@@ -599,7 +602,7 @@ k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCo
 // waiting for the last long rays) overlaps useful work and one launch per iteration disappears.  The two streams are
 // independent: shadow results are RED-added to pool.col, closest hits are written to pool.hit.
 template <int MODE>
-__global__ void __launch_bounds__(TRACE_BLOCK)
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
 k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
         const int refill, const int leaf_t, const int parity) {
     __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
@@ -1038,7 +1041,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         cudaError_t oe = h->trace_mode == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<2>, TRACE_BLOCK, 0)
                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<1>, TRACE_BLOCK, 0);
         if (oe != cudaSuccess || occ < 1) occ = 8;
-        const int per_sm = std::max(1, std::min(occ, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 8)));
+        const int per_sm = std::max(1, std::min(occ, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 16)));
         h->trace_grid = prop.multiProcessorCount * per_sm;
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
