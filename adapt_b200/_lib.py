@@ -66,6 +66,10 @@ class adapt_scene_desc(C.Structure):
         ("pixel_list", _ip),
         ("pool_size", C.c_int32),
         ("reserved", C.c_int32 * 7),
+        ("textures", C.c_void_p),
+        ("tex_image", _fp * 3),
+        ("tex_size", C.c_int32 * 3),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -249,6 +253,25 @@ def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed
     d.n_emitters = len(emitters)
     ps.keep["emitters"] = em
     d.emitters = C.cast(em.ctypes.data, C.POINTER(adapt_emitter))
+    # ---- textures (path_tracer.py:83-123, 262-266): per-object descriptors for the albedo / normal / bump maps + atlases ----
+    packed = prop.get("packed_textures", None)
+    d.textures = None
+    if packed is not None and any(packed.get(k) is not None for k in ("albedo", "normal", "bump")):
+        from .bxdf.texture import TEXTURE_DTYPE, Texture_np
+        tx = np.zeros((3, len(objects)), dtype=TEXTURE_DTYPE)
+        for m, key in enumerate(("albedo", "normal", "bump")):
+            img = packed.get(key)
+            for i, obj in enumerate(objects):
+                t = (obj.texture_group or {}).get(key) if img is not None else None
+                tx[m, i] = t.export() if t is not None else Texture_np.default()
+            if img is not None:
+                img = _f32(img)
+                if img.ndim != 3 or img.shape[0] != img.shape[1] or img.shape[2] != 3:
+                    raise ValueError(f"packed '{key}' texture must be a square (size, size, 3) image")
+                d.tex_image[m] = ps._ptr("tex_" + key, img, C.c_float)
+                d.tex_size[m] = img.shape[0]
+        ps.keep["textures"] = tx
+        d.textures = tx.ctypes.data
     # ---- back-end knobs ----
     d.seed = int(seed)
     d.device_id = int(device_id)

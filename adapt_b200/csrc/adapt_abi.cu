@@ -283,6 +283,29 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
             const int4 oi = __ldg(sv.obj_info + obj);
             hit_light = oi.w;
             mat = load_bxdf(sv.bxdfs + obj);
+            if (sv.textures) {
+                // get_uv_item (path_tracer.py:276-289): local (u, v) = barycentrics, or spherical coordinates on a sphere
+                // (tracer_base.py:219-221); meshes interpolate their per-vertex uv.  process_ns (:291-307) touches the PRIMARY hit
+                // only (vanilla_renderer.py:42, quirk 3); the albedo lookup happens at every bounce (:66) and replaces k_d wherever
+                // the BxDFs read it (`select(it.is_tex_invalid(), k_d, it.tex)` at every use, bxdf/brdf.py, bxdf/bsdf.py).
+                const bool t_alb = has_texture(sv, 0, obj);
+                const bool t_nrm = bounce == 0 && has_texture(sv, 1, obj), t_bmp = bounce == 0 && has_texture(sv, 2, obj);
+                if (t_alb || t_nrm || t_bmp) {
+                    float tu, tv;
+                    if (sphere) {
+                        tu = (atan2f(sf.n_g.y, sf.n_g.x) + PT_PI) * PT_INV_2PI;
+                        tv = acosf(sf.n_g.z) * PT_INV_PI;
+                    } else {
+                        const float4 q0 = __ldg(sv.prim_uv + (size_t)prim * 2), q1 = __ldg(sv.prim_uv + (size_t)prim * 2 + 1);
+                        const float bu = h4.y, bv = h4.z, bw = 1.f - bu - bv;
+                        tu = q0.z * bu + q1.x * bv + q0.x * bw;
+                        tv = q0.w * bu + q1.y * bv + q0.y * bw;
+                    }
+                    if (t_nrm) sf.n_s = to_world(sf.n_g, texture_query(sv, 1, obj, tu, tv));
+                    if (t_bmp) sf.n_s = to_world(sf.n_s, texture_query(sv, 2, obj, tu, tv));
+                    if (t_alb) mat.k_d = texture_query(sv, 0, obj, tu, tv);
+                }
+            }
             // emission MIS weight for the hit just found (vanilla_renderer.py:111-117); quirk 1/2:
             // tests is_delta of the *hit* object and the is_specular flag of the previous sample
             if (bounce > 0 && sv.use_mis) {
@@ -959,6 +982,38 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4;
     CKH(dev_upload(h, &tmp4, prim_shade.data(), prim_shade.size())); sv.prim_shade = tmp4;
     adapt_bxdf* dbx = nullptr; CKH(dev_upload(h, &dbx, d->bxdfs, (size_t)no)); sv.bxdfs = dbx;
+    // ---- textures: descriptors, per-primitive uv, RGBA-float atlases
+    sv.textures = nullptr; sv.prim_uv = nullptr;
+    for (int m = 0; m < 3; m++) { sv.tex_img[m] = nullptr; sv.tex_size[m] = 0; }
+    if (d->textures) {
+        bool any = false;
+        for (int m = 0; m < 3; m++) {
+            if (!d->tex_image[m] || d->tex_size[m] <= 0) continue;
+            const size_t sz = (size_t)d->tex_size[m];
+            for (int o = 0; o < no; o++) {
+                const adapt_texture& t = d->textures[(size_t)m * no + o];
+                if (t.type <= -255) continue;
+                if (t.type != 0) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: only image textures have a lookup (bxdf/texture.py:114)"));
+                if (t.w < 2 || t.h < 2 || t.off_x < 0 || t.off_y < 0 || (size_t)(t.off_x + t.w) > sz || (size_t)(t.off_y + t.h) > sz)
+                    return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: texture rectangle outside its atlas (or smaller than 2x2)"));
+            }
+            std::vector<float4> rgba(sz * sz);
+            for (size_t k = 0; k < sz * sz; k++) rgba[k] = make_float4(d->tex_image[m][k * 3], d->tex_image[m][k * 3 + 1], d->tex_image[m][k * 3 + 2], 0.f);
+            float4* dimg = nullptr; CKH(dev_upload(h, &dimg, rgba.data(), rgba.size()));
+            sv.tex_img[m] = dimg; sv.tex_size[m] = (int)sz;
+            any = true;
+        }
+        if (any) {
+            adapt_texture* dtx = nullptr; CKH(dev_upload(h, &dtx, d->textures, (size_t)3 * no)); sv.textures = dtx;
+            std::vector<float4> puv((size_t)np * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (d->uvs) for (int k = 0; k < np; k++) {
+                const float* q = d->uvs + (size_t)k * 6;
+                puv[(size_t)k * 2] = make_float4(q[0], q[1], q[2], q[3]);
+                puv[(size_t)k * 2 + 1] = make_float4(q[4], q[5], 0.f, 0.f);
+            }
+            float4* duv = nullptr; CKH(dev_upload(h, &duv, puv.data(), puv.size())); sv.prim_uv = duv;
+        }
+    }
     adapt_emitter* dem = nullptr; CKH(dev_upload(h, &dem, d->emitters, (size_t)d->n_emitters)); sv.emitters = dem;
     int4* doi = nullptr; CKH(dev_upload(h, &doi, obj_info.data(), obj_info.size())); sv.obj_info = doi;
     sv.n_objects = no; sv.n_emitters = d->n_emitters; sv.n_prims = np;

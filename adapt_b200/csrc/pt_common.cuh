@@ -120,6 +120,12 @@ struct SceneView {
     uint64_t seed;
     float3 world_lo, world_hi;   // padded scene bounds
     int cull_primary;
+    // textures (NULL / 0 when the scene has none): [3][n_objects] descriptors (albedo, normal, bump), per-primitive vertex
+    // uv as 2 x float4 (uv0, uv1 | uv2, -, -) and one RGBA-float atlas per map kind
+    const adapt_texture* textures;
+    const float4* prim_uv;
+    const float4* tex_img[3];
+    int tex_size[3];
 };
 
 // Path pool (SoA, one entry per slot) and queues. All float4 / uint4 so every access is one 128-bit

@@ -476,6 +476,30 @@ PT_D void brdf_sample(const Bxdf& m, const Surf& s, float3 in, Rng& g, float3& d
     if (!(dot(dir, s.n_g) > 0.f)) spec = mk3(0.f);                      // :558-559
 }
 
+// ---------------------------------------------------------------- textures (bxdf/texture.py:114-139, tracer/path_tracer.py:276-307)
+PT_D float floor_mod_f(float a, float b) { return a - b * floorf(a / b); }                 // taichi float __mod__
+PT_D float3 mix3(float3 x, float3 y, float a) { return x * (1.f - a) + y * a; }            // taichi.math.mix
+// Texture.query: wrap into the rectangle, bilinear blend of the four texels around (u, v)
+__device__ __noinline__ float3 texture_query(const SceneView& sv, int map, int obj, float u, float v) {
+    const float4* q = reinterpret_cast<const float4*>(sv.textures + (size_t)map * sv.n_objects + obj);
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    const int off_x = __float_as_int(a.y), off_y = __float_as_int(a.z), w = __float_as_int(a.w), h = __float_as_int(b.x);
+    const float scaled_u = floor_mod_f(u * b.y * (float)w, (float)w - 1.f);
+    const float scaled_v = floor_mod_f(v * b.z * (float)h, (float)h - 1.f);
+    const float floor_u = floorf(scaled_u), floor_v = floorf(scaled_v);
+    const float ratio_u = scaled_u - floor_u, ratio_v = scaled_v - floor_v;
+    const int iu = (int)(floor_u + (float)off_x), iv = (int)(floor_v + (float)off_y);
+    const float4* img = sv.tex_img[map];
+    const size_t size = (size_t)sv.tex_size[map];
+    const float4 ff = __ldg(img + (size_t)iv * size + iu), cf = __ldg(img + (size_t)iv * size + iu + 1);
+    const float4 fc = __ldg(img + (size_t)(iv + 1) * size + iu), cc = __ldg(img + (size_t)(iv + 1) * size + iu + 1);
+    return mix3(mix3(mk3(ff.x, ff.y, ff.z), mk3(cf.x, cf.y, cf.z), ratio_u), mix3(mk3(fc.x, fc.y, fc.z), mk3(cc.x, cc.y, cc.z), ratio_u), ratio_v);
+}
+// get_uv_item: does object `obj` carry a map of this kind?  (type > -255)
+PT_D bool has_texture(const SceneView& sv, int map, int obj) {
+    return sv.tex_img[map] != nullptr && __ldg(reinterpret_cast<const int*>(sv.textures + (size_t)map * sv.n_objects + obj)) > -255;
+}
+
 // ---------------------------------------------------------------- BSDF models (bxdf/bsdf.py), mode = TRANSPORT_UNI
 PT_D float3 bsdf_eval(const Bxdf& m, const Surf& s, float3 in, float3 out, float world_ior) {     // eval_surf :243-250
     if (m.type != 0 && m.type != 1) return mk3(0.f);

@@ -3,8 +3,8 @@
 Same schema, same 4-tuple and same error behaviour as the reference ``parsers/xml_parser.py``
 (scene_parsing :246-289, parse_wavefront :93-176, parse_global_sensor :225-244, parse_emitters
 :66-88, parse_bxdf :178-194, update_emitter_config :56-64), re-hosted without taichi / pywavefront.
-Textures and volumes are outside the `pt` hot path scope of this round; a scene that
-declares them raises ``NotImplementedError`` instead of silently rendering something else.
+Textures (albedo / normal / bump atlases, parse_texture :203-221) are parsed like the reference does; volumes are outside
+the `pt` hot path.
 """
 from __future__ import annotations
 
@@ -17,6 +17,7 @@ import numpy as np
 from ..bxdf import brdf as _brdf_mod
 from ..bxdf.brdf import BRDF_np
 from ..bxdf.bsdf import BSDF_np
+from ..bxdf.texture import Texture_np
 from ..emitters.area import AreaSource
 from ..emitters.collimated import CollimatedSource
 from ..emitters.point import PointSource
@@ -24,6 +25,7 @@ from ..emitters.spot import SpotSource
 from ..utils.tools import CONSOLE, timing
 from .general_parser import get, parse_sphere_element, transform_parse
 from .obj_desc import ObjDescriptor
+from .texture_packing import image_packer
 from .obj_loader import SPHERE, TRIANGLE_MESH, apply_transform, calculate_surface_area, extract_obj_info
 from .world import World_np
 
@@ -67,7 +69,7 @@ def parse_emitters(em_elem: list):
     return sources, source_id_dict
 
 
-def parse_wavefront(directory: str, obj_list: List[xet.Element], bsdf_dict: dict, emitter_dict: dict):
+def parse_wavefront(directory: str, obj_list: List[xet.Element], bsdf_dict: dict, emitter_dict: dict, texture_dict: dict = None):
     all_objs, all_prims, all_uvs, all_normals, all_v_norms = [], [], [], [], []
     indices = []
     attached_area_dict = {}
@@ -100,7 +102,18 @@ def parse_wavefront(directory: str, obj_list: List[xet.Element], bsdf_dict: dict
                 emit_ref_id = emitter_dict[ref_id]
                 attached_area_dict[emit_ref_id] = calculate_surface_area(meshes, obj_type)
             elif ref_type == "texture":
-                raise NotImplementedError("Textures are not on the `pt` hot path built so far (SURVEY 8(f) rank 1).")
+                ref_tag = ref_child.get("tag", None)
+                if ref_tag is None:
+                    ref_tag = "albedo"
+                    CONSOLE.log(f"[yellow]Warning: BXDF[/yellow] Texture ref_id {ref_id} has no tag. Set default as 'albedo'.")
+                elif ref_tag not in texture_group:
+                    ref_tag = "albedo"
+                    CONSOLE.log(f"[yellow]Warning: BXDF[/yellow] Texture ref_tag {ref_tag} not supported. Set default as 'albedo'.")
+                if texture_dict is None or texture_dict.get(ref_tag) is None or ref_id not in texture_dict[ref_tag]:
+                    raise KeyError(f"Texture id '{ref_id}' does not have tag '{ref_tag}' mapping, check if it is from other groups.")
+                texture_group[ref_tag] = texture_dict[ref_tag][ref_id]
+                if texture_group[ref_tag].mode == Texture_np.MODE_CHECKER:
+                    raise NotImplementedError("checkerboard textures have no lookup in the reference (bxdf/texture.py:102 TODO)")
         if bsdf_item is None:
             raise ValueError("Object should be attached with a BSDF for now since no default one implemented yet.")
         prim_num = meshes.shape[0]
@@ -134,6 +147,24 @@ def parse_bxdf(bxdf_list: List[xet.Element]):
             CONSOLE.log(f"[yellow]Warning: BXDF[/yellow] {bxdf_id} re-defined in XML file. Overwriting the existing BXDF.")
         results[bxdf_id] = bxdf
     return results
+
+
+def parse_texture(texture_list: List[xet.Element], directory: str = ""):
+    """Texture nodes -> ({tag: atlas image or None}, {tag: {id: Texture_np} or None}) (reference xml_parser.py:203-221)."""
+    if len(texture_list) == 0:
+        return None, None
+    textures = {"albedo": [], "normal": [], "bump": [], "roughness": []}
+    for texture in texture_list:
+        textures[texture.get("tag", "albedo")].append(Texture_np(texture, directory=directory))
+    packed_textures, packed_imgs = {}, {}
+    for key, value in textures.items():
+        if len(value) == 0:
+            tex_img, tex_info = None, None
+        else:
+            tex_img, tex_info = image_packer(value)
+        packed_imgs[key] = tex_img
+        packed_textures[key] = tex_info
+    return packed_imgs, packed_textures
 
 
 def parse_world(world_elem: xet.Element):
@@ -173,18 +204,17 @@ def scene_parsing(directory: str, file: str):
     world_node = root_node.find("world")
     volume_node = root_node.findall("volume")
     assert sensor_node is not None
-    if len(texture_nodes) > 0:
-        raise NotImplementedError("Textures are not on the `pt` hot path built so far (SURVEY 8(f) rank 1).")
+    teximgs, textures = parse_texture(texture_nodes, directory)
     # the reference flips microfacet support with a source-level flag (bxdf/brdf.py:8); here a sensor key
     for elem in sensor_node:
         if elem.tag == "boolean" and elem.get("name") == "enable_microfacet":
             _brdf_mod.set_enable_microfacet(elem.get("value", "false").lower() == "true")
     emitter_configs, emitter_dict = parse_emitters(emitter_nodes)
     bsdf_dict = parse_bxdf(bxdf_nodes)
-    array_info, all_objs, area_lut, has_vertex_normal = parse_wavefront(directory, shape_nodes, bsdf_dict, emitter_dict)
+    array_info, all_objs, area_lut, has_vertex_normal = parse_wavefront(directory, shape_nodes, bsdf_dict, emitter_dict, textures)
     configs = parse_global_sensor(sensor_node)
     configs["world"] = parse_world(world_node)
-    configs["packed_textures"] = None
+    configs["packed_textures"] = teximgs
     configs["has_vertex_normal"] = has_vertex_normal
     configs["volume"] = volume_node[:1]
     emitter_configs = update_emitter_config(emitter_configs, area_lut)

@@ -54,6 +54,15 @@ typedef struct {
     float inv_area, r, emit_time, _pad;
 } adapt_emitter;
 
+/* Mirrors reference `Texture` (bxdf/texture.py:103-112): one rectangle of a packed atlas. 32 bytes. */
+typedef struct {
+    int32_t type;        /* 0 image, 1 checkerboard (no lookup in the reference), -255 none */
+    int32_t off_x, off_y;/* rectangle origin in the atlas                                    */
+    int32_t w, h;        /* rectangle size                                                   */
+    float scale_u, scale_v;
+    int32_t _pad;
+} adapt_texture;
+
 /* Everything PathTracer.__init__ receives, flattened. */
 typedef struct {
     /* geometry: array_info of parsers/xml_parser.py:171-175 */
@@ -62,7 +71,7 @@ typedef struct {
     const float*   primitives;  /* [n_prims*9]  (N,3,3): triangle vertices; sphere = (center, (r,r,r), 0) */
     const float*   n_g;         /* [n_prims*3]  geometric normals                                          */
     const float*   n_s;         /* [n_prims*9]  per-vertex shading normals, or NULL (has_vertex_normal=0)  */
-    const float*   uvs;         /* [n_prims*6]  per-vertex uv, or NULL (unused until textures land)        */
+    const float*   uvs;         /* [n_prims*6]  per-vertex uv (only read for objects that carry a texture), or NULL */
     const int32_t* obj_info;    /* [n_objects*3] (first_prim, n_prims, type 0 mesh / 1 sphere), tracer/path_tracer.py:252-256 */
     const float*   obj_aabb;    /* [n_objects*6] (min, max) per object, parsers/obj_desc.py:9-25           */
     const int32_t* emitter_id;  /* [n_objects]   attached emitter index or -1                              */
@@ -87,6 +96,11 @@ typedef struct {
     const int32_t* pixel_list;  /* [n_pixels] film indices i*height + j owned by this handle, or NULL        */
     int32_t pool_size;          /* path slots kept in flight, 0 = auto                                       */
     int32_t reserved[7];
+    /* textures: tracer/path_tracer.py:83-123 (albedo_map / normal_map / bump_map + their packed images). All optional. */
+    const adapt_texture* textures;  /* [3][n_objects]: albedo, normal, bump descriptor per object, or NULL (no textures) */
+    const float* tex_image[3];      /* packed atlas per map kind, [tex_size][tex_size][3] floats (row = v, column = u), or NULL */
+    int32_t tex_size[3];            /* atlas edge length per map kind                                                      */
+    int32_t reserved2;
 } adapt_scene_desc;
 
 /* Counters since create (or the last adapt_reset_stats). Ray counts are the calls the reference

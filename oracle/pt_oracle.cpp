@@ -218,6 +218,11 @@ struct Scene {
     std::vector<LinearNode> lin_nodes;
     std::vector<LinearBVH> lin_bvhs;
     int node_num = 0;
+    // textures (tracer/path_tracer.py:83-123): per-object descriptors of the albedo / normal / bump maps + packed images
+    std::vector<float> uvs;                         // [n_prims*6] per-vertex uv (tracer_base.py:83)
+    std::vector<adapt_texture> textures[3];         // [n_objects] each; empty = this kind of map is absent (has_*_map False)
+    std::vector<float> tex_img[3];                  // [size][size][3]
+    int tex_size[3] = {0, 0, 0};
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1302,6 +1307,55 @@ inline vec3 pix2ray(const Scene& sc, Rng& rng, int i, int j, int cnt) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// bxdf/texture.py:114-139 Texture.query, tracer/path_tracer.py:276-307 get_uv_item / process_ns
+// ------------------------------------------------------------------------------------------------
+inline float floor_mod_f(float a, float b) { return a - b * std::floor(a / b); }        // taichi float __mod__
+inline vec3 texel(const Scene& sc, int map, int row, int col) {
+    const float* p = sc.tex_img[map].data() + ((size_t)row * sc.tex_size[map] + col) * 3;
+    return vec3(p[0], p[1], p[2]);
+}
+inline vec3 mix3(vec3 x, vec3 y, float a) { return x * (1.f - a) + y * a; }                 // taichi.math.mix
+inline vec3 texture_query(const Scene& sc, int map, const adapt_texture& t, float u, float v) {
+    float scaled_u = floor_mod_f(u * t.scale_u * (float)t.w, (float)t.w - 1.f);
+    float scaled_v = floor_mod_f(v * t.scale_v * (float)t.h, (float)t.h - 1.f);
+    float floor_u = std::floor(scaled_u), floor_v = std::floor(scaled_v);
+    float ratio_u = scaled_u - floor_u, ratio_v = scaled_v - floor_v;
+    int floor_ui = (int)(floor_u + (float)t.off_x), floor_vi = (int)(floor_v + (float)t.off_y);
+    int ceil_ui = floor_ui + 1, ceil_vi = floor_vi + 1;
+    vec3 q_ff = texel(sc, map, floor_vi, floor_ui), q_cf = texel(sc, map, floor_vi, ceil_ui);
+    vec3 q_fc = texel(sc, map, ceil_vi, floor_ui), q_cc = texel(sc, map, ceil_vi, ceil_ui);
+    return mix3(mix3(q_ff, q_cf, ratio_u), mix3(q_fc, q_cc, ratio_u), ratio_v);
+}
+// get_uv_item :276-289 -- INVALID (-1,-1,-1) unless the object carries a texture of this kind
+inline vec3 get_uv_item(const Scene& sc, int map, const Interaction& it, bool* valid) {
+    *valid = false;
+    vec3 tex_value(-1.f, -1.f, -1.f);
+    if (it.obj_id >= 0 && !sc.textures[map].empty() && sc.textures[map][it.obj_id].type > -255) {
+        float u = it.u, v = it.v;                 // local u, v (barycentrics; spherical coordinates on a sphere)
+        if (sc.obj_info[it.obj_id][2] == 0) {
+            const float* q = sc.uvs.data() + (size_t)it.prim_id * 6;
+            float gu = q[2] * u + q[4] * v + q[0] * (1.f - u - v);
+            float gv = q[3] * u + q[5] * v + q[1] * (1.f - u - v);
+            u = gu; v = gv;
+        }
+        tex_value = texture_query(sc, map, sc.textures[map][it.obj_id], u, v);
+        *valid = true;
+    }
+    return tex_value;
+}
+// process_ns :291-307 -- normal map replaces the shading normal, bump map tilts it (primary hit only, vanilla_renderer.py:42)
+inline void process_ns(const Scene& sc, Interaction& it) {
+    if (!sc.textures[1].empty()) {
+        bool ok; vec3 normal = get_uv_item(sc, 1, it, &ok);
+        if (ok) it.n_s = rotation_between(vec3(0.f, 1.f, 0.f), it.n_g) * normal;
+    }
+    if (!sc.textures[2].empty()) {
+        bool ok; vec3 delta_n = get_uv_item(sc, 2, it, &ok);
+        if (ok) it.n_s = delocalize_rotate(it.n_s, delta_n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // renderer/vanilla_renderer.py:36-120 -- one pixel-sample
 // ------------------------------------------------------------------------------------------------
 static thread_local bool g_dbg = false;
@@ -1312,7 +1366,7 @@ vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
     vec3 ray_o = sc.cam_t;
     Interaction it = ray_intersect(sc, ray_d, ray_o, cn);
     cn.rays_closest_useful++;
-    // process_ns: no normal / bump maps on this path (path_tracer.py:291-307 is a static no-op)
+    process_ns(sc, it);                                       // (possibly) normal map / bump map, primary hit only
     int hit_light = sc.emitter_id[std::max(it.obj_id, 0)];
     vec3 color(0.f), contribution(1.f);
     float emission_weight = 1.f;
@@ -1331,7 +1385,7 @@ vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
         float direct_pdf = 1.f, emitter_pdf = 1.f;
         bool break_flag = false;
         vec3 shadow_int(0.f), direct_int(0.f), direct_spec(1.f);
-        it.tex = vec3(-1.f, -1.f, -1.f);      // get_uv_item without textures: INVALID (path_tracer.py:279)
+        { bool tex_valid; it.tex = get_uv_item(sc, 0, it, &tex_valid); }      // :66
         for (int _j = 0; _j < sc.num_shadow_ray; _j++) {
             bool emitter_valid;
             int ei = sample_light(sc, rng, hit_light, &emitter_pdf, &emitter_valid);
@@ -1603,6 +1657,15 @@ oracle_scene* oracle_create(const adapt_scene_desc* d) {
         }
     }
     sc.src.assign(d->emitters, d->emitters + sc.n_emitters);
+    if (d->textures) {
+        if (d->uvs) sc.uvs.assign(d->uvs, d->uvs + (size_t)sc.n_prims * 6); else sc.uvs.assign((size_t)sc.n_prims * 6, 0.f);
+        for (int m = 0; m < 3; m++) {
+            if (!d->tex_image[m] || d->tex_size[m] <= 0) continue;
+            sc.textures[m].assign(d->textures + (size_t)m * sc.n_objects, d->textures + (size_t)(m + 1) * sc.n_objects);
+            sc.tex_size[m] = d->tex_size[m];
+            sc.tex_img[m].assign(d->tex_image[m], d->tex_image[m] + (size_t)d->tex_size[m] * d->tex_size[m] * 3);
+        }
+    }
     sc.w = d->width; sc.h = d->height;
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) sc.cam_r.m[r][c] = d->cam_r[r * 3 + c];
     sc.cam_t = vec3(d->cam_t);

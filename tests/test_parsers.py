@@ -102,7 +102,7 @@ def test_error_behaviour(tmp_path, scene_root):
     src = open(os.path.join(scene_root, "cbox", "cbox.xml")).read()
     tex = tmp_path / "tex.xml"
     tex.write_text(src.replace("</scene>", '<texture id="t" tag="albedo"/></scene>'))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AttributeError):          # image texture without a <string> child: same failure as bxdf/texture.py:59
         scene_parsing(str(tmp_path), "tex.xml")
 
 
@@ -128,3 +128,60 @@ def test_tile_partition_covers_film():
     win = tile_partition(64, 64, 0, 1, window=(8, 24, 16, 48))
     ii, jj = win // 64, win % 64
     assert ii.min() == 8 and ii.max() == 23 and jj.min() == 16 and jj.max() == 47 and len(win) == 16 * 32
+
+
+# ------------------------------------------------------------------------------------------------ textures
+def test_texture_scene_parses_and_packs(scene_root):
+    from conftest import load_scene
+    e, a, o, c = load_scene(scene_root, "test", "textured.xml")
+    packed = c["packed_textures"]
+    assert set(packed) == {"albedo", "normal", "bump", "roughness"} and packed["roughness"] is None
+    for key in ("albedo", "normal", "bump"):
+        img = packed[key]
+        assert img.dtype == np.float32 and img.shape[0] == img.shape[1] and img.shape[2] == 3
+    floor = o[1].texture_group["albedo"]
+    assert (floor.w, floor.h, floor.scale_u, floor.scale_v) == (48, 32, 2.0, 1.5)
+    # the rectangle in the atlas holds the image (RGB, /255), bump maps with G and B swapped (bxdf/texture.py:77-79)
+    import cv2
+    raw = cv2.cvtColor(cv2.imread(os.path.join(scene_root, "textures", "tex_albedo.png")), cv2.COLOR_BGR2RGB).astype(np.float32) / 255.0
+    np.testing.assert_array_equal(packed["albedo"][floor.off_y:floor.off_y + 32, floor.off_x:floor.off_x + 48], raw)
+    bump = o[7].texture_group["bump"]
+    rawb = cv2.cvtColor(cv2.imread(os.path.join(scene_root, "textures", "tex_bump.png")), cv2.COLOR_BGR2RGB).astype(np.float32) / 255.0
+    np.testing.assert_array_equal(packed["bump"][bump.off_y:bump.off_y + bump.h, bump.off_x:bump.off_x + bump.w], rawb[..., [0, 2, 1]])
+    # mesh uv coordinates reach array_info; objects without vt get zeros
+    assert a["uvs"].shape == (a["primitives"].shape[0], 3, 2) and a["uvs"][2:4].any() and not a["uvs"][4:6].any()
+
+
+def test_shelf_packer_places_without_overlap():
+    from adapt_b200.parsers.texture_packing import shelf_pack
+    rects = [(300, 200, 0), (500, 120, 1), (64, 64, 2), (400, 400, 3), (100, 700, 4)]
+    placed = shelf_pack(rects, 1024)
+    assert placed is not None and set(placed) == {0, 1, 2, 3, 4}
+    occ = np.zeros((1024, 1024), np.int32)
+    for w, h, rid in rects:
+        x, y = placed[rid]
+        assert x >= 0 and y >= 0 and x + w <= 1024 and y + h <= 1024
+        occ[y:y + h, x:x + w] += 1
+    assert occ.max() == 1
+    assert shelf_pack([(800, 800, 0), (800, 800, 1)], 1024) is None and shelf_pack([(2000, 10, 0)], 1024) is None
+
+
+def test_texture_errors(scene_root, tmp_path):
+    import shutil
+    from adapt_b200.parsers.xml_parser import scene_parsing
+    src = open(os.path.join(scene_root, "test", "textured.xml")).read()
+    d = tmp_path / "test"
+    d.mkdir()
+    shutil.copytree(os.path.join(scene_root, "meshes"), tmp_path / "meshes", ignore=shutil.ignore_patterns("synth"))
+    shutil.copytree(os.path.join(scene_root, "textures"), tmp_path / "textures")
+    (d / "missing.xml").write_text(src.replace("../textures/tex_bump.png", "../textures/nope.png"))
+    with pytest.raises(ValueError):
+        scene_parsing(str(d), "missing.xml")
+    (d / "badref.xml").write_text(src.replace('<ref type="texture" id="dents" tag="bump"/>', '<ref type="texture" id="dents" tag="normal"/>', 1))
+    with pytest.raises(KeyError):
+        scene_parsing(str(d), "badref.xml")
+    checker = '<texture id="chk" type="checkerboard" tag="albedo"><rgb name="c1" value="#000000"/><rgb name="c2" value="#FFFFFF"/></texture>'
+    (d / "checker.xml").write_text(src.replace("<emitter type=\"area\"", checker + "<emitter type=\"area\"", 1)
+                                   .replace('<ref type="texture" id="paint2" tag="albedo"/>', '<ref type="texture" id="chk" tag="albedo"/>', 1))
+    with pytest.raises(NotImplementedError):
+        scene_parsing(str(d), "checker.xml")

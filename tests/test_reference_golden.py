@@ -30,6 +30,7 @@ SCENES = {
     "complex": ("cbox", "complex.xml"), "balls_mono": ("csphere", "balls-mono.xml"), "mix_balls": ("csphere", "mix-balls.xml"),
     "balls_multi": ("csphere", "balls-multi.xml"), "allbxdf": ("test", "allbxdf.xml"),
     "allbxdf_nomis_norr": ("test", "allbxdf.xml"), "allbxdf_bvh": ("test", "allbxdf.xml"),
+    "textured": ("test", "textured.xml"),          # albedo / normal / bump maps on meshes and spheres
 }
 # scenes made of Lambertian planes and boxes only have no chaotic samples: exact agreement is demanded there
 SMOOTH = {"cbox", "cbox_b8_uniform", "cbox_point"}
@@ -78,6 +79,16 @@ def test_scene_ingestion_matches_reference_parsers(golden, scene_root, tag):
     np.testing.assert_allclose(np.asarray(ps.desc.cam_r[:9], np.float32).reshape(3, 3), g[tag + "/cam_r"], atol=1e-6)
     np.testing.assert_allclose(np.asarray(ps.desc.cam_t[:3], np.float32), g[tag + "/cam_t"], atol=1e-6)
     assert abs(1.0 / ps.desc.inv_focal - float(g[tag + "/focal"][0])) < 1e-3
+    if tag + "/uvs" in g.files:
+        np.testing.assert_allclose(a["uvs"], g[tag + "/uvs"], atol=1e-7)
+    for key in ("albedo", "normal", "bump"):
+        if tag + "/tex_" + key in g.files:       # (has texture, w, h, scale_u, scale_v) per object; atlas offsets are the packer's business
+            rows = []
+            for ob in o:
+                t = ob.texture_group.get(key)
+                rows.append([0, 0, 0, 1, 1] if t is None else [1, t.w, t.h, t.scale_u, t.scale_v])
+            np.testing.assert_allclose(np.asarray(rows, np.float32), g[tag + "/tex_" + key])
+            assert c["packed_textures"][key] is not None and ps.desc.tex_size[("albedo", "normal", "bump").index(key)] > 0
 
 
 @pytest.mark.parametrize("tag", sorted(SCENES))
