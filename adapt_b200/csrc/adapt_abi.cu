@@ -170,7 +170,7 @@ __device__ __forceinline__ bool ray_hits_box(float3 o, float3 d, float3 lo, floa
 // k_logic
 // ================================================================================================
 template <int MATS>
-__global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
+__global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
         const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort,
@@ -283,7 +283,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
             const int4 oi = __ldg(sv.obj_info + obj);
             hit_light = oi.w;
             mat = load_bxdf(sv.bxdfs + obj);
-            if (sv.textures) {
+            if ((MATS & M_TEXTURED) && sv.textures) {
                 // get_uv_item (path_tracer.py:276-289): local (u, v) = barycentrics, or spherical coordinates on a sphere
                 // (tracer_base.py:219-221); meshes interpolate their per-vertex uv.  process_ns (:291-307) touches the PRIMARY hit
                 // only (vanilla_renderer.py:42, quirk 3); the albedo lookup happens at every bounce (:66) and replaces k_d wherever
@@ -754,7 +754,16 @@ static int launch_iteration(adapt_handle* h) {
 #define LAUNCH_LOGIC(M, KEYS, FIRST) do { k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
         h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort, (unsigned)(KEYS), (FIRST), stamp); n_logic++; } while (0)
         const bool ts = (h->mats & M_TWOSIDED) != 0;
-        if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
+        if (h->sv.textures) {
+            // textured scenes: single launch of the matching instantiation + texture lookups
+            if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
+                if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED | M_TEXTURED, 0xffffffffu, 1); else LAUNCH_LOGIC(M_SIMPLE | M_TEXTURED, 0xffffffffu, 1);
+            } else if ((h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) {
+                LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF | M_TEXTURED, 0xffffffffu, 1);
+            } else {
+                LAUNCH_LOGIC(M_ALL | M_TEXTURED, 0xffffffffu, 1);
+            }
+        } else if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
             if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED, 0xffffffffu, 1); else LAUNCH_LOGIC(M_SIMPLE, 0xffffffffu, 1);
         } else if (!h->logic_passes || !h->logic_sort) {
             // one launch with every model compiled in

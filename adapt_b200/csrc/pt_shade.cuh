@@ -17,9 +17,10 @@ namespace adapt {
 
 // Material groups a k_logic instantiation is compiled for (the reference specialises its megakernel the same
 // way: ti.static flags and unused struct methods are compiled out per scene by the Taichi JIT).
-enum : int { M_SIMPLE = 1, M_GLOSSY = 2, M_COAT_GGX = 4, M_BSDF = 8, M_TWOSIDED = 16, M_ALL = 31 };
+enum : int { M_SIMPLE = 1, M_GLOSSY = 2, M_COAT_GGX = 4, M_BSDF = 8, M_TWOSIDED = 16, M_ALL = 31, M_TEXTURED = 32 };
 // groups: SIMPLE = phong(0) lambertian(1) specular(2) oren-nayar(6); GLOSSY = mod-phong(4) fresnel-blend(5);
-//         COAT_GGX = thin-coat(7) microfacet(3); BSDF = det-refraction / lambertian transmission / null
+//         COAT_GGX = thin-coat(7) microfacet(3); BSDF = det-refraction / lambertian transmission / null;
+//         TEXTURED adds the albedo / normal / bump map lookups (compiled out otherwise: they cost the small kernel its registers)
 
 // Material evaluators stay inline by default: measured on B200, passing the Bxdf/Surf structs through local memory
 // to out-of-line copies costs ~3 % more than the I-cache footprint it saves. -DPT_INLINE_MATS=0 is the A/B switch.
