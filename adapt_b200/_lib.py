@@ -89,6 +89,7 @@ class adapt_stats(C.Structure):
 # every symbol include/adapt_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "adapt_create", "adapt_destroy", "adapt_render", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
+    "adapt_read_pixels", "adapt_host_alloc", "adapt_host_free",
     "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch",
     "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version",
 ]
@@ -120,6 +121,12 @@ def load_library(path: Optional[str] = None):
     lib.adapt_read_accum.restype = C.c_int
     lib.adapt_load_accum.argtypes = [H, _fp, C.c_int32]
     lib.adapt_load_accum.restype = C.c_int
+    lib.adapt_read_pixels.argtypes = [H, _fp, _ip]
+    lib.adapt_read_pixels.restype = C.c_int
+    lib.adapt_host_alloc.argtypes = [C.c_uint64]
+    lib.adapt_host_alloc.restype = C.c_void_p
+    lib.adapt_host_free.argtypes = [C.c_void_p]
+    lib.adapt_host_free.restype = None
     lib.adapt_accum_device_ptr.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.adapt_accum_device_ptr.restype = C.c_int
     lib.adapt_set_stream.argtypes = [H, C.c_void_p]

@@ -683,6 +683,7 @@ struct adapt_handle {
     WorkStripe* h_work = nullptr;             // pinned copy the host polls
     Cursors* d_cur = nullptr;
     float* d_accum = nullptr;
+    float* d_mean = nullptr;                  // scratch of adapt_read_pixels, allocated on first use
     int* d_pixel_list = nullptr;
     int n_pixels = 0;
     int width = 0, height = 0;
@@ -1152,6 +1153,34 @@ int adapt_read_accum(adapt_handle* h, float* dst, int32_t* spp) {
     if (spp) *spp = h->cnt;
     return 0;
 }
+
+__global__ void k_resolve(const float* __restrict__ accum, float* __restrict__ mean, const size_t n, const float inv_cnt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mean[i] = accum[i] * inv_cnt;
+}
+
+int adapt_read_pixels(adapt_handle* h, float* dst, int32_t* spp) {
+    if (!h || !dst) return set_error(ADAPT_ERR_INVALID, "adapt_read_pixels: null argument");
+    int rc = adapt_sync(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->width * h->height * 3;
+    if (!h->d_mean) { rc = dev_alloc(h, &h->d_mean, n); if (rc) return rc; }
+    // color / cnt as one reciprocal multiply per component (what fast-math makes of the reference's vector / scalar division)
+    k_resolve<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_accum, h->d_mean, n, h->cnt > 0 ? 1.f / (float)h->cnt : 1.f);
+    CK(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    CK(cudaMemcpyAsync(dst, h->d_mean, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (spp) *spp = h->cnt;
+    return 0;
+}
+
+void* adapt_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void adapt_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int adapt_load_accum(adapt_handle* h, const float* src, int32_t spp) {
     if (!h || !src || spp < 0) return set_error(ADAPT_ERR_INVALID, "adapt_load_accum: bad argument");

@@ -35,11 +35,10 @@ class _FieldView:
     def shape(self):
         return (self._rdr.w, self._rdr.h)
 
-    def to_numpy(self) -> np.ndarray:
-        acc, cnt = self._rdr._read_accum()
-        if self._mean:
-            return acc / np.float32(max(cnt, 1)) if cnt > 0 else acc
-        return acc
+    def to_numpy(self, copy: bool = True) -> np.ndarray:
+        """(w, h, 3) float32.  ``copy=False`` returns a view of the renderer's page-locked staging buffer (valid until the
+        next read) and saves one host-side pass over the image."""
+        return self._rdr._read_film(self._mean, copy)[0]
 
     def from_numpy(self, arr: np.ndarray):
         if self._mean:
@@ -89,6 +88,8 @@ class Renderer:
         self._handle = C.c_void_p()
         check(self._lib, self._lib.adapt_create(C.byref(self._handle), C.byref(self._packed.desc)), "adapt_create")
         self._cnt = 0
+        self._pinned = None
+        self._pinned_ptr = None
         self.pixels = _FieldView(self, mean=True)
         self.color = _FieldView(self, mean=False)
         self.cnt = _Counter(self)
@@ -117,12 +118,26 @@ class Renderer:
         CONSOLE.print(f"PT SPP = {self._cnt}. Rendering time: {self.clock.toc():.3f} s", justify="center")
 
     # ------------------------------------------------------------------ framebuffer / checkpoint
-    def _read_accum(self):
-        acc = np.empty((self.w, self.h, 3), np.float32)
+    def _staging(self) -> np.ndarray:
+        """Page-locked (w, h, 3) host buffer the device copies land in (a pageable target is several times slower)."""
+        if self._pinned is None:
+            nbytes = self.w * self.h * 3 * 4
+            ptr = self._lib.adapt_host_alloc(nbytes)
+            if not ptr:
+                raise AdaptError("adapt_host_alloc failed")
+            self._pinned_ptr = ptr
+            self._pinned = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), (self.w, self.h, 3))
+        return self._pinned
+
+    def _read_film(self, mean: bool, copy: bool = True):
+        buf = self._staging()
         spp = C.c_int32(0)
-        check(self._lib, self._lib.adapt_read_accum(self._handle, acc.ctypes.data_as(C.POINTER(C.c_float)), C.byref(spp)),
-              "adapt_read_accum")
-        return acc, spp.value
+        fn, name = (self._lib.adapt_read_pixels, "adapt_read_pixels") if mean else (self._lib.adapt_read_accum, "adapt_read_accum")
+        check(self._lib, fn(self._handle, buf.ctypes.data_as(C.POINTER(C.c_float)), C.byref(spp)), name)
+        return (buf.copy() if copy else buf), spp.value
+
+    def _read_accum(self):
+        return self._read_film(False, True)
 
     def _load_accum(self, acc: np.ndarray, spp: int):
         acc = np.ascontiguousarray(acc, np.float32)
@@ -200,6 +215,10 @@ class Renderer:
         if getattr(self, "_handle", None) is not None and self._handle:
             self._lib.adapt_destroy(self._handle)
             self._handle = C.c_void_p()
+        if getattr(self, "_pinned_ptr", None):
+            self._pinned = None
+            self._lib.adapt_host_free(self._pinned_ptr)
+            self._pinned_ptr = None
 
     def __del__(self):
         try:

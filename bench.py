@@ -233,9 +233,9 @@ def run_b200(args):
         rdr.render_batch(spp_step)
         if world > 1:
             rdr.synchronize(); fb_out.copy_(fb); reduce_framebuffer(fb_out, dst=0)
-            out = (fb_out.cpu().numpy() if rank == 0 else rdr.pixels.to_numpy())   # D2H of the reduced film (sync point)
+            out = (fb_out.cpu().numpy() if rank == 0 else rdr.pixels.to_numpy(copy=False))   # D2H of the reduced film (sync point)
         else:
-            out = rdr.pixels.to_numpy()                # D2H of the mean buffer (sync point)
+            out = rdr.pixels.to_numpy(copy=False)      # D2H of the mean buffer into page-locked memory (sync point)
     ev1.record(stream)
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)

@@ -134,6 +134,13 @@ int adapt_sync(adapt_handle* h);
  * counter `cnt` (tracer/path_tracer.py:81, tracer_base.py:102). */
 int adapt_read_accum(adapt_handle* h, float* dst_whc, int32_t* spp);
 int adapt_load_accum(adapt_handle* h, const float* src_whc, int32_t spp);   /* checkpoint resume */
+/* `pixels.to_numpy()` of the reference (tracer_base.py:85, vanilla_renderer.py:120): the running mean color / cnt, divided on
+ * the device, then copied to dst_whc. */
+int adapt_read_pixels(adapt_handle* h, float* dst_whc, int32_t* spp);
+/* Page-locked host memory for the buffers handed to adapt_read_* / adapt_load_accum (a pageable destination makes the
+ * copy several times slower). Returns NULL on failure. */
+void* adapt_host_alloc(uint64_t bytes);
+void adapt_host_free(void* p);
 /* Device pointer of the (w,h,3) float sum, for in-place collectives (torch.distributed / NCCL). */
 int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats);
 
