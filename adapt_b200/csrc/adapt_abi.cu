@@ -66,12 +66,8 @@ static int env_int(const char* name, int dflt) {
 #define TRACE_MIN_BLOCKS 9
 #endif
 // sort keys of k_logic's block-local regrouping: material classes 0..10 (BRDF type 0..7, BSDF det-refraction 8, BSDF
-// Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot, 13 = not for this launch
-#define LOGIC_NKEY 14
-#define LOGIC_KEYS_SIMPLE ((1u << 0) | (1u << 1) | (1u << 2) | (1u << 6) | (1u << 11) | (1u << 12))
-#define LOGIC_KEYS_GLOSSY ((1u << 4) | (1u << 5))
-#define LOGIC_KEYS_COAT_GGX ((1u << 3) | (1u << 7))
-#define LOGIC_KEYS_BSDF ((1u << 8) | (1u << 9) | (1u << 10))
+// Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot
+#define LOGIC_NKEY 13
 
 // Block-wide allocation from a global counter: every thread passes `want` (0/1), gets its index.
 // Two barriers, one atomic per block. Must be called by all threads of the block.
@@ -173,11 +169,10 @@ template <int MATS>
 __global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort,
-        const unsigned key_mask, const int first_pass, const unsigned stamp) {
+        const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort) {
     const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
     // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
-    if (first_pass && tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
+    if (tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
     // work stripe of this warp (pt_common.cuh: WorkStripe)
     const int home = (int)((unsigned)(tslot >> 5) % PT_NSTRIPE);
 
@@ -188,26 +183,17 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // slots of the same class: key = material class of the surface hit (leaf record -> hit word, no extra load),
     // then slots whose path ends, then free slots.  All accesses stay inside the block's own 256-slot window of the
     // pool, so DRAM traffic is unchanged; what it costs is 13 ballots, a 104-entry prefix sum and three barriers.
-    //
-    // Scenes with several material groups run k_logic once per group (host: launch_iteration), each launch an
-    // instantiation that only contains that group's code (the all-in-one kernel is 125 KB of SASS and was instruction-fetch
-    // bound: ncu stall_no_instruction 46 %).  `key_mask` names the keys this launch handles; everything else, and every
-    // slot a previous launch of the same iteration has already advanced (misc.w == stamp), sorts to the end and is skipped.
     int slot = tslot;
-    bool mine = true;
     if (do_sort) {
         __shared__ unsigned s_cnt[LOGIC_NKEY * (LOGIC_BLOCK / 32)];
         __shared__ unsigned short s_perm[LOGIC_BLOCK];
         const uint4 m0 = pool.misc[tslot];
-        int key = LOGIC_NKEY - 2;                                           // free slot
-        if (m0.w == stamp) {
-            key = LOGIC_NKEY - 1;                                           // advanced by an earlier launch of this iteration
-        } else if (m0.z & SLOT_ALIVE) {
+        int key = LOGIC_NKEY - 1;                                           // free slot
+        if (m0.z & SLOT_ALIVE) {
             const int hw = __float_as_int(pool.hit[tslot].w);
-            key = ((m0.z & SLOT_FINISH) || hw < 0) ? LOGIC_NKEY - 3          // path ends here: splat, then regenerate
-                                                   : min((hw >> PT_HIT_PRIM_BITS) & 15, LOGIC_NKEY - 4);
+            key = ((m0.z & SLOT_FINISH) || hw < 0) ? LOGIC_NKEY - 2          // path ends here: splat, then regenerate
+                                                   : min((hw >> PT_HIT_PRIM_BITS) & 15, LOGIC_NKEY - 3);
         }
-        if (!((key_mask >> key) & 1u)) key = LOGIC_NKEY - 1;
         const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         unsigned my_rank = 0;
         #pragma unroll
@@ -234,12 +220,10 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         s_perm[s_cnt[key * (LOGIC_BLOCK / 32) + warp] + my_rank] = (unsigned short)threadIdx.x;
         __syncthreads();
         slot = blockIdx.x * LOGIC_BLOCK + (int)s_perm[threadIdx.x];
-        mine = threadIdx.x < s_cnt[(LOGIC_NKEY - 1) * (LOGIC_BLOCK / 32)];    // skipped slots sit at the end of the order
-        if (!__any_sync(0xffffffffu, mine)) return;
     }
 
     uint4 misc = pool.misc[slot];
-    bool alive = mine && (misc.z & SLOT_ALIVE) != 0;
+    bool alive = (misc.z & SLOT_ALIVE) != 0;
     // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
     if (!__any_sync(0xffffffffu, alive)) {
         bool dry = true;
@@ -428,7 +412,6 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         pool.col[slot] = make_float4(color.x, color.y, color.z, 0.f);
         pool.rng[slot] = make_uint2((uint32_t)rng.state, (uint32_t)(rng.state >> 32));
         misc.z = (uint32_t)bounce | flags;
-        misc.w = stamp;
         pool.misc[slot] = misc;
     }
 
@@ -450,7 +433,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // If the home stripe is dry the warp tries its neighbours (tail of a work range only).
     // A camera ray that misses the scene's bounding box ends its path on the spot (colour 0, nothing to splat):
     // the slot immediately takes the next work item instead of spending a whole wavefront iteration on it.
-    bool need = mine && !alive && !shading;
+    bool need = !alive && !shading;
     unsigned culled = 0;
     const bool may_cull = sv.cull_primary && sv.max_bounce > 0;
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -501,7 +484,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                     pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
                     pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
                     pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), stamp);
+                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
                     need = false;
                 }
             } else if (!live || attempt == 3) {
@@ -523,8 +506,8 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 // ================================================================================================
 // k_closest / k_shadow: persistent warps over the ray streams.
 //   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements and node counting)
-//   MODE 1: per-lane refill straight from the stream + vote-scheduled traversal (pt_trace.cuh: trace_stream_vote)
-//   MODE 2: the same traversal fed from a per-warp shared-memory ring filled by a cp.async pipeline (trace_stream_ring)
+//   MODE 1: per-lane refill + vote-scheduled traversal of the binary BVH (pt_trace.cuh: trace_stream_vote)
+//   MODE 2: the same over the 4-wide BVH collapsed from it
 // ================================================================================================
 struct ClosestSource {
     PathPool pool;
@@ -540,9 +523,6 @@ struct ClosestSource {
         o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z); tmax = o4.w;
         return true;
     }
-    PT_D const float4* o_ptr(unsigned i) const { return pool.ray_o + i; }
-    PT_D const float4* d_ptr(unsigned i) const { return pool.ray_d + i; }
-    PT_D bool accept(const float4 o4, const float4, float& tmax) const { tmax = o4.w; return o4.w > 0.f; }
     PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(pack_hit(h))); }
 };
 struct ShadowSource {
@@ -558,9 +538,6 @@ struct ShadowSource {
         tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF;
         return true;
     }
-    PT_D const float4* o_ptr(unsigned i) const { return sq.o + i; }
-    PT_D const float4* d_ptr(unsigned i) const { return sq.d + i; }
-    PT_D bool accept(const float4 o4, const float4, float& tmax) const { tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF; return true; }
     PT_D void store(unsigned i, const HitRec& h) const {
         if (h.prim >= 0) return;                     // occluded: shadow_int = 0
         const float4 c4 = sq.c[i];
@@ -599,9 +576,7 @@ k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ 
           const int refill, const int leaf_t) {
     unsigned traced = 0, nn = 0, np = 0;
     ClosestSource src{pool};
-    __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
-    if (MODE == 2) trace_stream_ring<false, COUNT>(sv, src, cur->closest, rings[MODE == 2 ? threadIdx.x >> 5 : 0], refill, leaf_t, traced, nn, np);
-    else if (MODE == 1) trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+    if (MODE >= 1) trace_stream_vote<false, COUNT, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
     else trace_stream_simple<false, COUNT>(sv, src, cur->closest, traced, nn, np);
     block_count(traced, &ctr->rays_closest);
     if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
@@ -613,9 +588,7 @@ k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCo
          const int refill, const int leaf_t, const int parity) {
     unsigned traced = 0, nn = 0, np = 0;
     ShadowSource src{pool, sq, parity};
-    __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
-    if (MODE == 2) trace_stream_ring<true, false>(sv, src, cur->shadow, rings[MODE == 2 ? threadIdx.x >> 5 : 0], refill, leaf_t, traced, nn, np);
-    else if (MODE == 1) trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    if (MODE >= 1) trace_stream_vote<true, false, MODE == 2>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
     else trace_stream_simple<true, false>(sv, src, cur->shadow, traced, nn, np);
     block_count(traced, &ctr->rays_shadow);
 }
@@ -628,20 +601,16 @@ template <int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
 k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
         const int refill, const int leaf_t, const int parity) {
-    __shared__ WarpRing rings[MODE == 2 ? TRACE_BLOCK / 32 : 1];
-    WarpRing& ring = rings[MODE == 2 ? threadIdx.x >> 5 : 0];
     unsigned traced = 0, nn = 0, np = 0;
     {
         ShadowSource src{pool, sq, parity};
-        if (MODE == 2) trace_stream_ring<true, false>(sv, src, cur->shadow, ring, refill, leaf_t, traced, nn, np);
-        else trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        trace_stream_vote<true, false, MODE == 2>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
         block_count(traced, &ctr->rays_shadow);
     }
     traced = 0;
     {
         ClosestSource src{pool};
-        if (MODE == 2) trace_stream_ring<false, false>(sv, src, cur->closest, ring, refill, leaf_t, traced, nn, np);
-        else trace_stream_vote<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        trace_stream_vote<false, false, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
         block_count(traced, &ctr->rays_closest);
     }
 }
@@ -695,9 +664,8 @@ struct adapt_handle {
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
     int trace_mode = 2;
     bool fuse_trace = true;
+    bool wide_ok = true;
     int logic_sort = 1;
-    int logic_passes = 1;
-    unsigned iter_stamp = 0;
     unsigned iter_parity = 0;
     int refill = 16, leaf_t = 12;
     bool count_nodes = false;
@@ -748,34 +716,19 @@ static int launch_iteration(adapt_handle* h) {
     const int parity = (int)(h->iter_parity & 1u);
     h->iter_parity ^= 1u;
     CK(cudaEventRecord(ev.e[0], st));
-    int n_logic = 0;
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
-        const unsigned stamp = ++h->iter_stamp ? h->iter_stamp : ++h->iter_stamp;      // never 0 (parked slots carry 0)
-#define LAUNCH_LOGIC(M, KEYS, FIRST) do { k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
-        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort, (unsigned)(KEYS), (FIRST), stamp); n_logic++; } while (0)
-        const bool ts = (h->mats & M_TWOSIDED) != 0;
-        if (h->sv.textures) {
-            // textured scenes: single launch of the matching instantiation + texture lookups
-            if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
-                if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED | M_TEXTURED, 0xffffffffu, 1); else LAUNCH_LOGIC(M_SIMPLE | M_TEXTURED, 0xffffffffu, 1);
-            } else if ((h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) {
-                LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF | M_TEXTURED, 0xffffffffu, 1);
-            } else {
-                LAUNCH_LOGIC(M_ALL | M_TEXTURED, 0xffffffffu, 1);
-            }
-        } else if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
-            if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED, 0xffffffffu, 1); else LAUNCH_LOGIC(M_SIMPLE, 0xffffffffu, 1);
-        } else if (!h->logic_passes || !h->logic_sort) {
-            // one launch with every model compiled in
-            if (h->mats == (M_SIMPLE | M_GLOSSY | M_BSDF)) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF, 0xffffffffu, 1);
-            else LAUNCH_LOGIC(M_ALL, 0xffffffffu, 1);
+#define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
+        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort)
+        // the instantiation that covers the scene's material groups (+ two-sided BRDFs, + texture lookups)
+        const bool ts = (h->mats & M_TWOSIDED) != 0, tex = h->sv.textures != nullptr;
+        if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
+            if (tex) { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED | M_TEXTURED); else LAUNCH_LOGIC(M_SIMPLE | M_TEXTURED); }
+            else { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED); else LAUNCH_LOGIC(M_SIMPLE); }
+        } else if ((h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) {
+            if (tex) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF | M_TEXTURED); else LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
         } else {
-            // one launch per material group present (k_logic: "block-local regrouping")
-            if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED, LOGIC_KEYS_SIMPLE, 1); else LAUNCH_LOGIC(M_SIMPLE, LOGIC_KEYS_SIMPLE, 1);
-            if (h->mats & M_GLOSSY) { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_TWOSIDED, LOGIC_KEYS_GLOSSY, 0); else LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY, LOGIC_KEYS_GLOSSY, 0); }
-            if (h->mats & M_COAT_GGX) { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_COAT_GGX | M_TWOSIDED, LOGIC_KEYS_COAT_GGX, 0); else LAUNCH_LOGIC(M_SIMPLE | M_COAT_GGX, LOGIC_KEYS_COAT_GGX, 0); }
-            if (h->mats & M_BSDF) LAUNCH_LOGIC(M_SIMPLE | M_BSDF, LOGIC_KEYS_BSDF, 0);
+            if (tex) LAUNCH_LOGIC(M_ALL | M_TEXTURED); else LAUNCH_LOGIC(M_ALL);
         }
 #undef LAUNCH_LOGIC
     }
@@ -798,7 +751,7 @@ static int launch_iteration(adapt_handle* h) {
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
     h->stats.iterations += 1;
-    h->stats.kernel_launches += n_logic + ((h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 2);
+    h->stats.kernel_launches += (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 2 : 3;
     return 0;
 }
 
@@ -961,13 +914,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
             else if (b.type == 7 || b.type == 3) need |= M_COAT_GGX;
         }
         if (d->brdf_two_sides) need |= M_TWOSIDED;
-        // M_SIMPLE alone: one launch of the small kernel.  Otherwise `mats` keeps the exact group bits: launch_iteration runs one
-        // specialised launch per group (ADAPT_LOGIC_PASSES=0: a single launch of the all-in-one instantiation instead).
-        h->mats = (need == M_SIMPLE) ? M_SIMPLE : need;
+        h->mats = need;
         if (env_int("ADAPT_LOGIC_GENERIC", 0)) h->mats = M_ALL;
-        h->logic_passes = env_int("ADAPT_LOGIC_PASSES", 0);      // measured on B200: per-group launches are slower than one sorted launch
-        if (!h->logic_passes && h->mats != M_SIMPLE && (h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) != 0) h->mats = M_ALL;
-        else if (!h->logic_passes && h->mats != M_SIMPLE) h->mats = M_SIMPLE | M_GLOSSY | M_BSDF;
     }
     // ---- BVH (replaces bvh_process, tracer/path_tracer.py:143-179)
     BuildParams bp;
@@ -988,6 +936,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     SceneView& sv = h->sv;
     float4* tmp4 = nullptr;
     CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes.data()), gb.nodes.size() * 4)); sv.nodes = tmp4;
+    CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes4.data()), gb.nodes4.size() * 8)); sv.nodes4 = tmp4;
+    h->wide_ok = 3 * gb.depth4 + 1 <= PT_STACK_SIZE;         // a 4-wide step can push three entries
     CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3)); sv.leaf_prims = tmp4;
     CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4;
     CKH(dev_upload(h, &tmp4, prim_shade.data(), prim_shade.size())); sv.prim_shade = tmp4;
@@ -1099,7 +1049,9 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
 
     // ---- launch shape: persistent trace kernels, a multiple of the SM count
     h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
-    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);     // 2 (shared-memory ring fed by cp.async) measured slower on B200, see DESIGN.md
+    // 2 = 4-wide tree: measured on B200 equal on orb500k, 6 % slower on bunny90k, 10 % faster only on the 18-primitive balls scene
+    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);
+    if (h->trace_mode == 2 && !h->wide_ok) h->trace_mode = 1;    // 4-wide tree too deep for the per-lane stack: binary tree
     {
         // persistent trace kernels: exactly as many blocks as are resident at once (one wave), at most ADAPT_TRACE_BLOCKS_PER_SM per SM
         int occ = 0;
@@ -1111,7 +1063,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
     h->logic_sort = env_int("ADAPT_LOGIC_SORT", (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) ? 1 : 0);
-    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", h->trace_mode == 2 ? 4 : 16)));
+    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
     h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 12)));
     h->ev_ring.resize(512);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));

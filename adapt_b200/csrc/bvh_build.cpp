@@ -211,6 +211,19 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
         g.v[4] = e.lo[0]; g.v[5] = e.hi[0]; g.v[6] = e.lo[1]; g.v[7] = e.hi[1]; g.v[10] = e.lo[2]; g.v[11] = e.hi[2];
         g.c[0] = leaf_code(br.nodes[0]); g.c[1] = g.c[0];
         out.depth = 1;
+        out.nodes4.resize(1);
+        GpuNode4& g4 = out.nodes4[0];
+        std::memset(&g4, 0, sizeof(g4));
+        for (int k = 0; k < 4; k++) {
+            for (int a = 0; a < 6; a++) g4.v[a * 4 + k] = 1.0e30f;
+            g4.c[k] = -1;
+        }
+        for (int a = 0; a < 3; a++) {
+            g4.v[(2 * a) * 4] = std::nextafterf(br.nodes[0].box.lo[a], -3.0e38f);
+            g4.v[(2 * a + 1) * 4] = std::nextafterf(br.nodes[0].box.hi[a], 3.0e38f);
+        }
+        g4.c[0] = leaf_code(br.nodes[0]);
+        out.depth4 = 1;
         return;
     }
     out.nodes.resize((size_t)n_inner);
@@ -233,6 +246,63 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
         st.push_back({nd.left, it.depth + 1}); st.push_back({nd.right, it.depth + 1});
     }
     out.depth = max_depth + 1;
+
+    // ---- 4-wide collapse: a node adopts its grandchildren in place of the inner child with the largest surface area
+    // until it has four children (or only leaves are left).  Same leaves, same primitive order.
+    {
+        struct Wide { int32_t child[4]; int n; };                 // binary node ids
+        std::vector<int32_t> wide_index(br.nodes.size(), -1);     // binary node id -> 4-wide node index (for collapsed roots)
+        std::vector<Wide> wides;
+        std::vector<int32_t> order;                               // binary ids of the wide nodes' roots, BFS
+        order.push_back(0);
+        wide_index[0] = 0;
+        for (size_t hd = 0; hd < order.size(); hd++) {
+            const BuildNode& nd = br.nodes[order[hd]];
+            Wide w; w.n = 0;
+            w.child[w.n++] = nd.left; w.child[w.n++] = nd.right;
+            while (w.n < 4) {
+                int best = -1; float best_area = -1.f;
+                for (int k = 0; k < w.n; k++) {
+                    const BuildNode& c = br.nodes[w.child[k]];
+                    if (c.left >= 0 && c.box.half_area() > best_area) { best_area = c.box.half_area(); best = k; }
+                }
+                if (best < 0) break;
+                const BuildNode& c = br.nodes[w.child[best]];
+                w.child[best] = c.left;
+                w.child[w.n++] = c.right;
+            }
+            for (int k = 0; k < w.n; k++)
+                if (br.nodes[w.child[k]].left >= 0) { wide_index[w.child[k]] = (int32_t)order.size(); order.push_back(w.child[k]); }
+            wides.push_back(w);
+        }
+        out.nodes4.resize(wides.size());
+        std::vector<int32_t> depth_of(wides.size(), 1);
+        int32_t max_depth4 = 1;
+        for (size_t i = 0; i < wides.size(); i++) {
+            GpuNode4& g = out.nodes4[i];
+            std::memset(&g, 0, sizeof(g));
+            for (int k = 0; k < 4; k++) {
+                if (k < wides[i].n) {
+                    const BuildNode& c = br.nodes[wides[i].child[k]];
+                    for (int a = 0; a < 3; a++) {
+                        g.v[(2 * a) * 4 + k] = std::nextafterf(c.box.lo[a], -3.0e38f);
+                        g.v[(2 * a + 1) * 4 + k] = std::nextafterf(c.box.hi[a], 3.0e38f);
+                    }
+                    if (c.left >= 0) {
+                        g.c[k] = wide_index[wides[i].child[k]];
+                        depth_of[g.c[k]] = depth_of[i] + 1;
+                        max_depth4 = std::max(max_depth4, depth_of[g.c[k]]);
+                    } else {
+                        g.c[k] = leaf_code(c);
+                    }
+                } else {
+                    for (int a = 0; a < 6; a++) g.v[a * 4 + k] = 1.0e30f;        // point box far away: never hit
+                    g.c[k] = -1;
+                }
+            }
+        }
+        out.depth4 = max_depth4 + 1;
+    }
 }
 
 void to_reference_layout(const BuildResult& br, const int32_t* prim_obj, const float* world_min, const float* world_max,

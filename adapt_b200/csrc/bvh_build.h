@@ -57,10 +57,17 @@ struct alignas(16) GpuNode { float v[12]; int32_t c[4]; };
 //   sphere: t0 = (center.xyz, radius)
 struct alignas(16) GpuPrim { float v[12]; };
 
+// ---- 4-wide layout collapsed from the binary tree: 128-byte nodes, child boxes as structure-of-arrays -------------
+// q0 = lo.x of children 0..3, q1 = hi.x, q2 = lo.y, q3 = hi.y, q4 = lo.z, q5 = hi.z, q6 = child codes (same encoding as the
+// binary layout), q7 = unused.  An unused child slot holds a far-away point box that no ray hits.
+struct alignas(16) GpuNode4 { float v[24]; int32_t c[4]; int32_t pad[4]; };
+
 struct GpuBvh {
     std::vector<GpuNode> nodes;
+    std::vector<GpuNode4> nodes4;
     std::vector<GpuPrim> prims;   // leaf order
-    int32_t depth = 0;
+    int32_t depth = 0;            // binary tree
+    int32_t depth4 = 0;           // 4-wide tree
 };
 void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj,
                    const uint8_t* obj_class, GpuBvh& out);

@@ -15,6 +15,7 @@ namespace adapt {
 #define PT_STACK_SIZE 64
 #define PT_T_EPS 1e-4f          // "ray_t > 1e-4" self-intersection guard of the reference
 #define PT_T_INF 1e7f           // min_depth initial value (tracer_base.py:176)
+#define PT_NODE_DONE ((int)0x80000000)
 
 struct HitRec {
     float t, u, v;
@@ -92,6 +93,41 @@ PT_D void child_slabs(const float4 n0, const float4 n1, const float4 n2, const R
     hit1 = tmin1 <= tmax1 * 1.0000005f;
 }
 
+// One step through a 4-wide node: slab test of the four child boxes (SoA), then the children that are hit are visited
+// nearest first -- the nearest becomes the current node, the others go on the stack farthest first.  Entry distances are
+// sorted with a 5-comparator network; a missed child carries +inf and sorts to the end.
+PT_D int wide_step(const float4* __restrict__ n, const RayPre& r, const float tmax, int* __restrict__ stack, int& sp) {
+    const float4 lox = __ldg(n + 0), hix = __ldg(n + 1), loy = __ldg(n + 2), hiy = __ldg(n + 3), loz = __ldg(n + 4), hiz = __ldg(n + 5);
+    const float4 cf = __ldg(n + 6);
+    float t[4]; int c[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
+#define PT_SLAB(K, LX, HX, LY, HY, LZ, HZ)                                                                         \
+    {                                                                                                              \
+        const float x0 = fmaf(LX, r.idir.x, -r.ood.x), x1 = fmaf(HX, r.idir.x, -r.ood.x);                          \
+        const float y0 = fmaf(LY, r.idir.y, -r.ood.y), y1 = fmaf(HY, r.idir.y, -r.ood.y);                          \
+        const float z0 = fmaf(LZ, r.idir.z, -r.ood.z), z1 = fmaf(HZ, r.idir.z, -r.ood.z);                          \
+        const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));                     \
+        const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));                    \
+        t[K] = tn <= tf * 1.0000005f ? tn : __int_as_float(0x7f800000);                                             \
+    }
+    PT_SLAB(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x)
+    PT_SLAB(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y)
+    PT_SLAB(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z)
+    PT_SLAB(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w)
+#undef PT_SLAB
+    const float inf = __int_as_float(0x7f800000);
+    const unsigned m = (t[0] < inf ? 1u : 0u) | (t[1] < inf ? 2u : 0u) | (t[2] < inf ? 4u : 0u) | (t[3] < inf ? 8u : 0u);
+    if (m == 0u) return sp ? stack[--sp] : PT_NODE_DONE;             // nothing hit: pop
+    if ((m & (m - 1u)) == 0u)                                         // one child hit (the common case): no ordering needed
+        return (m & 1u) ? c[0] : (m & 2u) ? c[1] : (m & 4u) ? c[2] : c[3];
+#define PT_CSWAP(A, B) { if (t[B] < t[A]) { const float tt = t[A]; t[A] = t[B]; t[B] = tt; const int cc = c[A]; c[A] = c[B]; c[B] = cc; } }
+    PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
+#undef PT_CSWAP
+    if (t[3] < inf && sp < PT_STACK_SIZE) stack[sp++] = c[3];
+    if (t[2] < inf && sp < PT_STACK_SIZE) stack[sp++] = c[2];
+    if (sp < PT_STACK_SIZE) stack[sp++] = c[1];
+    return c[0];
+}
+
 template <bool ANY_HIT, bool COUNT>
 PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit, unsigned& n_nodes, unsigned& n_prims) {
     const RayPre r = make_ray(o, d);
@@ -149,8 +185,6 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 }
 
 
-#define PT_NODE_DONE ((int)0x80000000)
-
 // ------------------------------------------------------------------------------------------------
 // Persistent-warp ray stream with per-lane refill and vote-scheduled traversal.
 //
@@ -158,7 +192,7 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 // so "32 rays in, wait for the slowest" leaves most lanes idle (ncu: ~6 of 32 lanes active per instruction).  Here
 // every lane keeps its own traversal state; as soon as `refill` or more lanes have finished, the warp grabs that many
 // new rays from a stream cursor with ONE atomic and the idle lanes start over, so the warp stays populated until the
-// stream runs dry.  Inside the loop one iteration gives every lane that holds an inner node ONE node step, and the
+// stream runs dry (WIDE: over the 4-wide tree, see wide_step).  Inside the loop one iteration gives every lane that holds an inner node ONE node step, and the
 // leaf code only runs when at least `leaf_t` lanes are parked on a leaf (or no lane has inner work left), so both
 // code paths execute with well-populated warps (ncu on the plain while-while loop: ~5 of 32 lanes in the node code).
 // The cursor is striped (pt_common.cuh: CursorStripe): one cursor for the whole stream cost 15 % of k_shadow's
@@ -168,7 +202,7 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 //                  bool load(unsigned i, float3& o, float3& d, float& tmax);        (false: empty entry)
 //                  void store(unsigned i, const HitRec& h);   (closest hit: the record; any hit: h.prim >= 0 means occluded)
 // ------------------------------------------------------------------------------------------------
-template <bool ANY_HIT, bool COUNT, typename Source>
+template <bool ANY_HIT, bool COUNT, bool WIDE, typename Source>
 PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, const int refill, const int leaf_t,
                             unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
     const unsigned FULL = 0xffffffffu;
@@ -233,24 +267,28 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
         if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)
         while (true) {
             if (node >= 0) {
-                const float4 n0 = __ldg(nodes + node * 4 + 0);
-                const float4 n1 = __ldg(nodes + node * 4 + 1);
-                const float4 n2 = __ldg(nodes + node * 4 + 2);
-                const float4 n3 = __ldg(nodes + node * 4 + 3);
                 if (COUNT) n_nodes++;
-                float tmin0, tmin1; bool h0, h1;
-                child_slabs(n0, n1, n2, r, hit.t, tmin0, tmin1, h0, h1);
-                int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    if (tmin1 < tmin0) { int tmp = c0; c0 = c1; c1 = tmp; }
-                    if (sp < PT_STACK_SIZE) stack[sp++] = c1;
-                    node = c0;
-                } else if (h0) {
-                    node = c0;
-                } else if (h1) {
-                    node = c1;
+                if (WIDE) {
+                    node = wide_step(sc.nodes4 + (size_t)node * 8, r, hit.t, stack, sp);
                 } else {
-                    node = sp ? stack[--sp] : PT_NODE_DONE;
+                    const float4 n0 = __ldg(nodes + node * 4 + 0);
+                    const float4 n1 = __ldg(nodes + node * 4 + 1);
+                    const float4 n2 = __ldg(nodes + node * 4 + 2);
+                    const float4 n3 = __ldg(nodes + node * 4 + 3);
+                    float tmin0, tmin1; bool h0, h1;
+                    child_slabs(n0, n1, n2, r, hit.t, tmin0, tmin1, h0, h1);
+                    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                    if (h0 && h1) {
+                        if (tmin1 < tmin0) { int tmp = c0; c0 = c1; c1 = tmp; }
+                        if (sp < PT_STACK_SIZE) stack[sp++] = c1;
+                        node = c0;
+                    } else if (h0) {
+                        node = c0;
+                    } else if (h1) {
+                        node = c1;
+                    } else {
+                        node = sp ? stack[--sp] : PT_NODE_DONE;
+                    }
                 }
             }
             const bool is_leaf = node < 0 && node != PT_NODE_DONE;
@@ -288,211 +326,6 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                 const unsigned act = __ballot_sync(FULL, cur >= 0);
                 if (act == 0u) break;
                 if (!exhausted && __popc(act) <= 32 - refill) break;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Ring-buffered ray stream (mode 2): the refill path of trace_stream_vote exposes two full memory round trips to the
-// whole warp (cursor atomic, then the ray records), so it can only afford to refill when half the lanes are idle --
-// ncu: 18 of 32 lanes active per instruction.  Here each warp keeps a small ring of ready rays in shared memory and
-// feeds it through a two-stage software pipeline that overlaps with traversal:
-//     stage A  lane 0 bumps the stream cursor by PT_CHUNK (atomic issued, result not consumed yet)
-//     stage B  the PT_CHUNK ray records are copied global -> shared staging area with cp.async (no registers held)
-//     stage C  staged records are validated (parked slots / unused queue space drop out) and compacted into the ring
-// so an idle lane takes its next ray from shared memory (~30 cycles) and the warp can refill as soon as `refill`
-// (default 4) lanes are free.  Traversal itself is the vote-scheduled loop of trace_stream_vote, one step per iteration.
-//
-// Source concept (in addition to stripe_range / store):
-//     const float4* o_ptr(unsigned i), d_ptr(unsigned i);   addresses of the two 16-byte records of entry i
-//     bool accept(float4 o4, float4 d4, float& tmax);       false: empty entry
-// ------------------------------------------------------------------------------------------------
-#define PT_RING 32
-#define PT_CHUNK 16
-#define PT_STAGE_AGE 0
-#define PT_INNER_STEPS 8
-struct WarpRing {
-    float4 o[PT_RING];        // (o.xyz, tmax)
-    float4 d[PT_RING];        // (d.xyz, stream index bits)
-    float4 so[PT_CHUNK];      // staging area the cp.async copies land in
-    float4 sd[PT_CHUNK];
-};
-PT_D void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-PT_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-PT_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-template <bool ANY_HIT, bool COUNT, typename Source>
-PT_D void trace_stream_ring(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, WarpRing& ring, const int refill,
-                            const int leaf_t, unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const float4* __restrict__ nodes = sc.nodes;
-    const float4* __restrict__ prims = sc.leaf_prims;
-    int stack[PT_STACK_SIZE];
-    int sp = 0, node = PT_NODE_DONE;
-    int cur = -1;
-    // ---- warp-uniform pipeline state
-    int stripe = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % PT_NCURSOR);
-    unsigned s_lo, s_hi;
-    src.stripe_range(stripe, s_lo, s_hi);
-    bool exhausted = false;                 // every stripe has been handed out: no further claims
-    bool claim_pending = false;             // stage A in flight: lane 0 holds the atomic's result in claim_reg
-    unsigned claim_reg = 0, claim_lo = 0, claim_hi = 0;
-    bool stage_pending = false;             // stage B in flight: entries stage_base + lane (lane < PT_CHUNK) < stage_hi
-    unsigned stage_base = 0, stage_hi = 0;
-    unsigned r_head = 0, r_count = 0;       // ring entries [r_head, r_head + r_count) mod PT_RING
-    // A pipeline stage is only consumed PT_STAGE_AGE outer iterations after it was issued (an outer iteration is up to
-    // PT_INNER_STEPS traversal steps of the whole warp, thousands of cycles with the other resident warps in between), or at
-    // once when the warp has nothing else to do: consuming it earlier would just block the warp on the memory round trip
-    // it is meant to hide.
-    int claim_age = 0, stage_age = 0;
-    RayPre r = make_ray(mk3(0.f), mk3(0.f, 0.f, 1.f));
-    HitRec hit; hit.prim = -1; hit.t = 0.f; hit.u = hit.v = 0.f; hit.obj = 0; hit.cls = 0;
-    while (true) {
-        // ---------------------------------------------------------------- stage C: staging area -> ring
-        const bool starving = r_count == 0u && !__any_sync(FULL, cur >= 0);
-        if (stage_pending && r_count <= PT_RING - PT_CHUNK && (++stage_age > PT_STAGE_AGE || starving)) {
-            cp_async_wait_all();
-            bool ok = false;
-            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
-            float tmax = 0.f;
-            if (lane < PT_CHUNK && stage_base + lane < stage_hi) {
-                o4 = ring.so[lane]; d4 = ring.sd[lane];
-                ok = src.accept(o4, d4, tmax);
-            }
-            const unsigned m = __ballot_sync(FULL, ok);
-            if (ok) {
-                const unsigned pos = (r_head + r_count + (unsigned)__popc(m & lt_mask)) & (PT_RING - 1);
-                ring.o[pos] = make_float4(o4.x, o4.y, o4.z, tmax);
-                ring.d[pos] = make_float4(d4.x, d4.y, d4.z, __uint_as_float(stage_base + lane));
-            }
-            r_count += (unsigned)__popc(m);
-            stage_pending = false;
-            __syncwarp();
-        }
-        // ---------------------------------------------------------------- stage B: claimed indices -> cp.async into the staging area
-        if (claim_pending && !stage_pending && (++claim_age > PT_STAGE_AGE || starving)) {
-            const unsigned base = __shfl_sync(FULL, claim_reg, 0) + claim_lo;
-            stage_base = base; stage_hi = claim_hi;
-            if (lane < PT_CHUNK && base + lane < claim_hi) {
-                cp_async16(&ring.so[lane], src.o_ptr(base + lane));
-                cp_async16(&ring.sd[lane], src.d_ptr(base + lane));
-            }
-            cp_async_commit();
-            stage_pending = true; claim_pending = false; stage_age = 0;
-            if (base + PT_CHUNK >= claim_hi && claim_lo == s_lo && !exhausted) {
-                // that claim drained the current stripe: look at all cursors at once (one round trip) and move to the next
-                // stripe that still has rays; a stripe seen dry stays dry, one seen live may dry before we get there
-                bool live = false;
-                if (lane < PT_NCURSOR) {
-                    unsigned lo_k, hi_k;
-                    src.stripe_range((int)lane, lo_k, hi_k);
-                    live = (int)lane != stripe && *reinterpret_cast<volatile unsigned*>(&cursors[lane].v) < hi_k - lo_k;
-                }
-                const unsigned avail = __ballot_sync(FULL, live);
-                if (avail == 0u) {
-                    exhausted = true;
-                } else {
-                    const unsigned above = avail & ~((2u << stripe) - 1u);          // stripes after the current one first
-                    stripe = __ffs(above ? above : avail) - 1;
-                    src.stripe_range(stripe, s_lo, s_hi);
-                }
-            }
-        }
-        // ---------------------------------------------------------------- stage A: next claim
-        if (!claim_pending && !exhausted && r_count + (stage_pending ? PT_CHUNK : 0) <= PT_RING - PT_CHUNK) {
-            if (lane == 0) claim_reg = atomicAdd(&cursors[stripe].v, (unsigned)PT_CHUNK);
-            claim_lo = s_lo; claim_hi = s_hi;
-            claim_pending = true; claim_age = 0;
-        }
-        // ---------------------------------------------------------------- idle lanes take rays from the ring
-        {
-            const unsigned idle = __ballot_sync(FULL, cur < 0);
-            const unsigned n_idle = (unsigned)__popc(idle);
-            if (r_count && (n_idle >= (unsigned)refill || idle == FULL)) {
-                const unsigned take = n_idle < r_count ? n_idle : r_count;
-                const unsigned rank = (unsigned)__popc(idle & lt_mask);
-                if (cur < 0 && rank < take) {
-                    const unsigned pos = (r_head + rank) & (PT_RING - 1);
-                    const float4 o4 = ring.o[pos], d4 = ring.d[pos];
-                    cur = (int)__float_as_uint(d4.w);
-                    r = make_ray(mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
-                    hit.prim = -1; hit.t = o4.w; hit.u = 0.f; hit.v = 0.f; hit.obj = 0; hit.cls = 0;
-                    node = 0; sp = 0;
-                    traced++;
-                }
-                r_head = (r_head + take) & (PT_RING - 1);
-                r_count -= take;
-                __syncwarp();
-            }
-        }
-        if (!__any_sync(FULL, cur >= 0)) {
-            if (exhausted && !claim_pending && !stage_pending && r_count == 0u) break;
-            continue;            // nothing to traverse yet: the pipeline stages above block on their own data
-        }
-        // ---------------------------------------------------------------- vote-scheduled traversal steps, until enough lanes
-        // have retired for a refill from the ring to pay off (or, every PT_INNER_STEPS steps, to service the pipeline)
-        #pragma unroll 1
-        for (int step = 0; step < PT_INNER_STEPS; step++) {
-            if (node >= 0) {
-                const float4 n0 = __ldg(nodes + node * 4 + 0);
-                const float4 n1 = __ldg(nodes + node * 4 + 1);
-                const float4 n2 = __ldg(nodes + node * 4 + 2);
-                const float4 n3 = __ldg(nodes + node * 4 + 3);
-                if (COUNT) n_nodes++;
-                float tmin0, tmin1; bool h0, h1;
-                child_slabs(n0, n1, n2, r, hit.t, tmin0, tmin1, h0, h1);
-                int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    if (tmin1 < tmin0) { int tmp = c0; c0 = c1; c1 = tmp; }
-                    if (sp < PT_STACK_SIZE) stack[sp++] = c1;
-                    node = c0;
-                } else if (h0) {
-                    node = c0;
-                } else if (h1) {
-                    node = c1;
-                } else {
-                    node = sp ? stack[--sp] : PT_NODE_DONE;
-                }
-            }
-            const bool is_leaf = node < 0 && node != PT_NODE_DONE;
-            const unsigned leaf_mask = __ballot_sync(FULL, is_leaf);
-            if (leaf_mask) {
-                // run the leaf code when enough lanes are parked on a leaf, or nobody has inner work left
-                if (__popc(leaf_mask) >= leaf_t || !__any_sync(FULL, node >= 0)) {
-                    if (is_leaf) {
-                        const int code = ~node;
-                        const int first = code >> 3, cnt = (code & 7) + 1;
-                        bool found = false;
-                        for (int k = 0; k < cnt; k++) {
-                            const float4 t0 = __ldg(prims + (first + k) * 3 + 0);
-                            const float4 t1 = __ldg(prims + (first + k) * 3 + 1);
-                            const float4 t2 = __ldg(prims + (first + k) * 3 + 2);
-                            if (COUNT) n_prims++;
-                            float t, u, v;
-                            if (prim_test(t0, t1, t2, r, hit.t, t, u, v)) {
-                                hit.t = t; hit.u = u; hit.v = v;
-                                hit.prim = __float_as_int(t2.y);
-                                hit.obj = __float_as_int(t2.z);
-                                hit.cls = __float_as_int(t2.w);
-                                found = true;
-                                if (ANY_HIT) break;
-                            }
-                        }
-                        node = (ANY_HIT && found) ? PT_NODE_DONE : (sp ? stack[--sp] : PT_NODE_DONE);
-                    }
-                }
-            }
-            const bool fin = node == PT_NODE_DONE && cur >= 0;
-            if (__any_sync(FULL, fin)) {
-                if (fin) { src.store((unsigned)cur, hit); cur = -1; }
-                const unsigned n_free = (unsigned)__popc(__ballot_sync(FULL, cur < 0));
-                if (n_free == 32u || (r_count && n_free >= (unsigned)refill)) break;
             }
         }
     }
