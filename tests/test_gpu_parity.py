@@ -270,3 +270,31 @@ def test_max_bounce_override_and_zero_bounce(Renderer, scene_root):
     c8 = dict(c); c8["max_bounce"] = 8
     acc, _ = _oracle(e, a, o, c8, 0).render(8)
     assert r8.max_bounce == 8 and rel_l2(r8.pixels.to_numpy(), acc / 8) < TOL
+
+
+def test_full_size_orb500k_window(Renderer, scene_root):
+    """BASELINE config 4 at full 1920x1080 (501 126 triangles: glass shell, GGX shell, Fresnel-blend core, 24 bounces): a
+    window of the full-size film against the oracle (its skip-pointer BVH path), plus size-independent properties."""
+    from adapt_b200.dist import tile_partition
+    from adapt_b200.scenes import ensure_big_meshes
+    ensure_big_meshes(scene_root, ("orb500k",))
+    e, a, o, c = load_scene(scene_root, "cbox", "orb500k.xml")
+    assert (c["film"]["width"], c["film"]["height"], c["max_bounce"]) == (1920, 1080, 24)
+    assert a["primitives"].shape[0] > 500000
+    r = Renderer(e, a, o, c, seed=0)
+    r.render_batch(2)
+    img = r.pixels.to_numpy()
+    st = r.stats()
+    assert img.shape == (1920, 1080, 3) and np.isfinite(img).all() and (img >= 0).all()
+    assert st["paths"] == 1920 * 1080 * 2 and st["paths"] <= st["rays_closest"] <= st["paths"] * 24
+    win = tile_partition(1920, 1080, 0, 1, window=(928, 992, 460, 508))          # 64 x 48 pixels through the orb
+    acc, cn = _oracle(e, a, o, c, 0).render(2, pixel_list=win)
+    ii, jj = win // 1080, win % 1080
+    got, want = img[ii, jj], acc[ii, jj] / 2
+    match, flipped = _flip_stats(got[None], want[None])
+    assert flipped < 0.05 and rel_l2(got[match[0]], want[match[0]]) < 2e-4
+    np.testing.assert_allclose(got.mean(axis=0), want.mean(axis=0), rtol=0.1)
+    # the same film from a renderer that only owns the window's pixels: identical samples (partition invariance)
+    rw = Renderer(e, a, o, c, seed=0, pixel_list=win)
+    rw.render_batch(2)
+    np.testing.assert_allclose(rw.pixels.to_numpy()[ii, jj], got, rtol=1e-5, atol=1e-6)
