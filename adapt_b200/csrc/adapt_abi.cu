@@ -204,17 +204,18 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         }
         __syncthreads();
         if (warp == 0) {
-            // exclusive prefix over (key major, warp minor): lane l owns entries 4l .. 4l+3
-            const int n_ent = LOGIC_NKEY * (LOGIC_BLOCK / 32);
-            unsigned v[4], sum = 0;
+            // exclusive prefix over (key major, warp minor): lane l owns LOGIC_EPL consecutive entries
+            constexpr int n_ent = LOGIC_NKEY * (LOGIC_BLOCK / 32);
+            constexpr int LOGIC_EPL = (n_ent + 31) / 32;
+            unsigned v[LOGIC_EPL], sum = 0;
             #pragma unroll
-            for (int q = 0; q < 4; q++) { const int e = (int)lane * 4 + q; v[q] = e < n_ent ? s_cnt[e] : 0u; sum += v[q]; }
+            for (int q = 0; q < LOGIC_EPL; q++) { const int e = (int)lane * LOGIC_EPL + q; v[q] = e < n_ent ? s_cnt[e] : 0u; sum += v[q]; }
             unsigned incl = sum;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
             unsigned run = incl - sum;
             #pragma unroll
-            for (int q = 0; q < 4; q++) { const int e = (int)lane * 4 + q; if (e < n_ent) s_cnt[e] = run; run += v[q]; }
+            for (int q = 0; q < LOGIC_EPL; q++) { const int e = (int)lane * LOGIC_EPL + q; if (e < n_ent) s_cnt[e] = run; run += v[q]; }
         }
         __syncthreads();
         s_perm[s_cnt[key * (LOGIC_BLOCK / 32) + warp] + my_rank] = (unsigned short)threadIdx.x;
