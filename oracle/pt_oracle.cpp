@@ -11,7 +11,8 @@
 // container).  The resulting golden vectors -- whole renders of 10 scene / flag combinations covering every BxDF,
 // emitter type, the brute-force and the BVH intersectors, and per-function eval / pdf / sample tables -- are committed
 // under tests/golden/ and checked by tests/test_reference_golden.py (this oracle, CPU) and its -m gpu half (CUDA path).
-// Further pins: closed-form known answers (tests/test_oracle_kat.py).  What stays unpinned is Taichi's LLVM fast-math
+// The SAH builder section is additionally checked, bit for bit, against the reference's own tracer/bvh/bvh.cpp compiled from
+// its sources (oracle/Makefile `ref` -> oracle/_ref/).  Further pins: closed-form known answers (tests/test_oracle_kat.py).  What stays unpinned is Taichi's LLVM fast-math
 // rounding, which only shows as ~1e-6 noise and rare threshold "flips" (DESIGN.md "Oracle").
 //
 // Reference files followed (paths relative to the reference root, commit f590925):
@@ -1451,6 +1452,12 @@ vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
 // ------------------------------------------------------------------------------------------------
 // tracer/bvh/bvh.cpp + bvh_helper.h -- recursive binned-SAH builder, restated without Eigen/pybind11
 // ------------------------------------------------------------------------------------------------
+// The reference's extension module is ordinary host C++ built without -march flags, i.e. without FMA contraction; SAH costs tie
+// often (symmetric meshes) and one ulp decides which bin wins, so this section is compiled the same way.  With that the four
+// arrays equal, bit for bit, those of the reference's own bvh.cpp compiled from its sources (oracle/Makefile `ref` target,
+// tests/test_reference_golden.py::test_oracle_bvh_builder_equals_compiled_reference).
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
 struct AABB {
     vec3 mini, maxi;
     AABB() : mini(1e4f), maxi(-1e4f) {}
@@ -1483,7 +1490,8 @@ BVHInfo make_bvh_info(const float* p9, int prim_idx, int obj_idx, bool is_sphere
             if (vget(d, i) < 1e-4f) { mnp[i] -= 1e-4f; mxp[i] += 1e-4f; }
         }
         b.bound = AABB(mn, mx);
-        b.centroid = vec3((c0.x + c1.x + c2.x) / 3.f, (c0.y + c1.y + c2.y) / 3.f, (c0.z + c1.z + c2.z) / 3.f);
+        // primitive.rowwise().mean() (bvh_helper.h:85): Eigen's unrolled reduction of three coefficients sums a0 + (a1 + a2)
+        b.centroid = vec3((c0.x + (c1.x + c2.x)) / 3.f, (c0.y + (c1.y + c2.y)) / 3.f, (c0.z + (c1.z + c2.z)) / 3.f);
     }
     return b;
 }
@@ -1614,6 +1622,7 @@ void bvh_build_impl(const float* prims, int n_prims, const int* obj_info2, int n
     }
     delete root;
 }
+#pragma GCC pop_options
 
 }  // namespace
 

@@ -198,3 +198,44 @@ def test_cuda_matches_reference_render(golden, scene_root, tag):
         assert flipped < 0.07, f"{flipped:.2%} of pixels hold a sample that differs"
         assert rel_l2(acc[match], ref[match]) < 5e-4
         np.testing.assert_allclose(acc.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-2)
+
+
+def _ref_bvh_cpp():
+    """The reference's own pybind11 module, compiled from tracer/bvh/bvh.cpp by `make -C oracle ref` (oracle/_ref/)."""
+    import glob
+    import importlib.util
+    hits = glob.glob(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "bvh_cpp*.so"))
+    if not hits:
+        pytest.skip("oracle/_ref/bvh_cpp*.so not built (needs the reference tree: make -C oracle ref)")
+    spec = importlib.util.spec_from_file_location("bvh_cpp", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("scene,name,big", [("cbox", "cbox.xml", None), ("test", "allbxdf.xml", None), ("cbox", "bunny90k.xml", "bunny90k")])
+def test_oracle_bvh_builder_equals_compiled_reference(scene_root, scene, name, big):
+    """The restated SAH builder (oracle/pt_oracle.cpp) against the reference's own bvh.cpp compiled from its sources:
+    all four arrays bit-identical (bvh_minmax, node_minmax, bvh_info, node_info), 34 ... 89 900 primitives."""
+    ref = _ref_bvh_cpp()
+    from oracle.pt_oracle import bvh_build as oracle_build
+    if big:
+        from adapt_b200.scenes import ensure_big_meshes
+        ensure_big_meshes(scene_root, (big,))
+    e, a, o, c = load_scene(scene_root, scene, name, 8, 8)
+    obj_info = np.zeros((2, len(o)), np.int32)
+    for k, ob in enumerate(o):
+        obj_info[0, k] = ob.meshes.shape[0]; obj_info[1, k] = ob.type
+    cam_t = np.float32(c["transform"][1])
+    lo = np.minimum(np.min([ob.aabb[0] for ob in o], axis=0), cam_t).astype(np.float32) - np.float32(0.1)     # path_tracer.py:130-138
+    hi = np.maximum(np.max([ob.aabb[1] for ob in o], axis=0), cam_t).astype(np.float32) + np.float32(0.1)
+    prims = np.ascontiguousarray(a["primitives"], np.float32)
+    want = ref.bvh_build(prims, obj_info, lo, hi)
+    got = oracle_build(prims, obj_info, lo, hi)
+    for w, g, what in zip(want, got, ("bvh_minmax", "node_minmax", "bvh_info", "node_info")):
+        np.testing.assert_array_equal(np.asarray(g).ravel(), np.asarray(w).ravel(), err_msg=what)
+    # the drop-in of boundary #2 returns the same shapes and a tree over the same primitives (its own SAH builder)
+    from adapt_b200 import bvh_cpp as dropin
+    mine = dropin.bvh_build(prims, obj_info, lo, hi)
+    assert mine[0].shape == np.asarray(want[0]).shape and mine[2].shape == np.asarray(want[2]).shape
+    assert sorted(mine[2].reshape(-1, 2)[:, 1].tolist()) == sorted(np.asarray(want[2]).reshape(-1, 2)[:, 1].tolist())
