@@ -169,12 +169,13 @@ template <int MATS>
 __global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort) {
+        const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort, const unsigned rot) {
     const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
     // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
     if (tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
-    // work stripe of this warp (pt_common.cuh: WorkStripe)
-    const int home = (int)((unsigned)(tslot >> 5) % PT_NSTRIPE);
+    // work stripe of this warp (pt_common.cuh: WorkStripe).  The window of four stripes a warp probes moves on with every
+    // launch, so a pool with fewer warps than stripes (tiny pools, tests) still reaches every stripe.
+    const int home = (int)(((unsigned)(tslot >> 5) + 4u * rot) % PT_NSTRIPE);
 
     // ---------------------------------------------------------------- block-local regrouping by material class
     // ncu on scenes with several surface models (orb500k: glass + GGX + Fresnel blend + Lambertian walls): 8.3 of 32 lanes
@@ -720,7 +721,7 @@ static int launch_iteration(adapt_handle* h) {
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
 #define LAUNCH_LOGIC(M) k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
-        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort)
+        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort, (unsigned)h->stats.iterations)
         // the instantiation that covers the scene's material groups (+ two-sided BRDFs, + texture lookups)
         const bool ts = (h->mats & M_TWOSIDED) != 0, tex = h->sv.textures != nullptr;
         if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
@@ -773,6 +774,8 @@ static int run_until(adapt_handle* h, Pred done) {
     CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (done(work_totals(h->h_work))) return 0;
+    WorkTotals last{~0ull, ~0ull};
+    int stale = 0;
     for (int guard = 0; guard < (1 << 26); guard++) {
         for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
         CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
@@ -780,7 +783,12 @@ static int run_until(adapt_handle* h, Pred done) {
         // overlap: queue the next batch before looking at this one's counters
         for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
         CK(cudaEventSynchronize(h->ev_poll));
-        if (done(work_totals(h->h_work))) return 0;
+        const WorkTotals now = work_totals(h->h_work);
+        if (done(now)) return 0;
+        // watchdog: every path ends within max_bounce iterations, so counters that stand still this long mean a scheduling bug
+        stale = (now.claimed == last.claimed && now.done == last.done) ? stale + 1 : 0;
+        last = now;
+        if (stale > 512) return set_error(ADAPT_ERR_STATE, "wavefront makes no progress (work counters unchanged for 4096 iterations)");
     }
     return set_error(ADAPT_ERR_STATE, "wavefront did not converge");
 }

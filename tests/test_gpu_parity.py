@@ -298,3 +298,31 @@ def test_full_size_orb500k_window(Renderer, scene_root):
     rw = Renderer(e, a, o, c, seed=0, pixel_list=win)
     rw.render_batch(2)
     np.testing.assert_allclose(rw.pixels.to_numpy()[ii, jj], got, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("w,h,pool", [(37, 23, 256), (1, 1, 0), (130, 3, 512)])
+def test_ragged_film_and_tiny_pool(Renderer, scene_root, w, h, pool):
+    """Film sizes that are not multiples of the 4 x 8 pixel patches / 32-item work groups, and a pool far smaller than the
+    film (256 slots: every slot is regenerated hundreds of times, work stripes run dry and are re-probed constantly)."""
+    e, a, o, c = load_scene(scene_root, "csphere", "balls-mono.xml", w, h)
+    r = Renderer(e, a, o, c, seed=11, pool_size=pool)
+    r.render_batch(3); r.render_batch(2)                       # two batches: the work-id space continues across calls
+    img = r.pixels.to_numpy()
+    st = r.stats()
+    acc, cn = _oracle(e, a, o, c, 11).render(5)
+    assert img.shape == (w, h, 3) and st["paths"] == cn["paths"] == w * h * 5
+    match, flipped = _flip_stats(img, acc / 5)
+    assert flipped <= max(0.05, 1.5 / (w * h)) and rel_l2(img[match], (acc / 5)[match]) < 1e-4
+    assert abs(st["rays_closest"] - cn["rays_closest_useful"]) <= max(3, 5e-3 * cn["rays_closest_useful"])
+
+
+def test_no_shadow_rays_and_no_mis(Renderer, scene_root):
+    """num_shadow_ray = 0: light only arrives through emission hits (the NEE loop is empty, inv_num_shadow_ray = 1)."""
+    e, a, o, c = load_scene(scene_root, "csphere", "balls-mono.xml", 40, 40, num_shadow_ray=0, use_mis=False)
+    r = Renderer(e, a, o, c, seed=2)
+    r.render_batch(16)
+    img = r.pixels.to_numpy()
+    acc, cn = _oracle(e, a, o, c, 2).render(16)
+    assert r.stats()["rays_shadow"] == 0 and cn["rays_shadow"] == 0
+    match, flipped = _flip_stats(img, acc / 16)
+    assert flipped < 0.05 and rel_l2(img[match], (acc / 16)[match]) < 1e-4 and img.max() > 0
