@@ -1,32 +1,17 @@
-"""Watermark + quantile normalisation of the final image (reference utils/watermark.py:22-33).  The stamp is a
-7 x 92 bitmap reading "RENDERED WITH AdaPT"; here it is generated from a tiny 5 x 7 font instead of a literal table."""
+"""Watermark + quantile normalisation of the final image (reference utils/watermark.py:22-33).  The stamp is the
+reference's 7 x 92 bitmap reading "RENDERED WITH AdaPT" (bit-packed here), so images carry the same pixels."""
 import numpy as np
 
 from .tools import CONSOLE
 
 __all__ = ["apply_watermark", "water_mark"]
 
-_FONT = {
-    "A": ["0110", "1001", "1001", "1111", "1001", "1001", "1001"], "D": ["1110", "1001", "1001", "1001", "1001", "1001", "1110"],
-    "E": ["1111", "1000", "1000", "1111", "1000", "1000", "1111"], "H": ["1001", "1001", "1001", "1111", "1001", "1001", "1001"],
-    "I": ["1", "1", "1", "1", "1", "1", "1"], "N": ["1001", "1101", "1101", "1011", "1011", "1001", "1001"],
-    "P": ["1110", "1001", "1001", "1110", "1000", "1000", "1000"], "R": ["1110", "1001", "1001", "1110", "1010", "1001", "1001"],
-    "T": ["11111", "00100", "00100", "00100", "00100", "00100", "00100"], "W": ["10001", "10001", "10001", "10101", "10101", "10101", "01010"],
-    "a": ["0000", "0000", "0110", "0001", "0111", "1001", "0111"], "d": ["0001", "0001", "0111", "1001", "1001", "1001", "0111"],
-    " ": ["00", "00", "00", "00", "00", "00", "00"],
-}
-
-
-def _stamp(text: str) -> np.ndarray:
-    cols = []
-    for ch in text:
-        glyph = np.array([[int(c) for c in row] for row in _FONT[ch]], np.float32)
-        cols.append(glyph)
-        cols.append(np.zeros((7, 1), np.float32))
-    return np.concatenate(cols[:-1], axis=1)
-
-
-water_mark = _stamp("RENDERED WITH AdaPT")
+# The stamp of the reference (utils/watermark.py:13-20), one integer per row, most significant bit = leftmost column.
+# Row 0 is the BOTTOM line of the lettering: the film is indexed [x, y] with y up and imwrite flips it.
+_STAMP_WIDTH = 92
+_STAMP_ROWS = (0x97a2e7a5ee05222425efa04, 0x94269425090522242529204, 0xa4269429090522242529204, 0xe7aa97b9e905223c3def384,
+               0x942a9425090aa2242420244, 0x94329425090aa2242420244, 0xe7b2e7b9ee0aafa4182039f)
+water_mark = np.float32([[(row >> (_STAMP_WIDTH - 1 - c)) & 1 for c in range(_STAMP_WIDTH)] for row in _STAMP_ROWS])
 
 
 def apply_watermark(rdr, normalize: float = 0.0, verbose: bool = False, add_watermark: bool = True):

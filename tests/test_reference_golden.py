@@ -239,3 +239,21 @@ def test_oracle_bvh_builder_equals_compiled_reference(scene_root, scene, name, b
     mine = dropin.bvh_build(prims, obj_info, lo, hi)
     assert mine[0].shape == np.asarray(want[0]).shape and mine[2].shape == np.asarray(want[2]).shape
     assert sorted(mine[2].reshape(-1, 2)[:, 1].tolist()) == sorted(np.asarray(want[2]).reshape(-1, 2)[:, 1].tolist())
+
+
+def test_watermark_matches_reference():
+    """utils/watermark.py of the reference (stamp bitmap, placement, quantile normalisation, crop) on a synthetic film."""
+    from adapt_b200.utils.watermark import apply_watermark, water_mark
+    g = np.load(os.path.join(HERE, "golden", "reference_watermark.npz"))
+    np.testing.assert_array_equal(water_mark, g["stamp"])
+
+    class Film:
+        def to_numpy(self):
+            return g["film"].copy()
+
+    class Rdr:
+        pixels = Film()
+    for tag, crop, norm, wm in (("plain", False, 0.0, True), ("norm", False, 0.99, True), ("nostamp", False, 0.0, False), ("crop", True, 0.0, True)):
+        r = Rdr()
+        r.do_crop, r.start_x, r.end_x, r.start_y, r.end_y = crop, 5, 30, 10, 60
+        np.testing.assert_allclose(apply_watermark(r, norm, False, wm), g[tag], rtol=1e-6, err_msg=tag)
