@@ -729,6 +729,8 @@ static int launch_iteration(adapt_handle* h) {
             else { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED); else LAUNCH_LOGIC(M_SIMPLE); }
         } else if ((h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) {
             if (tex) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF | M_TEXTURED); else LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
+        } else if (!ts && !tex) {
+            LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF);        // every model, one-sided: no inline shadow trace, half the stack
         } else {
             if (tex) LAUNCH_LOGIC(M_ALL | M_TEXTURED); else LAUNCH_LOGIC(M_ALL);
         }
