@@ -286,11 +286,17 @@ def run_b200(args):
         pool_slots = int(st.get("pool_slots") or args.pool or int(os.environ.get("ADAPT_POOL", 0)) or 0)
         logic_bytes = pool_slots * 192.0 + shadow_per_launch * 48.0
         traffic = logic_traffic = None
+        # ncu DRAM bytes per launch (profiles/ncu_summary.json) were captured on the default workload only
+        summary_ok = args.workload == "bunny90k" and not args.width
         try:
+            if not summary_ok:
+                raise KeyError("no ncu capture for this workload")
             logic_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("k_logic", {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         try:
+            if not summary_ok:
+                raise KeyError("no ncu capture for this workload")
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(kern, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
