@@ -227,7 +227,7 @@ k_classify(const PathPool pool, const ShadowQueue sq, Cursors* __restrict__ cur,
 // ================================================================================================
 // k_logic
 // ================================================================================================
-template <int MATS>
+template <int MATS, bool LISTED>
 __global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
@@ -235,7 +235,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         const unsigned* __restrict__ cls_items, const CursorStripe* __restrict__ cls_count, const KeySet keys) {
     const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
     // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
-    if (!cls_items && tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
+    if (!LISTED && tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
     // work stripe of this warp (pt_common.cuh: WorkStripe).  The window of four stripes a warp probes moves on with every
     // launch, so a pool with fewer warps than stripes (tiny pools, tests) still reaches every stripe.
     const int home = (int)(((unsigned)(tslot >> 5) + 4u * rot) % PT_NSTRIPE);
@@ -248,7 +248,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // then slots whose path ends, then free slots.  All accesses stay inside the block's own 256-slot window of the
     // pool, so DRAM traffic is unchanged; what it costs is 13 ballots, a 104-entry prefix sum and three barriers.
     int slot = tslot;
-    if (do_sort) {
+    if (!LISTED && do_sort) {
         __shared__ unsigned s_cnt[LOGIC_NKEY * (LOGIC_BLOCK / 32)];
         __shared__ unsigned short s_perm[LOGIC_BLOCK];
         const uint4 m0 = pool.misc[tslot];
@@ -287,7 +287,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         slot = blockIdx.x * LOGIC_BLOCK + (int)s_perm[threadIdx.x];
     }
 
-    if (cls_items) {
+    if (LISTED) {
         // listed mode (k_classify): global thread g works on the g-th entry of this launch's class lists, class after class
         unsigned g = (unsigned)tslot;
         slot = -1;
@@ -300,7 +300,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         }
         if (!__any_sync(0xffffffffu, slot >= 0)) return;              // past the end of the lists
     }
-    const bool listed_idle = slot < 0;                                // only in the last warp of a listed launch
+    const bool listed_idle = LISTED && slot < 0;                      // only in the last warp of a listed launch
     uint4 misc = listed_idle ? make_uint4(0u, 0u, 0u, 0u) : pool.misc[slot];
     bool alive = (misc.z & SLOT_ALIVE) != 0;
     // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
@@ -802,10 +802,11 @@ static int launch_iteration(adapt_handle* h) {
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
         const KeySet no_keys = {{-1, -1, -1, -1, -1, -1, -1, -1}};
-#define LAUNCH_LOGIC_L(M, ITEMS, KEYS) do { k_logic<M><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
-        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, (ITEMS) ? 0 : h->logic_sort, (unsigned)h->stats.iterations, \
-        (ITEMS), h->d_cls_count, (KEYS)); n_logic++; } while (0)
-#define LAUNCH_LOGIC(M) LAUNCH_LOGIC_L(M, (const unsigned*)nullptr, no_keys)
+#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { k_logic<M, LISTED><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
+        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort, (unsigned)h->stats.iterations, \
+        h->d_cls_items, h->d_cls_count, (KEYS)); n_logic++; } while (0)
+#define LAUNCH_LOGIC(M) LAUNCH_LOGIC_X(M, false, no_keys)
+#define LAUNCH_LOGIC_L(M, ITEMS, KEYS) LAUNCH_LOGIC_X(M, true, KEYS)
         // the instantiation that covers the scene's material groups (+ two-sided BRDFs, + texture lookups)
         const bool ts = (h->mats & M_TWOSIDED) != 0, tex = h->sv.textures != nullptr;
         if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
@@ -830,6 +831,7 @@ static int launch_iteration(adapt_handle* h) {
         }
 #undef LAUNCH_LOGIC
 #undef LAUNCH_LOGIC_L
+#undef LAUNCH_LOGIC_X
     }
     CK(cudaEventRecord(ev.e[1], st));
     const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t;
