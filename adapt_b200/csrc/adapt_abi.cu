@@ -231,7 +231,7 @@ template <int MATS, bool LISTED>
 __global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_hi, const long long cnt_origin, const int parity, const int do_sort, const unsigned rot,
+        const unsigned long long work_hi, const long long cnt_origin, const int parity, const unsigned rot,
         const unsigned* __restrict__ cls_items, const CursorStripe* __restrict__ cls_count, const KeySet keys) {
     const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
     // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
@@ -240,53 +240,9 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     // launch, so a pool with fewer warps than stripes (tiny pools, tests) still reaches every stripe.
     const int home = (int)(((unsigned)(tslot >> 5) + 4u * rot) % PT_NSTRIPE);
 
-    // ---------------------------------------------------------------- block-local regrouping by material class
-    // ncu on scenes with several surface models (orb500k: glass + GGX + Fresnel blend + Lambertian walls): 8.3 of 32 lanes
-    // active per instruction, because neighbouring slots hit different materials and every warp walks through every
-    // model's code.  The block therefore permutes its 256 slots among its threads so that threads of a warp work on
-    // slots of the same class: key = material class of the surface hit (leaf record -> hit word, no extra load),
-    // then slots whose path ends, then free slots.  All accesses stay inside the block's own 256-slot window of the
-    // pool, so DRAM traffic is unchanged; what it costs is 13 ballots, a 104-entry prefix sum and three barriers.
+    // Scenes that mix material groups run in "listed" mode: k_classify has sorted the slots into global per-class lists and this
+    // launch covers the classes in `keys` (see k_classify).  Otherwise thread t owns slot t.
     int slot = tslot;
-    if (!LISTED && do_sort) {
-        __shared__ unsigned s_cnt[LOGIC_NKEY * (LOGIC_BLOCK / 32)];
-        __shared__ unsigned short s_perm[LOGIC_BLOCK];
-        const uint4 m0 = pool.misc[tslot];
-        int key = LOGIC_NKEY - 1;                                           // free slot
-        if (m0.z & SLOT_ALIVE) {
-            const int hw = __float_as_int(pool.hit[tslot].w);
-            key = ((m0.z & SLOT_FINISH) || hw < 0) ? LOGIC_NKEY - 2          // path ends here: splat, then regenerate
-                                                   : min((hw >> PT_HIT_PRIM_BITS) & 15, LOGIC_NKEY - 3);
-        }
-        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        unsigned my_rank = 0;
-        #pragma unroll
-        for (int k = 0; k < LOGIC_NKEY; k++) {
-            const unsigned b = __ballot_sync(0xffffffffu, key == k);
-            if (key == k) my_rank = __popc(b & ((1u << lane) - 1u));
-            if (lane == 0) s_cnt[k * (LOGIC_BLOCK / 32) + warp] = __popc(b);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // exclusive prefix over (key major, warp minor): lane l owns LOGIC_EPL consecutive entries
-            constexpr int n_ent = LOGIC_NKEY * (LOGIC_BLOCK / 32);
-            constexpr int LOGIC_EPL = (n_ent + 31) / 32;
-            unsigned v[LOGIC_EPL], sum = 0;
-            #pragma unroll
-            for (int q = 0; q < LOGIC_EPL; q++) { const int e = (int)lane * LOGIC_EPL + q; v[q] = e < n_ent ? s_cnt[e] : 0u; sum += v[q]; }
-            unsigned incl = sum;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-            unsigned run = incl - sum;
-            #pragma unroll
-            for (int q = 0; q < LOGIC_EPL; q++) { const int e = (int)lane * LOGIC_EPL + q; if (e < n_ent) s_cnt[e] = run; run += v[q]; }
-        }
-        __syncthreads();
-        s_perm[s_cnt[key * (LOGIC_BLOCK / 32) + warp] + my_rank] = (unsigned short)threadIdx.x;
-        __syncthreads();
-        slot = blockIdx.x * LOGIC_BLOCK + (int)s_perm[threadIdx.x];
-    }
-
     if (LISTED) {
         // listed mode (k_classify): global thread g works on the g-th entry of this launch's class lists, class after class
         unsigned g = (unsigned)tslot;
@@ -744,7 +700,6 @@ struct adapt_handle {
     int trace_mode = 2;
     bool fuse_trace = true;
     bool wide_ok = true;
-    int logic_sort = 1;
     int logic_lists = 0;                      // global per-class slot lists + one k_logic launch per material group (k_classify)
     unsigned* d_cls_items = nullptr;          // [LOGIC_NKEY][n_slots]
     CursorStripe* d_cls_count = nullptr;      // [2][16]
@@ -801,36 +756,30 @@ static int launch_iteration(adapt_handle* h) {
     int n_logic = 0;
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
-        const KeySet no_keys = {{-1, -1, -1, -1, -1, -1, -1, -1}};
 #define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { k_logic<M, LISTED><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
-        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, h->logic_sort, (unsigned)h->stats.iterations, \
+        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, (unsigned)h->stats.iterations, \
         h->d_cls_items, h->d_cls_count, (KEYS)); n_logic++; } while (0)
-#define LAUNCH_LOGIC(M) LAUNCH_LOGIC_X(M, false, no_keys)
-#define LAUNCH_LOGIC_L(M, ITEMS, KEYS) LAUNCH_LOGIC_X(M, true, KEYS)
-        // the instantiation that covers the scene's material groups (+ two-sided BRDFs, + texture lookups)
+        // two-sided BRDFs and texture lookups are compile-time variants of every instantiation
+#define LAUNCH_LOGIC_V(M, LISTED, KEYS) do { \
+        if (ts && tex) LAUNCH_LOGIC_X((M) | M_TWOSIDED | M_TEXTURED, LISTED, KEYS); else if (ts) LAUNCH_LOGIC_X((M) | M_TWOSIDED, LISTED, KEYS); \
+        else if (tex) LAUNCH_LOGIC_X((M) | M_TEXTURED, LISTED, KEYS); else LAUNCH_LOGIC_X(M, LISTED, KEYS); } while (0)
         const bool ts = (h->mats & M_TWOSIDED) != 0, tex = h->sv.textures != nullptr;
-        if (!(h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF))) {
-            if (tex) { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED | M_TEXTURED); else LAUNCH_LOGIC(M_SIMPLE | M_TEXTURED); }
-            else { if (ts) LAUNCH_LOGIC(M_SIMPLE | M_TWOSIDED); else LAUNCH_LOGIC(M_SIMPLE); }
-        } else if (h->logic_lists && !tex) {
+        if (!h->logic_lists) {
+            // one material group (Lambertian / Phong / mirror / Oren-Nayar): thread t owns slot t
+            const KeySet no_keys = {{-1, -1, -1, -1, -1, -1, -1, -1}};
+            LAUNCH_LOGIC_V(M_SIMPLE, false, no_keys);
+        } else {
             // several material groups: global class lists, then one launch per group present (k_classify)
             k_classify<<<lg, LOGIC_BLOCK, 0, st>>>(h->pool, h->sq, h->d_cur, h->d_cls_items, h->d_cls_count, parity);
             n_logic++;
             const KeySet k_simple = {{0, 1, 2, 6, LOGIC_NKEY - 2, LOGIC_NKEY - 1, -1, -1}}, k_glossy = {{4, 5, -1, -1, -1, -1, -1, -1}};
             const KeySet k_coat = {{3, 7, -1, -1, -1, -1, -1, -1}}, k_bsdf = {{8, 9, 10, -1, -1, -1, -1, -1}};
-            if (ts) LAUNCH_LOGIC_L(M_SIMPLE | M_TWOSIDED, h->d_cls_items, k_simple); else LAUNCH_LOGIC_L(M_SIMPLE, h->d_cls_items, k_simple);
-            if (h->mats & M_GLOSSY) { if (ts) LAUNCH_LOGIC_L(M_SIMPLE | M_GLOSSY | M_TWOSIDED, h->d_cls_items, k_glossy); else LAUNCH_LOGIC_L(M_SIMPLE | M_GLOSSY, h->d_cls_items, k_glossy); }
-            if (h->mats & M_COAT_GGX) { if (ts) LAUNCH_LOGIC_L(M_SIMPLE | M_COAT_GGX | M_TWOSIDED, h->d_cls_items, k_coat); else LAUNCH_LOGIC_L(M_SIMPLE | M_COAT_GGX, h->d_cls_items, k_coat); }
-            if (h->mats & M_BSDF) LAUNCH_LOGIC_L(M_SIMPLE | M_BSDF, h->d_cls_items, k_bsdf);
-        } else if ((h->mats & ~(M_SIMPLE | M_GLOSSY | M_BSDF)) == 0) {
-            if (tex) LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF | M_TEXTURED); else LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_BSDF);
-        } else if (!ts && !tex) {
-            LAUNCH_LOGIC(M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF);        // every model, one-sided: no inline shadow trace, half the stack
-        } else {
-            if (tex) LAUNCH_LOGIC(M_ALL | M_TEXTURED); else LAUNCH_LOGIC(M_ALL);
+            LAUNCH_LOGIC_V(M_SIMPLE, true, k_simple);
+            if (h->mats & M_GLOSSY) LAUNCH_LOGIC_V(M_SIMPLE | M_GLOSSY, true, k_glossy);
+            if (h->mats & M_COAT_GGX) LAUNCH_LOGIC_V(M_SIMPLE | M_COAT_GGX, true, k_coat);
+            if (h->mats & M_BSDF) { if (tex) LAUNCH_LOGIC_X(M_SIMPLE | M_BSDF | M_TEXTURED, true, k_bsdf); else LAUNCH_LOGIC_X(M_SIMPLE | M_BSDF, true, k_bsdf); }
         }
-#undef LAUNCH_LOGIC
-#undef LAUNCH_LOGIC_L
+#undef LAUNCH_LOGIC_V
 #undef LAUNCH_LOGIC_X
     }
     CK(cudaEventRecord(ev.e[1], st));
@@ -1023,7 +972,6 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         }
         if (d->brdf_two_sides) need |= M_TWOSIDED;
         h->mats = need;
-        if (env_int("ADAPT_LOGIC_GENERIC", 0)) h->mats = M_ALL;
     }
     // ---- BVH (replaces bvh_process, tracer/path_tracer.py:143-179)
     BuildParams bp;
@@ -1170,8 +1118,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         h->trace_grid = prop.multiProcessorCount * per_sm;
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
-    h->logic_sort = env_int("ADAPT_LOGIC_SORT", (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) ? 1 : 0);
-    h->logic_lists = env_int("ADAPT_LOGIC_LISTS", 1) && (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) && !h->sv.textures;
+    h->logic_lists = (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) != 0;
     CKH(dev_alloc(h, &h->d_cls_count, (size_t)32)); CKC(cudaMemset(h->d_cls_count, 0, sizeof(CursorStripe) * 32));
     if (h->logic_lists) CKH(dev_alloc(h, &h->d_cls_items, (size_t)LOGIC_NKEY * (size_t)h->pool.n_slots));
     h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
