@@ -90,7 +90,7 @@ class adapt_stats(C.Structure):
 ABI_SYMBOLS = [
     "adapt_create", "adapt_destroy", "adapt_render", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
     "adapt_read_pixels", "adapt_host_alloc", "adapt_host_free",
-    "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch",
+    "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch", "adapt_bxdf_batch",
     "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version",
 ]
 
@@ -137,6 +137,8 @@ def load_library(path: Optional[str] = None):
     lib.adapt_reset_stats.restype = C.c_int
     lib.adapt_intersect_batch.argtypes = [H, _fp, _fp, _fp, C.c_int32, C.c_int32, _ip, _ip, _fp, _fp, _fp]
     lib.adapt_intersect_batch.restype = C.c_int
+    lib.adapt_bxdf_batch.argtypes = [H, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, C.c_uint64, _fp, _fp, _fp, _fp, _fp, _ip]
+    lib.adapt_bxdf_batch.restype = C.c_int
     lib.adapt_bvh_build.argtypes = [_fp, C.c_int32, _ip, C.c_int32, _fp, _fp,
                                     C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_ip), C.POINTER(_ip), _ip, _ip]
     lib.adapt_bvh_build.restype = C.c_int

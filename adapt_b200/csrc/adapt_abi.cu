@@ -672,6 +672,31 @@ __global__ void k_intersect_batch(const SceneView sv, int n, const float* __rest
     }
 }
 
+// stage-level test hook: the surface models as k_logic calls them (all groups compiled in)
+__global__ void k_bxdf_batch(const SceneView sv, const int obj, const int n, const float* __restrict__ ns_in, const float* __restrict__ ng_in,
+                             const float* __restrict__ incid_in, const float* __restrict__ out_in, const int two_sides, const uint64_t seed,
+                             float* __restrict__ ev, float* __restrict__ pdf, float* __restrict__ s_dir, float* __restrict__ s_spec,
+                             float* __restrict__ s_pdf, int* __restrict__ s_flag) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const Bxdf mat = load_bxdf(sv.bxdfs + obj);
+    Surf sf; sf.n_s = ld3(ns_in + (size_t)k * 3); sf.n_g = ld3(ng_in + (size_t)k * 3); sf.t = 1.f;
+    const float3 in = ld3(incid_in + (size_t)k * 3), out = ld3(out_in + (size_t)k * 3);
+    // brdf_two_sides: eval / surface_pdf / sample_new_ray flip both normals when the incident ray arrives from behind (:449-453)
+    Surf sb = sf;
+    if (two_sides && mat.kind == 0 && dot(in, sf.n_s) > 0.f) { sb.n_s = -sf.n_s; sb.n_g = -sf.n_g; }
+    const float3 e = mat.kind == 0 ? brdf_eval<M_ALL>(mat, sb, in, out) : bsdf_eval(mat, sf, in, out, sv.world_ior);
+    ev[(size_t)k * 3] = e.x; ev[(size_t)k * 3 + 1] = e.y; ev[(size_t)k * 3 + 2] = e.z;
+    pdf[k] = mat.kind == 0 ? brdf_pdf<M_ALL>(mat, sb, out, in) : bsdf_pdf(mat, sf, out, in, sv.world_ior);
+    Rng g; g.init(seed, (uint32_t)k, 0u);
+    float3 d, sp; float p; bool fl;
+    if (mat.kind == 0) brdf_sample<M_ALL>(mat, sb, in, g, d, sp, p, fl);
+    else bsdf_sample(mat, sf, in, sv.world_ior, g, d, sp, p, fl);
+    s_dir[(size_t)k * 3] = d.x; s_dir[(size_t)k * 3 + 1] = d.y; s_dir[(size_t)k * 3 + 2] = d.z;
+    s_spec[(size_t)k * 3] = sp.x; s_spec[(size_t)k * 3 + 1] = sp.y; s_spec[(size_t)k * 3 + 2] = sp.z;
+    s_pdf[k] = p; s_flag[k] = fl ? 1 : 0;
+}
+
 // ================================================================================================
 // handle
 // ================================================================================================
@@ -1284,6 +1309,36 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
     }
 #undef CKF
     cleanup();
+    return 0;
+}
+
+int adapt_bxdf_batch(adapt_handle* h, int32_t obj, int32_t n, const float* n_s, const float* n_g, const float* incid, const float* out,
+                     int32_t two_sides, uint64_t seed, float* eval3, float* pdf, float* s_dir3, float* s_spec3, float* s_pdf, int32_t* s_flag) {
+    if (!h || !n_s || !n_g || !incid || !out || !eval3 || !pdf || !s_dir3 || !s_spec3 || !s_pdf || !s_flag || n < 0)
+        return set_error(ADAPT_ERR_INVALID, "adapt_bxdf_batch: bad argument");
+    if (obj < 0 || obj >= h->sv.n_objects) return set_error(ADAPT_ERR_INVALID, "adapt_bxdf_batch: object index out of range");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const size_t n3 = (size_t)n * 3 * sizeof(float), n1 = (size_t)n * sizeof(float);
+    float* d_in = nullptr;      // [n_s | n_g | incid | out] then outputs [eval | s_dir | s_spec | pdf | s_pdf | flag]
+    CK(cudaMalloc(&d_in, 4 * n3 + 3 * n3 + 3 * n1));
+    float* d_ns = d_in; float* d_ng = d_ns + (size_t)n * 3; float* d_inc = d_ng + (size_t)n * 3; float* d_out = d_inc + (size_t)n * 3;
+    float* d_ev = d_out + (size_t)n * 3; float* d_sd = d_ev + (size_t)n * 3; float* d_ss = d_sd + (size_t)n * 3;
+    float* d_pdf = d_ss + (size_t)n * 3; float* d_sp = d_pdf + n; int* d_fl = reinterpret_cast<int*>(d_sp + n);
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    step(cudaMemcpy(d_ns, n_s, n3, cudaMemcpyHostToDevice)); step(cudaMemcpy(d_ng, n_g, n3, cudaMemcpyHostToDevice));
+    step(cudaMemcpy(d_inc, incid, n3, cudaMemcpyHostToDevice)); step(cudaMemcpy(d_out, out, n3, cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) {
+        k_bxdf_batch<<<(n + 127) / 128, 128, 0, h->stream>>>(h->sv, obj, n, d_ns, d_ng, d_inc, d_out, two_sides, seed, d_ev, d_pdf, d_sd, d_ss, d_sp, d_fl);
+        step(cudaGetLastError()); step(cudaStreamSynchronize(h->stream));
+        h->stats.kernel_launches += 1;
+    }
+    step(cudaMemcpy(eval3, d_ev, n3, cudaMemcpyDeviceToHost)); step(cudaMemcpy(s_dir3, d_sd, n3, cudaMemcpyDeviceToHost));
+    step(cudaMemcpy(s_spec3, d_ss, n3, cudaMemcpyDeviceToHost)); step(cudaMemcpy(pdf, d_pdf, n1, cudaMemcpyDeviceToHost));
+    step(cudaMemcpy(s_pdf, d_sp, n1, cudaMemcpyDeviceToHost)); step(cudaMemcpy(s_flag, d_fl, n1, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    if (e != cudaSuccess) return set_error(ADAPT_ERR_CUDA, std::string("adapt_bxdf_batch: ") + cudaGetErrorString(e));
     return 0;
 }
 

@@ -211,6 +211,19 @@ class Renderer:
             v.ctypes.data_as(fp)), "adapt_intersect_batch")
         return dict(obj=obj, prim=prim, t=t, u=u, v=v)
 
+    def bxdf_batch(self, obj: int, n_s, n_g, incid, out, two_sides: bool = False, seed: int = 0):
+        """Stage-level hook: eval / pdf / sample of object ``obj``'s surface model on the device (sample k draws from (seed, k, 0))."""
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        arrs = [np.ascontiguousarray(x, np.float32).reshape(-1, 3) for x in (n_s, n_g, incid, out)]
+        n = arrs[0].shape[0]
+        ev = np.zeros((n, 3), np.float32); sd = np.zeros((n, 3), np.float32); ss = np.zeros((n, 3), np.float32)
+        pdf = np.zeros(n, np.float32); sp = np.zeros(n, np.float32); fl = np.zeros(n, np.int32)
+        check(self._lib, self._lib.adapt_bxdf_batch(
+            self._handle, int(obj), n, *(x.ctypes.data_as(fp) for x in arrs), int(bool(two_sides)), int(seed),
+            ev.ctypes.data_as(fp), pdf.ctypes.data_as(fp), sd.ctypes.data_as(fp), ss.ctypes.data_as(fp), sp.ctypes.data_as(fp),
+            fl.ctypes.data_as(ip)), "adapt_bxdf_batch")
+        return dict(eval=ev, pdf=pdf, s_dir=sd, s_spec=ss, s_pdf=sp, s_flag=fl)
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle:
             self._lib.adapt_destroy(self._handle)

@@ -159,6 +159,13 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
                           int32_t n, int32_t any_hit, int32_t* hit_obj, int32_t* hit_prim,
                           float* hit_t, float* hit_u, float* hit_v);
 
+/* Stage-level hook for the surface models: PathTracer.eval / surface_pdf / sample_new_ray (tracer/path_tracer.py:424-494) of
+ * object `obj` on n tuples (n_s, n_g, incident, outgoing), [n*3] each.  Sample k draws from the RNG stream keyed (seed, k, 0).
+ * Outputs: eval [n*3], pdf [n], sampled direction [n*3], f*cos [n*3], sample pdf [n], is_specular [n]. */
+int adapt_bxdf_batch(adapt_handle* h, int32_t obj, int32_t n, const float* n_s, const float* n_g, const float* incid,
+                     const float* out, int32_t two_sides, uint64_t seed, float* eval3, float* pdf, float* s_dir3,
+                     float* s_spec3, float* s_pdf, int32_t* s_flag);
+
 /* Host SAH-BVH builder with the signature of the reference's pybind11 module
  * (tracer/bvh/bvh.cpp:274-285): DFS-linearised nodes with skip offsets.
  *   primitives [n_prims*9]; obj_info [2*n_objects] = (prim count row, is_sphere row);

@@ -257,3 +257,30 @@ def test_watermark_matches_reference():
         r = Rdr()
         r.do_crop, r.start_x, r.end_x, r.start_y, r.end_y = crop, 5, 30, 10, 60
         np.testing.assert_allclose(apply_watermark(r, norm, False, wm), g[tag], rtol=1e-6, err_msg=tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vset", ["A", "B"])
+def test_cuda_bxdf_models_match_reference(scene_root, vset):
+    """The device code of every BRDF / BSDF (csrc/pt_shade.cuh, through adapt_bxdf_batch) against the reference's own
+    eval / surface_pdf / sample_new_ray tables: same tolerances as the oracle's half of this test."""
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from adapt_b200.build import build
+    build()
+    from adapt_b200.renderer.vanilla_renderer import Renderer
+    g = np.load(BX)
+    e, a, o, c = load_scene(scene_root, "test", "allbxdf.xml", 4, 4)
+    r = Renderer(e, a, o, c)
+    n_obj, N = g[vset + "/pdf"].shape
+    assert n_obj == len(o)
+    seed, ts = int(g["seed"]), int(g[vset + "/two_sides"])
+    for ob in range(n_obj):
+        got = r.bxdf_batch(ob, g[vset + "/n_s"][ob], g[vset + "/n_g"][ob], g[vset + "/incid"][ob], g[vset + "/out"][ob], bool(ts), seed)
+        name = str(g["names"][ob])
+        assert _relerr(got["eval"], g[vset + "/eval"][ob]) < 5e-4, name
+        assert _relerr(got["pdf"], g[vset + "/pdf"][ob]) < 5e-4, name
+        assert np.abs(got["s_dir"] - g[vset + "/s_dir"][ob]).max() < 2e-5, name
+        assert _relerr(got["s_spec"], g[vset + "/s_spec"][ob]) < 5e-4, name
+        assert _relerr(got["s_pdf"], g[vset + "/s_pdf"][ob]) < 5e-4, name
+        np.testing.assert_array_equal(got["s_flag"], g[vset + "/s_flag"][ob])
