@@ -65,7 +65,9 @@ class adapt_scene_desc(C.Structure):
         ("device_id", C.c_int32), ("n_pixels", C.c_int32),
         ("pixel_list", _ip),
         ("pool_size", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("accelerator", C.c_int32),
+        ("bvh_builder", C.c_int32),
+        ("reserved", C.c_int32 * 5),
         ("textures", C.c_void_p),
         ("tex_image", _fp * 3),
         ("tex_size", C.c_int32 * 3),
@@ -91,6 +93,7 @@ ABI_SYMBOLS = [
     "adapt_create", "adapt_destroy", "adapt_render", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
     "adapt_read_pixels", "adapt_host_alloc", "adapt_host_free",
     "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch", "adapt_bxdf_batch",
+    "adapt_bvh_export", "adapt_update_geometry",
     "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version",
 ]
 
@@ -139,6 +142,10 @@ def load_library(path: Optional[str] = None):
     lib.adapt_intersect_batch.restype = C.c_int
     lib.adapt_bxdf_batch.argtypes = [H, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, C.c_int32, C.c_uint64, _fp, _fp, _fp, _fp, _fp, _ip]
     lib.adapt_bxdf_batch.restype = C.c_int
+    lib.adapt_bvh_export.argtypes = [H, _ip, _ip, _ip, _ip, _fp, _fp, _fp]
+    lib.adapt_bvh_export.restype = C.c_int
+    lib.adapt_update_geometry.argtypes = [H, _fp, _fp, _fp]
+    lib.adapt_update_geometry.restype = C.c_int
     lib.adapt_bvh_build.argtypes = [_fp, C.c_int32, _ip, C.c_int32, _fp, _fp,
                                     C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_ip), C.POINTER(_ip), _ip, _ip]
     lib.adapt_bvh_build.restype = C.c_int
@@ -181,7 +188,8 @@ class PackedScene:
 
 
 def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed: int = 0, device_id: int = 0,
-               pixel_list: Optional[np.ndarray] = None, pool_size: int = 0, max_bounce: Optional[int] = None) -> PackedScene:
+               pixel_list: Optional[np.ndarray] = None, pool_size: int = 0, max_bounce: Optional[int] = None,
+               bvh_builder=0) -> PackedScene:
     ps = PackedScene()
     d = ps.desc
     film = prop["film"]
@@ -292,8 +300,9 @@ def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed
         d.n_pixels = 0
         d.pixel_list = None
     d.pool_size = int(pool_size)
-    # reserved[0]: the reference's accelerator switch. The CUDA path always uses its BVH; the oracle
+    # the reference's accelerator switch. The CUDA path always uses its BVH; the oracle
     # follows the reference and picks brute force unless the XML asked for "bvh".
-    d.reserved[0] = 1 if prop.get("accelerator", "none") == "bvh" else 0
+    d.accelerator = 1 if prop.get("accelerator", "none") == "bvh" else 0
+    d.bvh_builder = {"sah": 0, "host": 0, "lbvh": 1, "device": 1}[bvh_builder] if isinstance(bvh_builder, str) else int(bvh_builder)
     ps.host.update(dict(num_objects=len(objects), num_prims=n_prims, src_num=len(emitters)))
     return ps

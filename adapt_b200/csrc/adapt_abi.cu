@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "bvh_device.h"
 #include "pt_common.cuh"
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
@@ -725,11 +727,21 @@ struct adapt_handle {
     int trace_mode = 2;
     bool fuse_trace = true;
     bool wide_ok = true;
+    int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH (bvh_device.cu)
+    int bvh_nodes = 0, bvh_depth = 0;
+    float bvh_build_ms = 0.f;
+    BuildParams bvh_params;
+    // host tables kept for adapt_update_geometry (the scene's topology: which object / class each primitive belongs to)
+    std::vector<uint8_t> sph, obj_class;
+    std::vector<int32_t> prim_obj;
+    bool has_ns = false;
+    float4* d_prim_geom = nullptr;            // writable aliases of sv.prim_geom / sv.prim_shade
+    float4* d_prim_shade = nullptr;
     int logic_lists = 0;                      // global per-class slot lists + one k_logic launch per material group (k_classify)
     unsigned* d_cls_items = nullptr;          // [LOGIC_NKEY][n_slots]
     CursorStripe* d_cls_count = nullptr;      // [2][16]
     unsigned iter_parity = 0;
-    int refill = 16, leaf_t = 12;
+    int refill = 16, leaf_t = 12, node_steps = 1;
     bool count_nodes = false;
     // timing
     struct IterEvents { cudaEvent_t e[4]; };
@@ -808,7 +820,7 @@ static int launch_iteration(adapt_handle* h) {
 #undef LAUNCH_LOGIC_X
     }
     CK(cudaEventRecord(ev.e[1], st));
-    const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t;
+    const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t | (h->node_steps << 8);   // node steps per scheduling round ride in the high bits
     if (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) {
         CK(cudaEventRecord(ev.e[2], st));          // fused: the whole trace time is booked under "closest"
         if (h->trace_mode == 2) k_trace<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
@@ -903,6 +915,91 @@ int adapt_bvh_build(const float* primitives, int32_t n_prims, const int32_t* obj
     return 0;
 }
 
+// ---- geometry tables (tracer_base.py:117-134 load_primitives): per-primitive (v0, e1, e2) / (centre, r) and normals
+static void pack_geometry(const float* primitives, const float* n_g, const float* n_s, int np, const std::vector<uint8_t>& sph,
+                          const std::vector<int32_t>& prim_obj, std::vector<float4>& prim_geom, std::vector<float4>& prim_shade) {
+    prim_geom.resize((size_t)np * 3); prim_shade.resize((size_t)np * 4);
+    for (int k = 0; k < np; k++) {
+        const float* v = primitives + (size_t)k * 9;
+        if (sph[k]) {
+            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], v[3]);
+            prim_geom[k * 3 + 1] = make_float4(0, 0, 0, 0);
+            prim_geom[k * 3 + 2] = make_float4(0, 0, 0, 0);
+        } else {
+            float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
+            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], e1[0]);
+            prim_geom[k * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+            prim_geom[k * 3 + 2] = make_float4(e2[2], 0, 0, 0);
+        }
+        const float* ng = n_g + (size_t)k * 3;
+        uint32_t ob = (uint32_t)prim_obj[k] | (sph[k] ? 0x80000000u : 0u);
+        float obf; std::memcpy(&obf, &ob, 4);
+        prim_shade[k * 4 + 0] = make_float4(ng[0], ng[1], ng[2], obf);
+        if (n_s) {
+            const float* q = n_s + (size_t)k * 9;
+            prim_shade[k * 4 + 1] = make_float4(q[0], q[1], q[2], q[3]);
+            prim_shade[k * 4 + 2] = make_float4(q[4], q[5], q[6], q[7]);
+            prim_shade[k * 4 + 3] = make_float4(q[8], 0, 0, 0);
+        } else {
+            prim_shade[k * 4 + 1] = prim_shade[k * 4 + 2] = prim_shade[k * 4 + 3] = make_float4(0, 0, 0, 0);
+        }
+    }
+}
+
+static void dev_release(adapt_handle* h, const void* p) {
+    if (!p) return;
+    auto it = std::find(h->allocs.begin(), h->allocs.end(), const_cast<void*>(p));
+    if (it != h->allocs.end()) { cudaFree(*it); h->allocs.erase(it); }
+}
+
+// ---- acceleration structure (replaces bvh_process, tracer/path_tracer.py:143-179) with the handle's builder; a previous
+// structure is released first (the handle must be idle).  Also sets the padded scene bounds.
+static int build_accel(adapt_handle* h, const float* primitives) {
+    SceneView& sv = h->sv;
+    const int np = sv.n_prims, no = sv.n_objects;
+    dev_release(h, sv.nodes); dev_release(h, sv.nodes4); dev_release(h, sv.leaf_prims);
+    sv.nodes = nullptr; sv.nodes4 = nullptr; sv.leaf_prims = nullptr;
+    float root_lo[3], root_hi[3];
+    if (h->bvh_builder == 1) {
+        // device build: linear BVH straight into the traversal layout; no 4-wide tree
+        DeviceBvh db; std::string what;
+        cudaError_t be = build_bvh_device(primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), np, no, h->bvh_params.max_leaf,
+                                          h->stream, db, what);
+        if (be != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH build: " + what + ": " + cudaGetErrorString(be));
+        h->allocs.push_back(db.nodes); h->allocs.push_back(db.leaf_prims);
+        sv.nodes = db.nodes; sv.leaf_prims = db.leaf_prims;
+        if (db.depth > PT_STACK_SIZE) return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack (use the host builder for this scene)");
+        h->wide_ok = false;
+        h->bvh_nodes = db.n_nodes; h->bvh_depth = db.depth; h->bvh_build_ms = db.build_ms;
+        for (int a = 0; a < 3; a++) { root_lo[a] = db.root_lo[a]; root_hi[a] = db.root_hi[a]; }
+    } else {
+        const auto t0 = std::chrono::steady_clock::now();
+        BuildResult br;
+        build_bvh(primitives, h->sph.data(), np, h->bvh_params, br);
+        GpuBvh gb;
+        to_gpu_layout(br, primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), gb);
+        h->bvh_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (gb.depth > PT_STACK_SIZE) return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack");
+        float4* tmp4 = nullptr;
+        int rc;
+        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes.data()), gb.nodes.size() * 4))) return rc;
+        sv.nodes = tmp4;
+        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes4.data()), gb.nodes4.size() * 8))) return rc;
+        sv.nodes4 = tmp4;
+        h->wide_ok = 3 * gb.depth4 + 1 <= PT_STACK_SIZE;         // a 4-wide step can push three entries
+        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3))) return rc;
+        sv.leaf_prims = tmp4;
+        h->bvh_nodes = (int)gb.nodes.size(); h->bvh_depth = gb.depth;
+        const Aabb& rb = br.nodes[0].box;
+        for (int a = 0; a < 3; a++) { root_lo[a] = rb.lo[a]; root_hi[a] = rb.hi[a]; }
+    }
+    // scene bounds (root of the BVH), padded: used to finish camera rays that cannot hit anything
+    const float pad = 1e-3f;
+    sv.world_lo = mk3(root_lo[0] - pad, root_lo[1] - pad, root_lo[2] - pad);
+    sv.world_hi = mk3(root_hi[0] + pad, root_hi[1] + pad, root_hi[2] + pad);
+    return 0;
+}
+
 void adapt_destroy(adapt_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -944,8 +1041,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
 
     const int np = d->n_prims, no = d->n_objects;
     // ---- per-primitive tables
-    std::vector<uint8_t> sph((size_t)np, 0);
-    std::vector<int32_t> prim_obj((size_t)np, -1);
+    std::vector<uint8_t>& sph = h->sph; sph.assign((size_t)np, 0);
+    std::vector<int32_t>& prim_obj = h->prim_obj; prim_obj.assign((size_t)np, -1);
     std::vector<int4> obj_info((size_t)no);
     for (int o = 0; o < no; o++) {
         int first = d->obj_info[o * 3], cnt = d->obj_info[o * 3 + 1], type = d->obj_info[o * 3 + 2];
@@ -960,32 +1057,9 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         if (d->emitters[e].type == 1 && (d->emitters[e].obj_ref_id < 0 || d->emitters[e].obj_ref_id >= no))
             return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: area emitter is not attached to an object"));
 
-    std::vector<float4> prim_geom((size_t)np * 3), prim_shade((size_t)np * 4);
-    for (int k = 0; k < np; k++) {
-        const float* v = d->primitives + (size_t)k * 9;
-        if (sph[k]) {
-            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], v[3]);
-            prim_geom[k * 3 + 1] = make_float4(0, 0, 0, 0);
-            prim_geom[k * 3 + 2] = make_float4(0, 0, 0, 0);
-        } else {
-            float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
-            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], e1[0]);
-            prim_geom[k * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
-            prim_geom[k * 3 + 2] = make_float4(e2[2], 0, 0, 0);
-        }
-        const float* ng = d->n_g + (size_t)k * 3;
-        uint32_t ob = (uint32_t)prim_obj[k] | (sph[k] ? 0x80000000u : 0u);
-        float obf; std::memcpy(&obf, &ob, 4);
-        prim_shade[k * 4 + 0] = make_float4(ng[0], ng[1], ng[2], obf);
-        if (d->n_s) {
-            const float* s = d->n_s + (size_t)k * 9;
-            prim_shade[k * 4 + 1] = make_float4(s[0], s[1], s[2], s[3]);
-            prim_shade[k * 4 + 2] = make_float4(s[4], s[5], s[6], s[7]);
-            prim_shade[k * 4 + 3] = make_float4(s[8], 0, 0, 0);
-        } else {
-            prim_shade[k * 4 + 1] = prim_shade[k * 4 + 2] = prim_shade[k * 4 + 3] = make_float4(0, 0, 0, 0);
-        }
-    }
+    std::vector<float4> prim_geom, prim_shade;
+    pack_geometry(d->primitives, d->n_g, d->n_s, np, sph, prim_obj, prim_geom, prim_shade);
+    h->has_ns = d->n_s != nullptr;
     // ---- which k_logic specialisation covers this scene
     {
         int need = M_SIMPLE;
@@ -999,29 +1073,22 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         h->mats = need;
     }
     // ---- BVH (replaces bvh_process, tracer/path_tracer.py:143-179)
-    BuildParams bp;
-    bp.max_leaf = std::min(8, std::max(1, env_int("ADAPT_BVH_MAX_LEAF", 4)));
-    bp.traverse_cost = (float)env_int("ADAPT_BVH_TRAV_COST_X10", 10) * 0.1f;
-    BuildResult br;
-    build_bvh(d->primitives, sph.data(), np, bp, br);
-    GpuBvh gb;
-    std::vector<uint8_t> obj_class((size_t)no, 0);
+    h->bvh_params.max_leaf = std::min(8, std::max(1, env_int("ADAPT_BVH_MAX_LEAF", 4)));
+    h->bvh_params.traverse_cost = (float)env_int("ADAPT_BVH_TRAV_COST_X10", 10) * 0.1f;
+    h->obj_class.assign((size_t)no, 0);
     for (int o = 0; o < no; o++) {
         const adapt_bxdf& b = d->bxdfs[o];
-        obj_class[o] = (uint8_t)(b.kind == 0 ? std::min(std::max(b.type, 0), 7) : (b.type == 0 ? 8 : (b.type == 1 ? 9 : 10)));
+        h->obj_class[o] = (uint8_t)(b.kind == 0 ? std::min(std::max(b.type, 0), 7) : (b.type == 0 ? 8 : (b.type == 1 ? 9 : 10)));
     }
     if (np >= (1 << PT_HIT_PRIM_BITS)) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: more than 2^27 primitives"));
-    to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), obj_class.data(), gb);
-    if (gb.depth > PT_STACK_SIZE) return fail(set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack"));
-
+    h->bvh_builder = d->bvh_builder ? d->bvh_builder : env_int("ADAPT_BVH_BUILDER", 0);
+    if (h->bvh_builder != 0 && h->bvh_builder != 1) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (host SAH) or 1 (device LBVH)"));
     SceneView& sv = h->sv;
+    sv.n_objects = no; sv.n_prims = np;
+    CKH(build_accel(h, d->primitives));
     float4* tmp4 = nullptr;
-    CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes.data()), gb.nodes.size() * 4)); sv.nodes = tmp4;
-    CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes4.data()), gb.nodes4.size() * 8)); sv.nodes4 = tmp4;
-    h->wide_ok = 3 * gb.depth4 + 1 <= PT_STACK_SIZE;         // a 4-wide step can push three entries
-    CKH(dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3)); sv.leaf_prims = tmp4;
-    CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4;
-    CKH(dev_upload(h, &tmp4, prim_shade.data(), prim_shade.size())); sv.prim_shade = tmp4;
+    CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4; h->d_prim_geom = tmp4;
+    CKH(dev_upload(h, &tmp4, prim_shade.data(), prim_shade.size())); sv.prim_shade = tmp4; h->d_prim_shade = tmp4;
     adapt_bxdf* dbx = nullptr; CKH(dev_upload(h, &dbx, d->bxdfs, (size_t)no)); sv.bxdfs = dbx;
     // ---- textures: descriptors, per-primitive uv, RGBA-float atlases
     sv.textures = nullptr; sv.prim_uv = nullptr;
@@ -1071,11 +1138,6 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     sv.inv_num_shadow_ray = d->num_shadow_ray > 0 ? 1.f / (float)d->num_shadow_ray : 1.f;
     sv.seed = d->seed;
     {
-        // scene bounds (root of the BVH), padded: used to finish camera rays that cannot hit anything
-        const Aabb& rb = br.nodes[0].box;
-        const float pad = 1e-3f;
-        sv.world_lo = mk3(rb.lo[0] - pad, rb.lo[1] - pad, rb.lo[2] - pad);
-        sv.world_hi = mk3(rb.hi[0] + pad, rb.hi[1] + pad, rb.hi[2] + pad);
         sv.cull_primary = env_int("ADAPT_CULL_PRIMARY", 0);
     }
     h->width = d->width; h->height = d->height;
@@ -1148,6 +1210,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     if (h->logic_lists) CKH(dev_alloc(h, &h->d_cls_items, (size_t)LOGIC_NKEY * (size_t)h->pool.n_slots));
     h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
     h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 12)));
+    h->node_steps = std::min(8, std::max(1, env_int("ADAPT_NODE_STEPS", 1)));
     h->ev_ring.resize(512);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
     CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));
@@ -1309,6 +1372,38 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
     }
 #undef CKF
     cleanup();
+    return 0;
+}
+
+int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s) {
+    if (!h || !primitives || !n_g) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: null argument");
+    if (h->has_ns && !n_s) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: the scene was created with vertex normals, n_s is required");
+    CK(cudaSetDevice(h->device));
+    int rc = adapt_sync(h);                                      // nothing may still be tracing through the old structure
+    if (rc) return rc;
+    const int np = h->sv.n_prims;
+    std::vector<float4> prim_geom, prim_shade;
+    pack_geometry(primitives, n_g, h->has_ns ? n_s : nullptr, np, h->sph, h->prim_obj, prim_geom, prim_shade);
+    CK(cudaMemcpyAsync(h->d_prim_geom, prim_geom.data(), prim_geom.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_prim_shade, prim_shade.data(), prim_shade.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = build_accel(h, primitives);
+    if (rc) return rc;
+    if (h->trace_mode == 2 && !h->wide_ok) h->trace_mode = 1;
+    return 0;
+}
+
+int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_t* depth, int32_t* builder, float* build_ms,
+                     float* nodes_out, float* prims_out) {
+    if (!h) return set_error(ADAPT_ERR_INVALID, "adapt_bvh_export: null handle");
+    if (n_nodes) *n_nodes = h->bvh_nodes;
+    if (n_prims) *n_prims = h->sv.n_prims;
+    if (depth) *depth = h->bvh_depth;
+    if (builder) *builder = h->bvh_builder;
+    if (build_ms) *build_ms = h->bvh_build_ms;
+    CK(cudaSetDevice(h->device));
+    if (nodes_out) CK(cudaMemcpy(nodes_out, h->sv.nodes, (size_t)h->bvh_nodes * 16 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (prims_out) CK(cudaMemcpy(prims_out, h->sv.leaf_prims, (size_t)h->sv.n_prims * 12 * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -1,0 +1,25 @@
+// bvh_device.h -- device-side BVH build (linear BVH, see bvh_lbvh.h) into the traversal layout of bvh_build.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+namespace adapt {
+
+struct DeviceBvh {
+    float4* nodes = nullptr;        // [n_nodes * 4], cudaMalloc'ed, owned by the caller after a successful build
+    float4* leaf_prims = nullptr;   // [n_prims * 3], same
+    int32_t n_nodes = 0;
+    int32_t depth = 0;              // longest chain of inner nodes = entries the traversal stack may need
+    float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+    float build_ms = 0.f;           // CUDA-event time of the kernels and the sort (uploads excluded)
+};
+
+// Host inputs as adapt_create holds them: primitives [n*9], sphere flags [n], object of each primitive [n], material class
+// of each object [n_objects].  Runs on `stream` and synchronises it.  Returns cudaSuccess or the failing call's error;
+// `what` then names the call.
+cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj, const uint8_t* obj_class,
+                             int32_t n, int32_t n_objects, int max_leaf, cudaStream_t stream, DeviceBvh& out, std::string& what);
+
+}  // namespace adapt

@@ -203,9 +203,11 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 //                  void store(unsigned i, const HitRec& h);   (closest hit: the record; any hit: h.prim >= 0 means occluded)
 // ------------------------------------------------------------------------------------------------
 template <bool ANY_HIT, bool COUNT, bool WIDE, typename Source>
-PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, const int refill, const int leaf_t,
+PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, const int refill, const int leaf_t_packed,
                             unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
     const unsigned FULL = 0xffffffffu;
+    const int leaf_t = leaf_t_packed & 0xff;
+    const int node_steps = (leaf_t_packed >> 8) > 0 ? (leaf_t_packed >> 8) : 1;   // node steps per scheduling round (warp-uniform)
     const unsigned lane = threadIdx.x & 31;
     const float4* __restrict__ nodes = sc.nodes;
     const float4* __restrict__ prims = sc.leaf_prims;
@@ -266,6 +268,7 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
         }
         if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)
         while (true) {
+            for (int step = 0; step < node_steps; step++)
             if (node >= 0) {
                 if (COUNT) n_nodes++;
                 if (WIDE) {

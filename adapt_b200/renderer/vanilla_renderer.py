@@ -63,11 +63,13 @@ class _Counter:
 class Renderer:
     def __init__(self, emitters: List, array_info: dict, objects: List, prop: dict, *, seed: int = 0,
                  device_id: int = 0, pixel_list: Optional[np.ndarray] = None, pool_size: int = 0,
-                 max_bounce: Optional[int] = None):
+                 max_bounce: Optional[int] = None, bvh_builder=0):
+        """bvh_builder: 0 / "sah" = host binned-SAH build (default), 1 / "lbvh" = linear BVH built on the device."""
         self.clock = TicToc()
         self._lib = load_library()
         self._packed = pack_scene(emitters, array_info, objects, prop, seed=seed, device_id=device_id,
-                                  pixel_list=pixel_list, pool_size=pool_size, max_bounce=max_bounce)
+                                  pixel_list=pixel_list, pool_size=pool_size, max_bounce=max_bounce,
+                                  bvh_builder=bvh_builder)
         host = self._packed.host
         # attributes the reference driver / watermark / checkpoint code read
         for key in ("w", "h", "crop_x", "crop_y", "crop_rx", "crop_ry", "do_crop", "start_x", "end_x", "start_y",
@@ -210,6 +212,42 @@ class Renderer:
             int(any_hit), obj.ctypes.data_as(ip), prim.ctypes.data_as(ip), t.ctypes.data_as(fp), u.ctypes.data_as(fp),
             v.ctypes.data_as(fp)), "adapt_intersect_batch")
         return dict(obj=obj, prim=prim, t=t, u=u, v=v)
+
+    def update_geometry(self, primitives, n_g, n_s=None):
+        """New vertex positions for the same topology (animated meshes): (N,3,3) primitives, (N,3) geometric normals and, when
+        the scene has vertex normals, (N,3,3) shading normals -- the arrays of ``array_info``.  Rebuilds the acceleration
+        structure with this renderer's builder; the accumulation buffer is kept (``reset_accumulation()`` starts over)."""
+        fp = C.POINTER(C.c_float)
+        n = self.num_prims
+        pr = np.ascontiguousarray(primitives, np.float32).reshape(-1)
+        ng = np.ascontiguousarray(n_g, np.float32).reshape(-1)
+        if pr.size != n * 9 or ng.size != n * 3:
+            raise ValueError(f"update_geometry: expected {n} primitives")
+        ns = None
+        if n_s is not None:
+            ns = np.ascontiguousarray(n_s, np.float32).reshape(-1)
+            if ns.size != n * 9:
+                raise ValueError(f"update_geometry: expected {n} x 3 shading normals")
+        check(self._lib, self._lib.adapt_update_geometry(self._handle, pr.ctypes.data_as(fp), ng.ctypes.data_as(fp),
+                                                         None if ns is None else ns.ctypes.data_as(fp)), "adapt_update_geometry")
+
+    def reset_accumulation(self):
+        self._load_accum(np.zeros((self.w, self.h, 3), np.float32), 0)
+
+    def bvh_export(self, arrays: bool = True) -> dict:
+        """Stage-level hook: the device acceleration structure (64-byte nodes, 48-byte leaf records), its builder and build time."""
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        nn, npr, dep, bld = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        ms = C.c_float()
+        check(self._lib, self._lib.adapt_bvh_export(self._handle, C.byref(nn), C.byref(npr), C.byref(dep), C.byref(bld), C.byref(ms),
+                                                    None, None), "adapt_bvh_export")
+        out = dict(n_nodes=nn.value, n_prims=npr.value, depth=dep.value, builder=bld.value, build_ms=ms.value)
+        if arrays:
+            nodes = np.zeros((nn.value, 16), np.float32); prims = np.zeros((npr.value, 12), np.float32)
+            check(self._lib, self._lib.adapt_bvh_export(self._handle, None, None, None, None, None, nodes.ctypes.data_as(fp),
+                                                        prims.ctypes.data_as(fp)), "adapt_bvh_export")
+            out.update(nodes=nodes, prims=prims)
+        return out
 
     def bxdf_batch(self, obj: int, n_s, n_g, incid, out, two_sides: bool = False, seed: int = 0):
         """Stage-level hook: eval / pdf / sample of object ``obj``'s surface model on the device (sample k draws from (seed, k, 0))."""

@@ -309,6 +309,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})",
                        "spp_per_step": spp_step, "pool_slots": pool_slots,
+                       "bvh": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in rdr.bvh_export(arrays=False).items()
+                               if k in ("builder", "n_nodes", "depth", "build_ms")},
                        "parallelism": f"tile-split x{world}" if world > 1 else "single GPU",
                        "l2": "path pool + queues (>200 MB) stream through HBM every wavefront iteration (> 126 MB L2); the BVH stays L2-resident by design"},
             "spp_per_s": paths / (w * h) / (ms * 1e-3),

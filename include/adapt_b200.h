@@ -95,7 +95,10 @@ typedef struct {
     int32_t n_pixels;           /* pixels owned by this handle (tile partition), 0 = whole film / crop window */
     const int32_t* pixel_list;  /* [n_pixels] film indices i*height + j owned by this handle, or NULL        */
     int32_t pool_size;          /* path slots kept in flight, 0 = auto                                       */
-    int32_t reserved[7];
+    int32_t accelerator;        /* the reference's <string name="accelerator"> switch: 1 = "bvh". This library always uses its
+                                   BVH; the CPU oracle follows the reference (brute force unless 1)                           */
+    int32_t bvh_builder;        /* 0 = default (host binned-SAH build, or env ADAPT_BVH_BUILDER), 1 = linear BVH built on the device */
+    int32_t reserved[5];
     /* textures: tracer/path_tracer.py:83-123 (albedo_map / normal_map / bump_map + their packed images). All optional. */
     const adapt_texture* textures;  /* [3][n_objects]: albedo, normal, bump descriptor per object, or NULL (no textures) */
     const float* tex_image[3];      /* packed atlas per map kind, [tex_size][tex_size][3] floats (row = v, column = u), or NULL */
@@ -158,6 +161,21 @@ int adapt_reset_stats(adapt_handle* h);
 int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* rays_d, const float* tmax,
                           int32_t n, int32_t any_hit, int32_t* hit_obj, int32_t* hit_prim,
                           float* hit_t, float* hit_u, float* hit_v);
+
+/* New vertex positions for the SAME scene topology (animated / edited meshes): primitives [n_prims*9], n_g [n_prims*3] and
+ * n_s [n_prims*9] (required iff the scene was created with vertex normals) as in adapt_scene_desc.  Waits for enqueued work,
+ * replaces the per-primitive tables of load_primitives (tracer/tracer_base.py:117-134) and rebuilds the acceleration structure
+ * with the handle's builder (bvh_process, tracer/path_tracer.py:143-179; with bvh_builder = 1 entirely on the device).  The
+ * reference has no counterpart: it re-creates the renderer.  Emitter descriptors (inv_area of mesh lights) and the accumulation
+ * buffer are left as they are -- reset the latter with adapt_load_accum when the image should start over. */
+int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s);
+
+/* Stage-level hook for the acceleration structure that replaces LinearBVH / LinearNode (tracer/ti_bvh.py:10-53) on the device:
+ * sizes, builder used (0 host SAH, 1 device linear BVH) and its build time; nodes_out [n_nodes*16] receives the 64-byte nodes
+ * (x/y bounds of child 0, x/y bounds of child 1, z bounds of both, two child codes), prims_out [n_prims*12] the 48-byte leaf
+ * records in leaf order (layout: csrc/bvh_build.h). Either array may be NULL. */
+int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_t* depth, int32_t* builder, float* build_ms,
+                     float* nodes_out, float* prims_out);
 
 /* Stage-level hook for the surface models: PathTracer.eval / surface_pdf / sample_new_ray (tracer/path_tracer.py:424-494) of
  * object `obj` on n tuples (n_s, n_g, incident, outgoing), [n*3] each.  Sample k draws from the RNG stream keyed (seed, k, 0).

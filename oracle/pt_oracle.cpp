@@ -1633,7 +1633,7 @@ struct oracle_scene { Scene sc; };
 
 extern "C" {
 
-// desc->reserved[0] != 0 selects the reference's BVH path (<string name="accelerator" value="bvh"/>)
+// desc->accelerator != 0 selects the reference's BVH path (<string name="accelerator" value="bvh"/>)
 oracle_scene* oracle_create(const adapt_scene_desc* d) {
     oracle_scene* os = new oracle_scene();
     Scene& sc = os->sc;
@@ -1685,7 +1685,7 @@ oracle_scene* oracle_create(const adapt_scene_desc* d) {
     sc.stratified = d->stratified_sampling; sc.two_sides = d->brdf_two_sides; sc.has_v_normal = d->has_v_normal;
     sc.rr_threshold = d->rr_threshold; sc.world_ior = d->world_ior; sc.seed = d->seed;
     sc.inv_num_shadow_ray = sc.num_shadow_ray > 0 ? 1.f / (float)sc.num_shadow_ray : 1.f;
-    sc.use_bvh = d->reserved[0] != 0;
+    sc.use_bvh = d->accelerator != 0;
     if (sc.use_bvh) {
         // world AABB (path_tracer.py:130-138)
         vec3 mn(1e3f), mx(-1e3f);

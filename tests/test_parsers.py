@@ -58,7 +58,7 @@ def test_camera_constants(scene_root):
     np.testing.assert_allclose(ps.host["cam_t"], [2.78, 2.73, -8.0], rtol=1e-6)
     d = ps.desc
     assert (d.n_prims, d.n_objects, d.n_emitters, d.width, d.height) == (34, 7, 1, 512, 512)
-    assert d.reserved[0] == 0                                # no accelerator requested in cbox.xml
+    assert d.accelerator == 0                                # no accelerator requested in cbox.xml
 
 
 def test_rgb_parse_variants():

@@ -6,5 +6,5 @@ for v in "DEFAULT=1" "$@"; do
   echo -n "== $args | $v : "
   env $v timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu $args 2> /dev/null | python -c "
 import sys, json
-d = json.loads(sys.stdin.read()); print(round(d['value'], 1), 'Mrays/s', round(d['ms_per_step'], 2), 'ms/step', {k: round(v, 2) for k, v in d['stage_ms_per_step'].items()}, 'e2e', round(d['e2e']['value'], 1))"
+d = json.loads(sys.stdin.read()); print(round(d['value'], 1), 'Mrays/s', round(d['ms_per_step'], 2), 'ms/step', {k: round(v, 2) for k, v in d['stage_ms_per_step'].items()}, 'e2e', round(d['e2e']['value'], 1), d['config'].get('bvh'))"
 done | tee -a gpurun_out/ab.txt
