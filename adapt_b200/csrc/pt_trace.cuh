@@ -195,6 +195,11 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 // stream runs dry (WIDE: over the 4-wide tree, see wide_step).  Inside the loop one iteration gives every lane that holds an inner node ONE node step, and the
 // leaf code only runs when at least `leaf_t` lanes are parked on a leaf (or no lane has inner work left), so both
 // code paths execute with well-populated warps (ncu on the plain while-while loop: ~5 of 32 lanes in the node code).
+// The votes that drive this cost about a third of the loop's instructions (ncu source view: ~37 full-warp instructions per
+// round against ~56 for one node step), so a scheduling round gives every lane up to `node_steps` node steps before the
+// next vote (default 4: k_trace 39.3 -> 36.4 ms/step on bunny90k, 56.5 -> 53.6 on orb500k, 20.9 -> 19.1 on balls-mono;
+// 3..6 are equal, 8 is slower).  Replacing the four votes by one warp reduction of packed lane states (`redux.sync.add`)
+// was measured and rejected: -1 % with one step per round, nothing on top of node_steps, +10 % on the sphere scene.
 // The cursor is striped (pt_common.cuh: CursorStripe): one cursor for the whole stream cost 15 % of k_shadow's
 // stall samples (131 k same-address atomics per launch).
 //
@@ -268,7 +273,12 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
         }
         if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)
         while (true) {
+#ifdef TRACE_NODE_STEPS_CT
+            #pragma unroll
+            for (int step = 0; step < TRACE_NODE_STEPS_CT; step++)
+#else
             for (int step = 0; step < node_steps; step++)
+#endif
             if (node >= 0) {
                 if (COUNT) n_nodes++;
                 if (WIDE) {
