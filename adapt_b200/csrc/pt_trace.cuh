@@ -13,6 +13,10 @@
 namespace adapt {
 
 #define PT_STACK_SIZE 64
+// node steps per scheduling round of trace_stream_vote, unrolled at compile time (0: run-time value, ADAPT_NODE_STEPS)
+#ifndef TRACE_NODE_STEPS_CT
+#define TRACE_NODE_STEPS_CT 4
+#endif
 #define PT_T_EPS 1e-4f          // "ray_t > 1e-4" self-intersection guard of the reference
 #define PT_T_INF 1e7f           // min_depth initial value (tracer_base.py:176)
 #define PT_NODE_DONE ((int)0x80000000)
@@ -198,7 +202,7 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 // The votes that drive this cost about a third of the loop's instructions (ncu source view: ~37 full-warp instructions per
 // round against ~56 for one node step), so a scheduling round gives every lane up to `node_steps` node steps before the
 // next vote (default 4: k_trace 39.3 -> 36.4 ms/step on bunny90k, 56.5 -> 53.6 on orb500k, 20.9 -> 19.1 on balls-mono;
-// 3..6 are equal, 8 is slower).  Replacing the four votes by one warp reduction of packed lane states (`redux.sync.add`)
+// 3..6 are equal, 8 is slower; unrolled at compile time, TRACE_NODE_STEPS_CT, another 2.6 %).  Replacing the four votes by one warp reduction of packed lane states (`redux.sync.add`)
 // was measured and rejected: -1 % with one step per round, nothing on top of node_steps, +10 % on the sphere scene.
 // The cursor is striped (pt_common.cuh: CursorStripe): one cursor for the whole stream cost 15 % of k_shadow's
 // stall samples (131 k same-address atomics per launch).
@@ -273,7 +277,7 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
         }
         if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)
         while (true) {
-#ifdef TRACE_NODE_STEPS_CT
+#if TRACE_NODE_STEPS_CT > 0
             #pragma unroll
             for (int step = 0; step < TRACE_NODE_STEPS_CT; step++)
 #else
