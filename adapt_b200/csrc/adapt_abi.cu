@@ -741,7 +741,7 @@ struct adapt_handle {
     unsigned* d_cls_items = nullptr;          // [LOGIC_NKEY][n_slots]
     CursorStripe* d_cls_count = nullptr;      // [2][16]
     unsigned iter_parity = 0;
-    int refill = 16, leaf_t = 12, node_steps = 4;
+    int refill = 16, leaf_t = 8, node_steps = 4;
     bool count_nodes = false;
     // timing
     struct IterEvents { cudaEvent_t e[4]; };
@@ -1209,7 +1209,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKH(dev_alloc(h, &h->d_cls_count, (size_t)32)); CKC(cudaMemset(h->d_cls_count, 0, sizeof(CursorStripe) * 32));
     if (h->logic_lists) CKH(dev_alloc(h, &h->d_cls_items, (size_t)LOGIC_NKEY * (size_t)h->pool.n_slots));
     h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
-    h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 12)));
+    h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 8)));
     h->node_steps = std::min(8, std::max(1, env_int("ADAPT_NODE_STEPS", 4)));
     h->ev_ring.resize(512);
     for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
