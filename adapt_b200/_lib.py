@@ -38,6 +38,28 @@ class adapt_emitter(C.Structure):
                 ("inv_area", C.c_float), ("r", C.c_float), ("emit_time", C.c_float), ("_pad", C.c_float)]
 
 
+class adapt_medium(C.Structure):
+    """include/adapt_b200.h: adapt_medium (reference bxdf/medium.py:71-78 + bxdf/phase.py:30-34)."""
+    _fields_ = [("type", C.c_int32), ("ior", C.c_float), ("u_a", C.c_float * 3), ("u_s", C.c_float * 3), ("u_e", C.c_float * 3),
+                ("par", C.c_float * 3), ("pdf", C.c_float * 3), ("_pad", C.c_int32 * 3)]
+
+
+MEDIUM_DTYPE = np.dtype([("type", "<i4"), ("ior", "<f4"), ("u_a", "<f4", 3), ("u_s", "<f4", 3), ("u_e", "<f4", 3), ("par", "<f4", 3),
+                         ("pdf", "<f4", 3), ("_pad", "<i4", 3)])
+assert C.sizeof(adapt_medium) == MEDIUM_DTYPE.itemsize == 80
+
+
+def medium_record(m) -> np.ndarray:
+    """Medium_np (or None = transparent) -> one adapt_medium record."""
+    rec = np.zeros((), dtype=MEDIUM_DTYPE)
+    rec["type"], rec["ior"], rec["pdf"] = -1, 1.0, (1.0, 0.0, 0.0)
+    if m is not None:
+        rec["type"], rec["ior"] = m.type_id, m.ior
+        for k in ("u_a", "u_s", "u_e", "par", "pdf"):
+            rec[k] = np.broadcast_to(np.float32(getattr(m, k)), 3)
+    return rec
+
+
 assert C.sizeof(adapt_bxdf) == BXDF_DTYPE.itemsize == 64
 assert C.sizeof(adapt_emitter) == EMITTER_DTYPE.itemsize == 64
 
@@ -71,7 +93,8 @@ class adapt_scene_desc(C.Structure):
         ("textures", C.c_void_p),
         ("tex_image", _fp * 3),
         ("tex_size", C.c_int32 * 3),
-        ("reserved2", C.c_int32),
+        ("integrator", C.c_int32),
+        ("media", C.POINTER(adapt_medium)),
     ]
 
 
@@ -189,7 +212,7 @@ class PackedScene:
 
 def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed: int = 0, device_id: int = 0,
                pixel_list: Optional[np.ndarray] = None, pool_size: int = 0, max_bounce: Optional[int] = None,
-               bvh_builder=0) -> PackedScene:
+               bvh_builder=0, integrator="pt") -> PackedScene:
     ps = PackedScene()
     d = ps.desc
     film = prop["film"]
@@ -289,6 +312,19 @@ def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed
                 d.tex_size[m] = img.shape[0]
         ps.keep["textures"] = tx
         d.textures = tx.ctypes.data
+    # ---- participating media (renderer/vpt.py): the medium attached to every BSDF object + the world's free-space medium ----
+    if integrator not in ("pt", "vpt"):
+        raise NotImplementedError(f"integrator '{integrator}': this path covers 'pt' (and 'vpt' in the CPU oracle)")
+    d.integrator = 1 if integrator == "vpt" else 0
+    if prop.get("volume"):
+        if integrator == "vpt":
+            raise NotImplementedError("grid volumes (<volume>, bxdf/volume.py) are outside the homogeneous-media slice of vpt")
+    md = np.zeros(len(objects) + 1, dtype=MEDIUM_DTYPE)
+    for i, obj in enumerate(objects):
+        md[i] = medium_record(getattr(obj.bsdf, "medium", None))
+    md[len(objects)] = medium_record(world.medium if world is not None else None)
+    ps.keep["media"] = md
+    d.media = C.cast(md.ctypes.data, C.POINTER(adapt_medium))
     # ---- back-end knobs ----
     d.seed = int(seed)
     d.device_id = int(device_id)

@@ -1018,6 +1018,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     if (d->n_prims <= 0 || d->n_objects <= 0 || !d->primitives || !d->n_g || !d->obj_info || !d->emitter_id || !d->bxdfs)
         return set_error(ADAPT_ERR_INVALID, "adapt_create: empty scene or missing arrays");
     if (d->width <= 0 || d->height <= 0) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad film size");
+    if (d->integrator != 0)
+        return set_error(ADAPT_ERR_INVALID, "adapt_create: integrator 1 (vpt, participating media) has no kernels yet -- only `pt` runs on the device; there is no CPU fallback");
     if (d->n_emitters < 0 || (d->n_emitters > 0 && !d->emitters)) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad emitters");
     if (d->n_emitters == 0 && d->num_shadow_ray > 0)
         return set_error(ADAPT_ERR_INVALID, "adapt_create: num_shadow_ray > 0 needs at least one emitter (sample_light would divide by zero)");

@@ -305,6 +305,34 @@ def write_allbxdf(root):
     _write_xml(os.path.join(root, "test", "allbxdf.xml"), [sensor, mats, lights, room + balls + boxes, _WORLD])
 
 
+def _medium(kind, u_a, u_s, par, ior, pdf=None):
+    out = [f'<medium type="{kind}">', f'<rgb name="u_a" value="{u_a}"/>', f'<rgb name="u_s" value="{u_s}"/>', f'<rgb name="par" value="{par}"/>']
+    if pdf is not None:
+        out.append(f'<rgb name="pdf" value="{pdf}"/>')
+    return out + [f'<float name="ior" value="{ior}"/>', "</medium>"]
+
+
+def write_media(root):
+    """Coverage scenes of the volumetric integrator (renderer/vpt.py, homogeneous media): a glass ball filled with an HG medium, a
+    null-surface box of Rayleigh 'smoke' that light and shadow rays pass through, a frosted (Lambertian-transmission) ball with a
+    multi-HG medium, Lambertian walls, an area light and a point light (sample_light's two-draw branch).  media.xml fills the
+    free space with a thin multi-HG medium, media-clear.xml leaves it transparent."""
+    mats, room = _room("lambertian")
+    mats += ['<bsdf type="det-refraction" id="milk-glass">', '<rgb name="k_d" value="#FAFAFA"/>'] + _medium("hg", "0.05, 0.1, 0.2", "0.9, 0.6, 0.4", "0.35", 1.45) + ["</bsdf>"]
+    mats += ['<bsdf type="null" id="smoke">', '<rgb name="k_d" value="#FFFFFF"/>'] + _medium("rayleigh", "0.1", "0.7, 0.8, 1.1", "0.0", 1.0) + ["</bsdf>"]
+    mats += ['<bsdf type="lambertian" id="wax">', '<rgb name="k_d" value="#E0D0B0"/>'] \
+        + _medium("multi-hg", "0.02", "1.5, 1.2, 0.9", "0.8, -0.3, 0.1", 1.3, pdf="0.5, 0.3, 0.2") + ["</bsdf>"]
+    mats += _brdf("lambertian", "box", k_d="#BCBCBC", k_g="1.0", k_s="0.0")
+    lights = _AREA + ['<emitter type="point" id="pt">', '<rgb name="emission" value="6.0, 6.0, 5.0"/>', '<point name="center" x="1.0" y="4.2" z="1.2"/>', "</emitter>"]
+    shapes = room + _sphere((1.6, 1.1, 2.0), 1.0, "milk-glass") + _sphere((4.2, 0.7, 1.4), 0.7, "wax") \
+        + _obj(_M + "cbox_smallbox.obj", "smoke", translate=(2.2, 1.8, 1.6)) + _obj(_M + "cbox_largebox.obj", "box", euler=(0, 0, 0))
+    sensor = _sensor(128, 128, 10, 1)
+    fog = ['<world name="fog">', '<rgb name="skybox" value="0.0"/>', '<rgb name="ambient" value="0.0"/>'] \
+        + _medium("multi-hg", "0.01", "0.06, 0.07, 0.09", "0.7, 0.2, -0.4", 1.0, pdf="0.6, 0.3, 0.1") + ["</world>"]
+    _write_xml(os.path.join(root, "test", "media.xml"), [sensor, mats, lights, shapes, fog])
+    _write_xml(os.path.join(root, "test", "media-clear.xml"), [sensor, mats, lights, shapes, _WORLD])
+
+
 def write_big_xml(root):
     """XML of BASELINE configs 3-5; the OBJ files come from ensure_big_meshes()."""
     S = "../meshes/synth/"
@@ -332,6 +360,8 @@ def ensure_small_scenes(root: str):
         write_balls_mono(root)
         write_allbxdf(root)
         write_big_xml(root)
+    if not os.path.exists(os.path.join(root, "test", "media.xml")):
+        write_media(root)
     return root
 
 
@@ -363,7 +393,7 @@ if __name__ == "__main__":
     if "--root" in sys.argv:
         root = sys.argv[sys.argv.index("--root") + 1]
     write_cornell_meshes(os.path.join(root, "meshes", "cornell"))
-    write_cbox(root); write_balls_mono(root); write_allbxdf(root); write_big_xml(root)
+    write_cbox(root); write_balls_mono(root); write_allbxdf(root); write_media(root); write_big_xml(root)
     if "--big" in sys.argv:
         ensure_big_meshes(root, ("bunny90k", "orb500k", "car290k"))
     print("scenes written under", root)

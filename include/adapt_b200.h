@@ -63,6 +63,16 @@ typedef struct {
     int32_t _pad;
 } adapt_texture;
 
+/* Mirrors reference `Medium` + `PhaseFunction` (bxdf/medium.py:71-78, bxdf/phase.py:30-34): the homogeneous medium attached to a BSDF
+ * object, or the free-space medium of the world block.  Only read by the volumetric integrator (integrator = 1). 80 bytes. */
+typedef struct {
+    int32_t type;        /* -1 transparent (not scattering), 0 hg, 1 multi-hg, 2 rayleigh, 3 mie (declared, never sampled by the reference) */
+    float ior;
+    float u_a[3], u_s[3], u_e[3];   /* absorption, scattering, extinction = u_a + u_s */
+    float par[3], pdf[3];           /* phase-function parameters (g per lobe) and lobe weights of multi-hg */
+    int32_t _pad[3];
+} adapt_medium;
+
 /* Everything PathTracer.__init__ receives, flattened. */
 typedef struct {
     /* geometry: array_info of parsers/xml_parser.py:171-175 */
@@ -103,7 +113,10 @@ typedef struct {
     const adapt_texture* textures;  /* [3][n_objects]: albedo, normal, bump descriptor per object, or NULL (no textures) */
     const float* tex_image[3];      /* packed atlas per map kind, [tex_size][tex_size][3] floats (row = v, column = u), or NULL */
     int32_t tex_size[3];            /* atlas edge length per map kind                                                      */
-    int32_t reserved2;
+    int32_t integrator;             /* 0 = `pt` (renderer/vanilla_renderer.py), 1 = `vpt` (renderer/vpt.py: homogeneous media; the CPU oracle
+                                       implements it, libadapt_b200 rejects it with ADAPT_ERR_INVALID until its kernels exist)  */
+    /* participating media: renderer/vpt.py:53, bxdf/bsdf.py:37, parsers/world.py:34. Optional (NULL = everything transparent). */
+    const adapt_medium* media;      /* [n_objects + 1]: medium of each object's BSDF (ignored for BRDF objects), last entry = world medium */
 } adapt_scene_desc;
 
 /* Counters since create (or the last adapt_reset_stats). Ray counts are the calls the reference

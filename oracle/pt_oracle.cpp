@@ -224,6 +224,11 @@ struct Scene {
     std::vector<adapt_texture> textures[3];         // [n_objects] each; empty = this kind of map is absent (has_*_map False)
     std::vector<float> tex_img[3];                  // [size][size][3]
     int tex_size[3] = {0, 0, 0};
+    // participating media (renderer/vpt.py): per-object medium of the BSDF objects, the world's free-space medium, world AABB
+    int integrator = 0;                             // 0 pt, 1 vpt
+    std::vector<adapt_medium> media;                // [n_objects]
+    adapt_medium world_medium{};
+    vec3 w_aabb_min, w_aabb_max;                    // tracer/path_tracer.py:130-138
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1450,6 +1455,316 @@ vec3 render_sample(const Scene& sc, int i, int j, int cnt, Counters& cn) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// renderer/vpt.py, bxdf/medium.py, bxdf/phase.py, sampler/phase_sampling.py -- volumetric path tracer over homogeneous media
+// (the world's free-space medium and the media attached to BSDF objects; grid volumes, has_volume, are not restated)
+// ------------------------------------------------------------------------------------------------
+inline vec3 vexp(vec3 a) { return {std::exp(a.x), std::exp(a.y), std::exp(a.z)}; }
+// random_rgb, sampler/general_sampling.py:17-27
+inline float random_rgb(Rng& rng, vec3 v) {
+    int idx = floor_mod(rng.rand_i(), 3);
+    float result = idx == 0 ? v.x : (idx == 1 ? v.y : v.z);
+    return std::fmax(result, 1e-5f);
+}
+// phase_hg / phase_rayleigh, bxdf/phase.py:18-27
+inline float phase_hg(float cos_theta, float g) {
+    float g2 = g * g;
+    float denom = 1.f + g2 - 2.f * g * cos_theta;
+    return (1.f - g2) / (std::sqrt(denom) * denom) * 0.5f * INV_2PI;
+}
+inline float phase_rayleigh(float cos_theta) { return (float)(0.375 * (0.5 / 3.14159265358979323846)) * (1.f + cos_theta * cos_theta); }
+// sample_hg / sample_rayleigh, sampler/phase_sampling.py:16-41: local direction about the y axis + cos(theta)
+inline vec3 sample_hg(Rng& rng, float g, float* cos_out) {
+    float cos_theta = 0.f;
+    if (std::fabs(g) < 1e-4f) {
+        cos_theta = 1.f - 2.f * rng.rand_f();
+    } else {
+        float g2 = g * g;
+        float sqr_term = (1.f - g2) / (1.f + g - 2.f * g * rng.rand_f());
+        cos_theta = (1.f + g2 - sqr_term * sqr_term) / (2.f * g);
+    }
+    float sin_theta = std::sqrt(std::fmax(0.f, 1.f - cos_theta * cos_theta));
+    float phi = PI2 * rng.rand_f();
+    *cos_out = cos_theta;
+    return vec3(std::cos(phi) * sin_theta, cos_theta, std::sin(phi) * sin_theta);
+}
+inline vec3 sample_rayleigh(Rng& rng, float* cos_out) {
+    float rd = 2.f * rng.rand_f() - 1.f;
+    float u = -std::pow(2.f * rd + std::sqrt(4.f * rd * rd + 1.f), (float)(1. / 3.));
+    float cos_theta = std::fmin(std::fmax(u - 1.f / u, -1.f), 1.f);
+    float sin_theta = std::sqrt(std::fmax(0.f, 1.f - cos_theta * cos_theta));
+    float phi = PI2 * rng.rand_f();
+    *cos_out = cos_theta;
+    return vec3(std::cos(phi) * sin_theta, cos_theta, std::sin(phi) * sin_theta);
+}
+struct Medium {                                   // bxdf/medium.py:71-125 with its PhaseFunction (bxdf/phase.py:29-82)
+    int _type;
+    float ior;
+    vec3 u_s, u_a, u_e, par, pdf;
+    explicit Medium(const adapt_medium& m) : _type(m.type), ior(m.ior), u_s(m.u_s), u_a(m.u_a), u_e(m.u_e), par(m.par), pdf(m.pdf) {}
+    bool is_scattering() const { return _type >= 0; }
+    vec3 transmittance(float depth) const { return vexp(-u_e * depth); }
+    // sample_mfp :88-108 -> (is_medium_interaction, distance, beta = transmittance [* u_s] / pdf)
+    void sample_mfp(Rng& rng, float max_depth, int* is_mi, float* mfp, vec3* beta) const {
+        float random_ue = random_rgb(rng, u_e);
+        float sample_t = -std::log(1.f - rng.rand_f()) / random_ue;
+        if (sample_t >= max_depth) {
+            sample_t = max_depth;
+            vec3 tr = vexp(-u_e * max_depth);
+            float p = (tr.x + tr.y + tr.z) / 3.f;
+            p = p > 0.f ? p : 1.f;
+            *beta = tr / p;
+            *is_mi = 0;
+        } else {
+            vec3 tr = vexp(-u_e * sample_t);
+            vec3 ut = u_e * tr;
+            float p = (ut.x + ut.y + ut.z) / 3.f;
+            p = p > 0.f ? p : 1.f;
+            *beta = tr * u_s / p;
+            *is_mi = 1;
+        }
+        *mfp = sample_t;
+    }
+    // PhaseFunction.sample_p :36-62
+    vec3 sample_p(Rng& rng, vec3 incid, float* p_out) const {
+        vec3 ret_dir = incid;
+        float ret_p = 1.f, cos_t = 0.f;
+        if (_type == 0) {
+            float g = par.x;
+            ret_dir = sample_hg(rng, g, &cos_t);
+            ret_p = phase_hg(cos_t, g);
+        } else if (_type == 1) {
+            float eps = rng.rand_f();
+            float g = eps < pdf.x ? par.x : (eps < pdf.x + pdf.y ? par.y : par.z);
+            ret_dir = sample_hg(rng, g, &cos_t);
+            ret_p = phase_hg(cos_t, g);
+        } else if (_type == 2) {
+            ret_dir = sample_rayleigh(rng, &cos_t);
+            ret_p = phase_rayleigh(cos_t);
+        }
+        *p_out = ret_p;
+        return ret_dir;
+    }
+    // PhaseFunction.eval_p :64-79
+    float eval(vec3 ray_in, vec3 ray_out) const {
+        float ret_p = 1.f;
+        float cos_theta = -dot(ray_in, ray_out);
+        if (_type == 0) {
+            ret_p = phase_hg(cos_theta, par.x);
+        } else if (_type == 1) {
+            ret_p = phase_hg(cos_theta, par.x) * pdf.x + phase_hg(cos_theta, par.y) * pdf.y;
+            if (pdf.y > 1e-4f) ret_p += phase_hg(cos_theta, par.z) * pdf.z;
+        } else if (_type == 2) {
+            ret_p = phase_rayleigh(cos_theta);
+        }
+        return ret_p;
+    }
+    // sample_new_rays :112-121
+    void sample_new_rays(Rng& rng, vec3 incid, vec3* dir, vec3* spec, float* pdf_out) const {
+        *spec = vec3(1.f); *dir = incid; *pdf_out = 1.f;
+        if (is_scattering()) {
+            float p;
+            vec3 local_new_dir = sample_p(rng, incid, &p);
+            *dir = delocalize_rotate(incid, local_new_dir);
+            *pdf_out = p;
+            *spec = vec3(1.f) * p;
+        }
+    }
+};
+inline bool obj_is_brdf(const Scene& sc, int idx) { return sc.bxdfs[idx].kind == 0; }              // ti.is_active(self.obj_nodes, idx)
+// is_scattering, tracer/path_tracer.py:528-535
+inline bool is_scattering(const Scene& sc, int idx) {
+    return idx >= 0 && !obj_is_brdf(sc, idx) && Medium(sc.media[idx]).is_scattering();
+}
+// get_ior :506-515
+inline float get_ior(const Scene& sc, int idx, bool in_free_space) {
+    float ior = 1.f;
+    if (in_free_space) ior = sc.world_medium.ior;
+    else if (idx >= 0) ior = sc.media[idx].ior;
+    return ior;
+}
+// non_null_surface, renderer/vpt.py:67-73
+inline bool non_null_surface(const Scene& sc, int idx) {
+    bool non_null = true;
+    if (idx >= 0 && !obj_is_brdf(sc, idx)) non_null = sc.bxdfs[idx].type >= 0;
+    return non_null;
+}
+// get_transmittance :55-65
+inline vec3 get_transmittance(const Scene& sc, int idx, bool in_free_space, float depth) {
+    vec3 transmittance(1.f);
+    bool world_scattering = sc.world_medium.type >= 0;
+    bool world_valid_scat = in_free_space && world_scattering;
+    if (world_valid_scat || is_scattering(sc, idx)) {
+        if (world_valid_scat) transmittance = Medium(sc.world_medium).transmittance(depth);
+        else if (!in_free_space) transmittance = Medium(sc.media[idx]).transmittance(depth);
+    }
+    return transmittance;
+}
+// sample_mfp :75-101 (has_volume False)
+inline void vpt_sample_mfp(const Scene& sc, Rng& rng, int idx, bool in_free_space, float depth, int* is_mi, float* mfp, vec3* beta) {
+    *is_mi = 0; *mfp = depth; *beta = vec3(1.f);
+    bool world_scattering = sc.world_medium.type >= 0;
+    bool world_valid_scat = in_free_space && world_scattering;
+    if (world_valid_scat || is_scattering(sc, idx)) {
+        if (world_valid_scat) Medium(sc.world_medium).sample_mfp(rng, depth, is_mi, mfp, beta);
+        else if (!in_free_space) Medium(sc.media[idx]).sample_mfp(rng, depth, is_mi, mfp, beta);
+    }
+}
+// track_ray :103-137 (has_volume False): transmittance towards a point `depth` away, through null surfaces and media
+inline vec3 track_ray(const Scene& sc, vec3 cur_ray, vec3 cur_point, float depth, Counters& cn) {
+    vec3 tr(1.f);
+    bool world_scattering = sc.world_medium.type >= 0;
+    bool in_free_space = true;
+    for (int _i = 0; _i < 7; _i++) {
+        Interaction it = ray_intersect(sc, cur_ray, cur_point, cn, depth);
+        cn.rays_closest_useful++;
+        if (it.obj_id < 0) {
+            if (!world_scattering) break;
+            it.min_depth = depth;
+            in_free_space = true;
+            it.obj_id = -1;
+        } else {
+            if (non_null_surface(sc, it.obj_id)) { tr = vec3(0.f); break; }
+            in_free_space = dot(it.n_g, cur_ray) < 0.f;
+        }
+        tr *= get_transmittance(sc, it.obj_id, in_free_space, it.min_depth);
+        cur_point += cur_ray * it.min_depth;
+        depth -= it.min_depth;
+        if (depth <= 5e-5f) break;
+    }
+    return tr;
+}
+// world_bound_time :139-143
+inline float world_bound_time(const Scene& sc, vec3 ray_o, vec3 ray_d) {
+    vec3 t_min = (sc.w_aabb_min - ray_o) / ray_d;
+    vec3 t_max = (sc.w_aabb_max - ray_o) / ray_d;
+    vec3 m(std::fmax(t_min.x, t_max.x), std::fmax(t_min.y, t_max.y), std::fmax(t_min.z, t_max.z));
+    return std::fmin(std::fmin(m.x, m.y), m.z);
+}
+// eval / sample_new_ray / (phase value as pdf) with medium interactions, tracer/path_tracer.py:424-479
+inline vec3 vpt_eval(const Scene& sc, Interaction& it, vec3 incid, vec3 out, int is_mi, bool in_free_space) {
+    if (is_mi) {
+        float p = in_free_space ? Medium(sc.world_medium).eval(incid, out) : Medium(sc.media[it.obj_id]).eval(incid, out);
+        return vec3(p);
+    }
+    return eval_bxdf(sc, it, incid, out);
+}
+// render, renderer/vpt.py:145-258 -- one pixel-sample
+vec3 render_sample_vpt(const Scene& sc, int i, int j, int cnt, Counters& cn) {
+    Rng rng;
+    rng.init(sc.seed, (uint32_t)(i * sc.h + j), (uint32_t)cnt);
+    const bool world_scattering = sc.world_medium.type >= 0;
+    vec3 ray_d = pix2ray(sc, rng, i, j, cnt);
+    vec3 ray_o = sc.cam_t;
+    vec3 color(0.f), throughput(1.f);
+    float emission_weight = 1.f;
+    bool in_free_space = true;
+    int bounce = 0;
+    while (true) {
+        // Step 1: ray termination test
+        if (sc.use_rr) {
+            float max_value = vmax(throughput);
+            if (max_value < sc.rr_threshold && bounce >= sc.rr_bounce_th) {
+                if (rng.rand_f() > max_value) break;
+                else throughput *= 1.f / (max_value + 1e-7f);
+            }
+        } else {
+            if (vmax(throughput) < 1e-5f) break;
+        }
+        // Step 2: ray intersection
+        Interaction it = ray_intersect(sc, ray_d, ray_o, cn);
+        cn.rays_closest_useful++;
+        if (it.obj_id < 0) {
+            if (!world_scattering) break;
+            it.min_depth = world_bound_time(sc, ray_o, ray_d);
+            in_free_space = true;
+            it.obj_id = -1;
+        } else {
+            in_free_space = dot(it.n_g, ray_d) < 0.f;
+        }
+        // Step 3: mean free path sampling; path_beta = transmittance / pdf
+        int is_mi; vec3 path_beta;
+        vpt_sample_mfp(sc, rng, it.obj_id, in_free_space, it.min_depth, &is_mi, &it.min_depth, &path_beta);
+        if (it.obj_id < 0 && !is_mi) break;                       // leaving the world bound
+        vec3 hit_point = ray_d * it.min_depth + ray_o;
+        throughput *= path_beta;
+        if (!is_mi && !non_null_surface(sc, it.obj_id)) {
+            ray_o = hit_point;
+            continue;
+        }
+        int hit_light = is_mi ? -1 : sc.emitter_id[it.obj_id];
+        // Step 4: direct component
+        float emitter_pdf = 1.f, direct_pdf = 1.f;
+        bool break_flag = false;
+        vec3 shadow_int(0.f), direct_int(0.f), direct_spec(1.f);
+        if (!is_mi || it.obj_id >= 0) { bool tex_valid; it.tex = get_uv_item(sc, 0, it, &tex_valid); }
+        else it.tex = vec3(-1.f);
+        for (int _j = 0; _j < sc.num_shadow_ray; _j++) {
+            bool emitter_valid;
+            int ei = sample_light(sc, rng, hit_light, &emitter_pdf, &emitter_valid);
+            Source emitter(sc.src[ei]);
+            vec3 light_dir(0.f);
+            if (emitter_valid) {
+                vec3 emit_pos;
+                emitter.sample_hit(rng, sc, hit_point, &emit_pos, &shadow_int, &direct_pdf);
+                vec3 to_emitter = emit_pos - hit_point;
+                float emitter_d = norm(to_emitter);
+                light_dir = to_emitter / emitter_d;
+                vec3 tr = track_ray(sc, light_dir, hit_point, emitter_d, cn);
+                shadow_int *= tr;
+                direct_spec = vpt_eval(sc, it, ray_d, light_dir, is_mi, in_free_space);
+            } else {
+                break_flag = true;
+                break;
+            }
+            float light_pdf = emitter_pdf * direct_pdf;
+            if (sc.use_mis) {
+                float mis_w = 1.f;
+                if (!emitter.is_delta_pos()) {
+                    float bsdf_pdf = is_mi ? direct_spec.x : surface_pdf(sc, it, light_dir, ray_d);
+                    mis_w = balance_heuristic(light_pdf, bsdf_pdf);
+                }
+                direct_int += direct_spec * shadow_int * mis_w / emitter_pdf;
+            } else {
+                direct_int += direct_spec * shadow_int / emitter_pdf;
+            }
+        }
+        if (!break_flag) direct_int *= sc.inv_num_shadow_ray;
+        // Step 5: emission
+        vec3 emit_int(0.f);
+        if (hit_light >= 0) emit_int = Source(sc.src[hit_light]).eval_le(hit_point - ray_o, it.n_g);
+        // Step 6: new ray (surface or medium interaction)
+        vec3 new_dir, indirect_spec; float ray_pdf; bool is_specular = false;
+        if (is_mi) {
+            if (in_free_space) Medium(sc.world_medium).sample_new_rays(rng, ray_d, &new_dir, &indirect_spec, &ray_pdf);
+            else Medium(sc.media[it.obj_id]).sample_new_rays(rng, ray_d, &new_dir, &indirect_spec, &ray_pdf);
+        } else {
+            sample_new_ray(sc, rng, it, ray_d, &new_dir, &indirect_spec, &ray_pdf, &is_specular);
+        }
+        ray_d = new_dir;
+        ray_o = hit_point;
+        color += (direct_int + emit_int * emission_weight) * throughput;
+        if (!is_mi) {
+            if (vmax(indirect_spec) == 0.f || ray_pdf == 0.f) break;
+            throughput *= indirect_spec / ray_pdf;
+        }
+        bounce++;
+        if (bounce >= sc.max_bounce) break;
+        if (it.obj_id >= 0) {                                     // emission MIS
+            hit_light = sc.emitter_id[it.obj_id];
+            if (sc.use_mis) {
+                emitter_pdf = 0.f;
+                if (hit_light >= 0 && is_delta(sc, it.obj_id) == 0 && !is_specular)
+                    emitter_pdf = Source(sc.src[hit_light]).solid_angle_pdf(it, ray_d);
+                emission_weight = balance_heuristic(ray_pdf, emitter_pdf);
+            }
+        }
+    }
+    cn.paths++;
+    cn.rng_draws += rng.draws;
+    return vec3(std::isnan(color.x) ? 0.f : color.x, std::isnan(color.y) ? 0.f : color.y, std::isnan(color.z) ? 0.f : color.z);
+}
+
+// ------------------------------------------------------------------------------------------------
 // tracer/bvh/bvh.cpp + bvh_helper.h -- recursive binned-SAH builder, restated without Eigen/pybind11
 // ------------------------------------------------------------------------------------------------
 // The reference's extension module is ordinary host C++ built without -march flags, i.e. without FMA contraction; SAH costs tie
@@ -1686,11 +2001,24 @@ oracle_scene* oracle_create(const adapt_scene_desc* d) {
     sc.rr_threshold = d->rr_threshold; sc.world_ior = d->world_ior; sc.seed = d->seed;
     sc.inv_num_shadow_ray = sc.num_shadow_ray > 0 ? 1.f / (float)sc.num_shadow_ray : 1.f;
     sc.use_bvh = d->accelerator != 0;
-    if (sc.use_bvh) {
-        // world AABB (path_tracer.py:130-138)
+    // world AABB (path_tracer.py:130-138)
+    vec3 wmin, wmax;
+    {
         vec3 mn(1e3f), mx(-1e3f);
         for (int o = 0; o < sc.n_objects; o++) { mn = vminv(mn, sc.aabbs[o][0]); mx = vmaxv(mx, sc.aabbs[o][1]); }
-        vec3 wmin = vminv(sc.cam_t, mn) - 0.1f, wmax = vmaxv(sc.cam_t, mx) + 0.1f;
+        wmin = vminv(sc.cam_t, mn) - 0.1f; wmax = vmaxv(sc.cam_t, mx) + 0.1f;
+        sc.w_aabb_min = wmin; sc.w_aabb_max = wmax;
+    }
+    // participating media (renderer/vpt.py)
+    sc.integrator = d->integrator;
+    adapt_medium transparent{}; transparent.type = -1; transparent.ior = 1.f; transparent.pdf[0] = 1.f;
+    sc.media.assign((size_t)sc.n_objects, transparent);
+    sc.world_medium = transparent; sc.world_medium.ior = d->world_ior;
+    if (d->media) {
+        for (int o = 0; o < sc.n_objects; o++) sc.media[o] = d->media[o];
+        sc.world_medium = d->media[sc.n_objects];
+    }
+    if (sc.use_bvh) {
         bvh_build_impl(d->primitives, sc.n_prims, bvh_obj_info.data(), sc.n_objects, &wmin.x, &wmax.x, sc.lin_bvhs, sc.lin_nodes);
         sc.node_num = (int)sc.lin_nodes.size();
     }
@@ -1724,7 +2052,7 @@ void oracle_render(oracle_scene* os, int cnt_start, int n_spp, float* accum, con
             int i = pixel_list[k] / sc.h, j = pixel_list[k] % sc.h;
             float* px = accum + (size_t)pixel_list[k] * 3;
             for (int s = 1; s <= n_spp; s++) {
-                vec3 c = render_sample(sc, i, j, cnt_start + s, local);
+                vec3 c = sc.integrator == 1 ? render_sample_vpt(sc, i, j, cnt_start + s, local) : render_sample(sc, i, j, cnt_start + s, local);
                 px[0] += c.x; px[1] += c.y; px[2] += c.z;
             }
         }
@@ -1742,7 +2070,7 @@ void oracle_render(oracle_scene* os, int cnt_start, int n_spp, float* accum, con
 void oracle_set_debug(int on) { g_dbg = on != 0; }
 void oracle_render_sample(oracle_scene* os, int i, int j, int cnt, float* rgb, uint64_t* draws) {
     Counters cn;
-    vec3 c = render_sample(os->sc, i, j, cnt, cn);
+    vec3 c = os->sc.integrator == 1 ? render_sample_vpt(os->sc, i, j, cnt, cn) : render_sample(os->sc, i, j, cnt, cn);
     rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
     if (draws) *draws = cn.rng_draws;
 }
@@ -1800,6 +2128,31 @@ int oracle_bvh_build(const float* primitives, int32_t n_prims, const int32_t* ob
     }
     return 0;
 }
+// ---- medium hooks for the closed-form tests (tests/test_vpt_oracle.py)
+void oracle_phase_eval(const adapt_medium* m, const float* incid, const float* out, int n, float* val) {
+    Medium md(*m);
+    for (int k = 0; k < n; k++) val[k] = md.eval(vec3(incid + 3 * k), vec3(out + 3 * k));
+}
+// n draws of Medium.sample_new_rays about one incident direction; sample k uses the RNG stream (seed, k, 0)
+void oracle_phase_sample(const adapt_medium* m, const float* incid, uint64_t seed, int n, float* dirs, float* pdf) {
+    Medium md(*m);
+    for (int k = 0; k < n; k++) {
+        Rng rng; rng.init(seed, (uint32_t)k, 0u);
+        vec3 d, spec; float p;
+        md.sample_new_rays(rng, vec3(incid), &d, &spec, &p);
+        dirs[3 * k] = d.x; dirs[3 * k + 1] = d.y; dirs[3 * k + 2] = d.z; pdf[k] = p;
+    }
+}
+void oracle_medium_sample_mfp(const adapt_medium* m, float max_depth, uint64_t seed, int n, int32_t* is_mi, float* t, float* beta) {
+    Medium md(*m);
+    for (int k = 0; k < n; k++) {
+        Rng rng; rng.init(seed, (uint32_t)k, 0u);
+        int mi; float mfp; vec3 b;
+        md.sample_mfp(rng, max_depth, &mi, &mfp, &b);
+        is_mi[k] = mi; t[k] = mfp; beta[3 * k] = b.x; beta[3 * k + 1] = b.y; beta[3 * k + 2] = b.z;
+    }
+}
+
 void oracle_free(void* p) { std::free(p); }
 
 // ---- known-answer hooks (tests/test_oracle_kat.py)

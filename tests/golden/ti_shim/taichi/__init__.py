@@ -33,6 +33,9 @@ f32 = np.float32
 i32 = np.int32
 u32 = np.uint32
 f64 = np.float64
+float32 = np.float32
+int32 = np.int32
+float64 = np.float64
 float = float          # noqa: A001  (ti.float)
 int = int              # noqa: A001
 cpu = "cpu"

@@ -29,7 +29,8 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.adapt_bxdf) == 64 and C.sizeof(_lib.adapt_emitter) == 64
+    assert C.sizeof(_lib.adapt_bxdf) == 64 and C.sizeof(_lib.adapt_emitter) == 64 and C.sizeof(_lib.adapt_medium) == 80
+    assert _lib.adapt_scene_desc.media.offset % 8 == 0 and _lib.adapt_scene_desc.media.offset + 8 == C.sizeof(_lib.adapt_scene_desc)
     assert _lib.adapt_scene_desc.seed.offset % 8 == 0
     assert C.sizeof(_lib.adapt_stats) == 5 * 8 + 4 * 4 + 2 * 8 + 4 * 8
 
