@@ -26,6 +26,8 @@
 #include "pt_common.cuh"
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
+#include "pt_path.cuh"
+#include "scene_pack.h"
 
 using namespace adapt;
 
@@ -109,48 +111,6 @@ __device__ __forceinline__ void block_count(unsigned v, unsigned long long* coun
     // warp reduce then one atomic per warp (only used for statistics)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
-}
-
-// Shading frame of a hit: geometric + shading normal (tracer_base.py:215-232 / path_tracer.py:372-389)
-__device__ __forceinline__ void load_surface(const SceneView& sv, int prim, float3 o, float3 d, float t, float u, float v,
-                                             Surf& s, int& obj, bool& sphere) {
-    const float4 s0 = __ldg(sv.prim_shade + (size_t)prim * 4);
-    const uint32_t ob = __float_as_uint(s0.w);
-    obj = (int)(ob & 0x7fffffffu);
-    sphere = (ob & 0x80000000u) != 0;
-    s.t = t;
-    if (sphere) {
-        const float4 g0 = __ldg(sv.prim_geom + (size_t)prim * 3);
-        s.n_g = normalized(o + t * d - mk3(g0.x, g0.y, g0.z));
-        s.n_s = s.n_g;
-    } else {
-        s.n_g = mk3(s0.x, s0.y, s0.z);
-        if (sv.has_v_normal) {
-            const float4 a = __ldg(sv.prim_shade + (size_t)prim * 4 + 1), b = __ldg(sv.prim_shade + (size_t)prim * 4 + 2),
-                         c = __ldg(sv.prim_shade + (size_t)prim * 4 + 3);
-            float3 n0 = mk3(a.x, a.y, a.z), n1 = mk3(a.w, b.x, b.y), n2 = mk3(b.z, b.w, c.x);
-            s.n_s = n0 * (1.f - u - v) + u * n1 + v * n2;     // not renormalised, like the reference (quirk 4)
-        } else {
-            s.n_s = s.n_g;
-        }
-    }
-}
-
-// pix2ray (tracer_base.py:136-157)
-__device__ __forceinline__ float3 camera_ray(const SceneView& sv, Rng& g, int i, int j, int cnt) {
-    float vx = 0.5f, vy = 0.5f;
-    if (sv.anti_alias) {
-        if (sv.stratified) {
-            int m = cnt % 16;
-            vx = (float)(m % 4) * 0.25f + g.rand_f() * 0.25f;
-            vy = (float)(m / 4) * 0.25f + g.rand_f() * 0.25f;
-        } else {
-            vx = g.rand_f() * 0.9998f + 1e-4f;
-            vy = g.rand_f() * 0.9998f + 1e-4f;
-        }
-    }
-    float3 cd = mk3((sv.half_w + vx - (float)i) * sv.inv_focal, ((float)j - sv.half_h - vy) * sv.inv_focal, 1.f);
-    return normalized(mul(sv.cam_r, cd));
 }
 
 // conservative ray / box test (same slab arithmetic as the traversal, with slack): false only if the ray cannot hit anything inside
@@ -913,37 +873,6 @@ int adapt_bvh_build(const float* primitives, int32_t n_prims, const int32_t* obj
     *bvh_info = dup(rl.bvh_info); *node_info = dup(rl.node_info);
     *n_refs = (int32_t)(rl.bvh_info.size() / 2); *n_nodes = (int32_t)(rl.node_info.size() / 3);
     return 0;
-}
-
-// ---- geometry tables (tracer_base.py:117-134 load_primitives): per-primitive (v0, e1, e2) / (centre, r) and normals
-static void pack_geometry(const float* primitives, const float* n_g, const float* n_s, int np, const std::vector<uint8_t>& sph,
-                          const std::vector<int32_t>& prim_obj, std::vector<float4>& prim_geom, std::vector<float4>& prim_shade) {
-    prim_geom.resize((size_t)np * 3); prim_shade.resize((size_t)np * 4);
-    for (int k = 0; k < np; k++) {
-        const float* v = primitives + (size_t)k * 9;
-        if (sph[k]) {
-            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], v[3]);
-            prim_geom[k * 3 + 1] = make_float4(0, 0, 0, 0);
-            prim_geom[k * 3 + 2] = make_float4(0, 0, 0, 0);
-        } else {
-            float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
-            prim_geom[k * 3 + 0] = make_float4(v[0], v[1], v[2], e1[0]);
-            prim_geom[k * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
-            prim_geom[k * 3 + 2] = make_float4(e2[2], 0, 0, 0);
-        }
-        const float* ng = n_g + (size_t)k * 3;
-        uint32_t ob = (uint32_t)prim_obj[k] | (sph[k] ? 0x80000000u : 0u);
-        float obf; std::memcpy(&obf, &ob, 4);
-        prim_shade[k * 4 + 0] = make_float4(ng[0], ng[1], ng[2], obf);
-        if (n_s) {
-            const float* q = n_s + (size_t)k * 9;
-            prim_shade[k * 4 + 1] = make_float4(q[0], q[1], q[2], q[3]);
-            prim_shade[k * 4 + 2] = make_float4(q[4], q[5], q[6], q[7]);
-            prim_shade[k * 4 + 3] = make_float4(q[8], 0, 0, 0);
-        } else {
-            prim_shade[k * 4 + 1] = prim_shade[k * 4 + 2] = prim_shade[k * 4 + 3] = make_float4(0, 0, 0, 0);
-        }
-    }
 }
 
 static void dev_release(adapt_handle* h, const void* p) {

@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE: the device code of the volumetric integrator compiled as host C++ (see dev_host.cpp, cuda_host_shim.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_CSRC = os.path.join(_ROOT, "adapt_b200", "csrc")
+SRC = os.path.join(_HERE, "dev_host.cpp")
+DEPS = [SRC, os.path.join(_HERE, "cuda_host_shim.h")] + [os.path.join(_CSRC, f) for f in (
+    "pt_common.cuh", "pt_shade.cuh", "pt_trace.cuh", "pt_path.cuh", "pt_volume.cuh", "scene_pack.h", "bvh_build.cpp", "bvh_build.h")]
+LIB = os.path.join(_HERE, "_build", "libdev_host.so")
+CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in DEPS):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    # same contraction / ISA choices as the oracle build (nvcc contracts a*b+c into FMA by default as well)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-fopenmp", "-ffp-contract=fast", "-march=x86-64-v3", "-I" + CUDA_INC,
+                           "-shared", "-o", LIB, SRC, os.path.join(_CSRC, "bvh_build.cpp")])
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(build())
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        lib.dev_host_create.restype = C.c_void_p
+        lib.dev_host_create.argtypes = [C.c_void_p]
+        lib.dev_host_destroy.argtypes = [C.c_void_p]
+        lib.dev_host_render_vpt.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, C.POINTER(C.c_uint64)]
+        lib.dev_host_phase_eval.argtypes = [C.c_void_p, fp, fp, C.c_int, fp]
+        lib.dev_host_phase_sample.argtypes = [C.c_void_p, fp, C.c_uint64, C.c_int, fp, fp]
+        lib.dev_host_medium_sample_mfp.argtypes = [C.c_void_p, C.c_float, C.c_uint64, C.c_int, ip, fp, fp]
+        _lib = lib
+    return _lib
+
+
+class DevHostScene:
+    """vpt through the device functions (vol_shade_step / vol_transmit_step / trace) on the CPU, for one packed scene."""
+
+    def __init__(self, packed):
+        self.lib = load()
+        self.packed = packed
+        self.h = self.lib.dev_host_create(C.addressof(packed.desc))
+        if not self.h:
+            raise NotImplementedError("scene uses brdf_two_sides or textures: not covered by the volumetric device code")
+        self.w, self.hh = packed.desc.width, packed.desc.height
+
+    def render(self, n_spp: int, cnt_start: int = 0):
+        acc = np.zeros((self.w, self.hh, 3), np.float32)
+        st = np.zeros(3, np.uint64)
+        self.lib.dev_host_render_vpt(self.h, cnt_start, n_spp, acc.ctypes.data_as(C.POINTER(C.c_float)), st.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return acc, dict(paths=int(st[0]), traces=int(st[1]), segments=int(st[2]))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.dev_host_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
