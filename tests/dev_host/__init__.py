@@ -32,7 +32,9 @@ def load():
         lib = C.CDLL(build())
         fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
         lib.dev_host_create.restype = C.c_void_p
-        lib.dev_host_create.argtypes = [C.c_void_p]
+        lib.dev_host_create.argtypes = [C.c_void_p, C.c_int]
+        lib.dev_host_bxdf_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_uint64, fp, fp, fp, fp, fp, ip]
+        lib.dev_host_intersect_batch.argtypes = [C.c_void_p, fp, fp, fp, C.c_int, C.c_int, ip, ip, fp, fp, fp]
         lib.dev_host_destroy.argtypes = [C.c_void_p]
         lib.dev_host_render_vpt.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, C.POINTER(C.c_uint64)]
         lib.dev_host_phase_eval.argtypes = [C.c_void_p, fp, fp, C.c_int, fp]
@@ -45,10 +47,10 @@ def load():
 class DevHostScene:
     """vpt through the device functions (vol_shade_step / vol_transmit_step / trace) on the CPU, for one packed scene."""
 
-    def __init__(self, packed):
+    def __init__(self, packed, for_vpt: bool = True):
         self.lib = load()
         self.packed = packed
-        self.h = self.lib.dev_host_create(C.addressof(packed.desc))
+        self.h = self.lib.dev_host_create(C.addressof(packed.desc), int(for_vpt))
         if not self.h:
             raise NotImplementedError("scene uses brdf_two_sides or textures: not covered by the volumetric device code")
         self.w, self.hh = packed.desc.width, packed.desc.height
@@ -58,6 +60,30 @@ class DevHostScene:
         st = np.zeros(3, np.uint64)
         self.lib.dev_host_render_vpt(self.h, cnt_start, n_spp, acc.ctypes.data_as(C.POINTER(C.c_float)), st.ctypes.data_as(C.POINTER(C.c_uint64)))
         return acc, dict(paths=int(st[0]), traces=int(st[1]), segments=int(st[2]))
+
+    def bxdf_batch(self, obj, n_s, n_g, incid, out, two_sides=False, seed=0):
+        """Host twin of Renderer.bxdf_batch / k_bxdf_batch: the device surface models of object ``obj``."""
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        arrs = [np.ascontiguousarray(x, np.float32).reshape(-1, 3) for x in (n_s, n_g, incid, out)]
+        n = arrs[0].shape[0]
+        ev = np.zeros((n, 3), np.float32); sd = np.zeros((n, 3), np.float32); ss = np.zeros((n, 3), np.float32)
+        pdf = np.zeros(n, np.float32); sp = np.zeros(n, np.float32); fl = np.zeros(n, np.int32)
+        self.lib.dev_host_bxdf_batch(self.h, int(obj), n, *(x.ctypes.data_as(fp) for x in arrs), int(bool(two_sides)), int(seed),
+                                     ev.ctypes.data_as(fp), pdf.ctypes.data_as(fp), sd.ctypes.data_as(fp), ss.ctypes.data_as(fp),
+                                     sp.ctypes.data_as(fp), fl.ctypes.data_as(ip))
+        return dict(eval=ev, pdf=pdf, s_dir=sd, s_spec=ss, s_pdf=sp, s_flag=fl)
+
+    def intersect_batch(self, rays_o, rays_d, tmax=None, any_hit=False):
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        ro = np.ascontiguousarray(rays_o, np.float32).reshape(-1, 3); rd = np.ascontiguousarray(rays_d, np.float32).reshape(-1, 3)
+        n = ro.shape[0]
+        tm = None if tmax is None else np.ascontiguousarray(tmax, np.float32)
+        obj = np.zeros(n, np.int32); prim = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+        self.lib.dev_host_intersect_batch(self.h, ro.ctypes.data_as(fp), rd.ctypes.data_as(fp), None if tm is None else tm.ctypes.data_as(fp), n,
+                                          int(any_hit), obj.ctypes.data_as(ip), prim.ctypes.data_as(ip), t.ctypes.data_as(fp),
+                                          u.ctypes.data_as(fp), v.ctypes.data_as(fp))
+        return dict(obj=obj, prim=prim, t=t, u=u, v=v)
 
     def __del__(self):
         try:

@@ -28,8 +28,9 @@ struct DevHost {
 
 extern "C" {
 
-DevHost* dev_host_create(const adapt_scene_desc* d) {
-    if (!d || d->brdf_two_sides || d->textures) return nullptr;       // not covered by the volumetric device code yet
+// for_vpt != 0: refuse what the volumetric device code does not cover yet (two-sided BRDFs, textures)
+DevHost* dev_host_create(const adapt_scene_desc* d, int for_vpt) {
+    if (!d || (for_vpt && (d->brdf_two_sides || d->textures))) return nullptr;
     DevHost* h = new DevHost();
     const int np = d->n_prims, no = d->n_objects;
     std::vector<uint8_t> sph((size_t)np, 0), obj_class((size_t)no, 0);
@@ -119,6 +120,45 @@ void dev_host_render_vpt(DevHost* h, int cnt_start, int n_spp, float* accum, uin
         }
     }
     if (stats) { stats[0] = n_paths; stats[1] = n_trace; stats[2] = n_seg; }
+}
+
+// The surface models exactly as k_bxdf_batch (adapt_abi.cu) calls them on the device: eval / pdf / sample of object `obj` on n tuples.
+void dev_host_bxdf_batch(DevHost* h, int obj, int n, const float* ns_in, const float* ng_in, const float* incid_in, const float* out_in,
+                         int two_sides, uint64_t seed, float* ev, float* pdf, float* s_dir, float* s_spec, float* s_pdf, int* s_flag) {
+    const SceneView& sv = h->sv;
+    for (int k = 0; k < n; k++) {
+        const Bxdf mat = load_bxdf(sv.bxdfs + obj);
+        Surf sf; sf.n_s = ld3(ns_in + (size_t)k * 3); sf.n_g = ld3(ng_in + (size_t)k * 3); sf.t = 1.f;
+        const float3 in = ld3(incid_in + (size_t)k * 3), out = ld3(out_in + (size_t)k * 3);
+        Surf sb = sf;
+        if (two_sides && mat.kind == 0 && dot(in, sf.n_s) > 0.f) { sb.n_s = -sf.n_s; sb.n_g = -sf.n_g; }
+        const float3 e = mat.kind == 0 ? brdf_eval<M_ALL>(mat, sb, in, out) : bsdf_eval(mat, sf, in, out, sv.world_ior);
+        ev[(size_t)k * 3] = e.x; ev[(size_t)k * 3 + 1] = e.y; ev[(size_t)k * 3 + 2] = e.z;
+        pdf[k] = mat.kind == 0 ? brdf_pdf<M_ALL>(mat, sb, out, in) : bsdf_pdf(mat, sf, out, in, sv.world_ior);
+        Rng g; g.init(seed, (uint32_t)k, 0u);
+        float3 d, sp; float p; bool fl;
+        if (mat.kind == 0) brdf_sample<M_ALL>(mat, sb, in, g, d, sp, p, fl);
+        else bsdf_sample(mat, sf, in, sv.world_ior, g, d, sp, p, fl);
+        s_dir[(size_t)k * 3] = d.x; s_dir[(size_t)k * 3 + 1] = d.y; s_dir[(size_t)k * 3 + 2] = d.z;
+        s_spec[(size_t)k * 3] = sp.x; s_spec[(size_t)k * 3 + 1] = sp.y; s_spec[(size_t)k * 3 + 2] = sp.z;
+        s_pdf[k] = p; s_flag[k] = fl ? 1 : 0;
+    }
+}
+// The device traversal (pt_trace.cuh: trace<>) over the host-built tree in the device layout: closest hit / any hit of a ray batch.
+void dev_host_intersect_batch(DevHost* h, const float* ro, const float* rd, const float* tmax, int n, int any_hit, int* hit_obj, int* hit_prim,
+                              float* hit_t, float* hit_u, float* hit_v) {
+    #pragma omp parallel for schedule(static)
+    for (int k = 0; k < n; k++) {
+        HitRec hr; unsigned nn = 0, np = 0;
+        float tm = (tmax && tmax[k] > 0.f) ? tmax[k] - 1e-4f : PT_T_INF;
+        if (any_hit) {
+            hit_prim[k] = trace<true, false>(h->sv, ld3(ro + 3 * k), ld3(rd + 3 * k), tm, hr, nn, np) ? 1 : 0;
+        } else {
+            trace<false, false>(h->sv, ld3(ro + 3 * k), ld3(rd + 3 * k), tm, hr, nn, np);
+            hit_prim[k] = hr.prim; hit_obj[k] = hr.prim >= 0 ? (int)(hr.obj & 0x7fffffff) : -1;
+            hit_t[k] = hr.t; hit_u[k] = hr.u; hit_v[k] = hr.v;
+        }
+    }
 }
 
 // medium functions one by one (same call shapes as the oracle's hooks oracle_phase_eval / oracle_phase_sample / oracle_medium_sample_mfp)
