@@ -40,6 +40,9 @@ def main(argv=None):
     opts = get_options(argv=argv)
     from adapt_b200.renderer.vanilla_renderer import Renderer
     rdr_mapping = {"pt": Renderer}
+    if opts.type not in rdr_mapping:
+        # `vpt` (the reference's default): oracle + device functions exist, the kernels do not -- and nothing falls back
+        raise NotImplementedError(f"--type {opts.type}: only the unidirectional path tracer `pt` runs on the device in this build")
     input_folder = os.path.join(opts.input_path, opts.scene)
     emitter_configs, array_info, all_objs, configs = scene_parsing(input_folder, opts.name)
     output_folder = folder_path(opts.output_path)
