@@ -27,6 +27,7 @@
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
 #include "pt_path.cuh"
+#include "pt_volume.cuh"
 #include "scene_pack.h"
 
 using namespace adapt;
@@ -501,6 +502,135 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 }
 
 // ================================================================================================
+// k_logic_vpt: the volumetric integrator's step between two closest-hit traces (pt_volume.cuh: vol_shade_step), first version.
+// ================================================================================================
+// Thread t owns slot t.  The next-event transmittance (track_ray, up to seven closest-hit segments through null surfaces and
+// media) is resolved INSIDE this kernel with the single-ray traversal, like k_logic's rare two-sided corner case -- correct but
+// divergent; moving it to a re-arming stream of k_trace is the planned second version.  Path continuation rays
+// go through the unchanged k_closest stream.  Slot layout as for `pt`, except that thr.w carries the emission weight.
+// NOT YET RUN ON A GPU: adapt_create only accepts integrator = 1 with ADAPT_ENABLE_VPT=1 (the functions it calls are verified on
+// the CPU, tests/test_vpt_device_code.py; this glue is not).
+template <int MATS>
+__global__ void __launch_bounds__(LOGIC_BLOCK, 2)
+k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
+            Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
+            const unsigned long long work_hi, const long long cnt_origin, const unsigned rot) {
+    const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
+    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; }
+    const int home = (int)(((unsigned)(slot >> 5) + 4u * rot) % PT_NSTRIPE);
+    uint4 misc = pool.misc[slot];
+    bool alive = (misc.z & SLOT_ALIVE) != 0;
+    if (!__any_sync(0xffffffffu, alive)) {
+        bool dry = true;
+        if ((threadIdx.x & 31) < 4) {
+            const int c = (home + (int)(threadIdx.x & 31)) % PT_NSTRIPE;
+            dry = *reinterpret_cast<volatile unsigned long long*>(&work[c].claimed) >= stripe_limit(work_hi, c);
+        }
+        if (__all_sync(0xffffffffu, dry)) return;
+    }
+    unsigned finished = 0, n_segments = 0;
+    if (alive) {
+        const float4 c4 = pool.col[slot], h4 = pool.hit[slot], o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
+        const uint2 r2 = pool.rng[slot];
+        VolPath p;
+        p.ray_o = mk3(o4.x, o4.y, o4.z); p.ray_d = mk3(d4.x, d4.y, d4.z);
+        p.throughput = mk3(t4.x, t4.y, t4.z); p.emission_weight = t4.w;
+        p.color = mk3(c4.x, c4.y, c4.z);
+        p.bounce = (int)(misc.z & 0xffffu);
+        p.rng.state = ((uint64_t)r2.y << 32) | r2.x;
+        HitRec h; h.t = h4.x; h.u = h4.y; h.v = h4.z; h.obj = 0; h.cls = 0;
+        const int hit_word = __float_as_int(h4.w);
+        h.prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
+        VolRequest reqs[VOL_MAX_REQUESTS]; int n_req = 0;
+        const VolOutcome out = vol_shade_step<MATS>(sv, vv, p, h, reqs, n_req);
+        for (int r = 0; r < n_req; r++) {
+            VolTransmit t; vol_transmit_begin(t, reqs[r]);
+            while (true) {
+                HitRec sh; unsigned nn = 0, np = 0;
+                trace<false, false>(sv, t.point, t.dir, vol_transmit_tmax(t), sh, nn, np);
+                n_segments++;
+                if (!vol_transmit_step(sv, vv, t, sh)) break;
+            }
+            p.color += reqs[r].payload * t.tr;
+        }
+        if (out == VOL_TRACE) {
+            pool.ray_o[slot] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, PT_T_INF);
+            pool.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.f);
+            pool.thr[slot] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, p.emission_weight);
+            pool.col[slot] = make_float4(p.color.x, p.color.y, p.color.z, 0.f);
+            pool.rng[slot] = make_uint2((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32));
+            misc.z = (uint32_t)p.bounce | SLOT_ALIVE;
+            pool.misc[slot] = misc;
+        } else {
+            // the path is over: NaN scrub + splat (vpt.py:260-261); every transmittance was resolved above
+            float* px = accum + (size_t)misc.x * 3;
+            if (!isnan(p.color.x) && p.color.x != 0.f) atomicAdd(px + 0, p.color.x);
+            if (!isnan(p.color.y) && p.color.y != 0.f) atomicAdd(px + 1, p.color.y);
+            if (!isnan(p.color.z) && p.color.z != 0.f) atomicAdd(px + 2, p.color.z);
+            alive = false;
+            finished = 1;
+        }
+    }
+    block_count(n_segments, &ctr->rays_shadow);
+    // regeneration: as in k_logic (striped work ids, excess handed back, neighbours probed when the home stripe is dry)
+    bool need = !alive;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned ballot = __ballot_sync(0xffffffffu, need);
+        if (ballot == 0u) break;
+        const int leader = __ffs(ballot) - 1;
+        const unsigned want = (unsigned)__popc(ballot);
+        const int c_probe = (home + (int)(lane & 3u)) % PT_NSTRIPE;
+        const unsigned long long lim_probe = stripe_limit(work_hi, c_probe);
+        bool has = false;
+        if (lane < 4u) has = *reinterpret_cast<volatile unsigned long long*>(&work[c_probe].claimed) < lim_probe;
+        const unsigned live = __ballot_sync(0xffffffffu, has) & 0xfu;
+        unsigned long long base = 0, limit = 0;
+        int c = home;
+        if (live) {
+            const int pick = __ffs(live) - 1;
+            c = (home + pick) % PT_NSTRIPE;
+            limit = __shfl_sync(0xffffffffu, lim_probe, pick);
+            if ((int)lane == leader) {
+                base = atomicAdd(&work[c].claimed, (unsigned long long)want);
+                if (base + want > limit) {
+                    const unsigned long long ok = base < limit ? limit - base : 0ull;
+                    atomicAdd(&work[c].claimed, (unsigned long long)(0ull - ((unsigned long long)want - ok)));
+                }
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+        }
+        const unsigned long long v = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
+        if (need) {
+            if (live && v < limit) {
+                const unsigned long long id = stripe_item_id(v, c);
+                const unsigned long long s = id / (unsigned long long)n_pixels;
+                const int k = (int)(id - s * (unsigned long long)n_pixels);
+                const int pixel = __ldg(pixel_list + k);
+                const int cnt = (int)(cnt_origin + (long long)s + 1);
+                Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
+                const int i = pixel / sv.height, jj = pixel - i * sv.height;
+                const float3 d = camera_ray(sv, g, i, jj, cnt);
+                pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, PT_T_INF);
+                pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+                pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                     // throughput, emission weight
+                pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
+                pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE, 0u);
+                need = false;
+            } else if (!live || attempt == 3) {
+                if (misc.z & SLOT_ALIVE) {
+                    pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
+                    pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                need = false;
+            }
+        }
+    }
+    block_count(finished, &work[home].done);
+}
+
+// ================================================================================================
 // k_closest / k_shadow: persistent warps over the ray streams.
 //   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements and node counting)
 //   MODE 1: per-lane refill + vote-scheduled traversal of the binary BVH (pt_trace.cuh: trace_stream_vote)
@@ -687,6 +817,8 @@ struct adapt_handle {
     int trace_mode = 2;
     bool fuse_trace = true;
     bool wide_ok = true;
+    int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt; only with ADAPT_ENABLE_VPT=1, not yet run on a GPU)
+    VolumeView vv{};
     int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH (bvh_device.cu)
     int bvh_nodes = 0, bvh_depth = 0;
     float bvh_build_ms = 0.f;
@@ -750,6 +882,20 @@ static int launch_iteration(adapt_handle* h) {
     const int parity = (int)(h->iter_parity & 1u);
     h->iter_parity ^= 1u;
     CK(cudaEventRecord(ev.e[0], st));
+    if (h->integrator == 1) {
+        // volumetric integrator, first version: k_logic_vpt (transmittance resolved inside) + the unchanged closest-hit stream
+        k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+            h->sv, h->vv, h->pool, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin,
+            (unsigned)h->stats.iterations);
+        CK(cudaEventRecord(ev.e[1], st));
+        CK(cudaEventRecord(ev.e[2], st));
+        k_closest<false, 1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, h->refill, h->leaf_t | (h->node_steps << 8));
+        CK(cudaEventRecord(ev.e[3], st));
+        CK(cudaGetLastError());
+        h->stats.iterations += 1;
+        h->stats.kernel_launches += 2;
+        return 0;
+    }
     int n_logic = 0;
     {
         const int lg = h->pool.n_slots / LOGIC_BLOCK;
@@ -947,8 +1093,14 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     if (d->n_prims <= 0 || d->n_objects <= 0 || !d->primitives || !d->n_g || !d->obj_info || !d->emitter_id || !d->bxdfs)
         return set_error(ADAPT_ERR_INVALID, "adapt_create: empty scene or missing arrays");
     if (d->width <= 0 || d->height <= 0) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad film size");
-    if (d->integrator != 0)
-        return set_error(ADAPT_ERR_INVALID, "adapt_create: integrator 1 (vpt, participating media) has no kernels yet -- only `pt` runs on the device; there is no CPU fallback");
+    if (d->integrator != 0) {
+        // vpt: the device functions are verified on the CPU, the kernel that launches them has not run on a GPU yet
+        if (d->integrator != 1 || env_int("ADAPT_ENABLE_VPT", 0) == 0)
+            return set_error(ADAPT_ERR_INVALID, "adapt_create: integrator 1 (vpt, participating media) is not enabled in this build -- only `pt` runs on the device "
+                                                "(ADAPT_ENABLE_VPT=1 switches on the not yet GPU-validated first version); there is no CPU fallback");
+        if (d->brdf_two_sides || d->textures || !d->obj_aabb || d->num_shadow_ray > VOL_MAX_REQUESTS)
+            return set_error(ADAPT_ERR_INVALID, "adapt_create: vpt does not cover two-sided BRDFs, textures or more than 8 shadow rays yet (and needs obj_aabb)");
+    }
     if (d->n_emitters < 0 || (d->n_emitters > 0 && !d->emitters)) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad emitters");
     if (d->n_emitters == 0 && d->num_shadow_ray > 0)
         return set_error(ADAPT_ERR_INVALID, "adapt_create: num_shadow_ray > 0 needs at least one emitter (sample_light would divide by zero)");
@@ -1021,6 +1173,20 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4; h->d_prim_geom = tmp4;
     CKH(dev_upload(h, &tmp4, prim_shade.data(), prim_shade.size())); sv.prim_shade = tmp4; h->d_prim_shade = tmp4;
     adapt_bxdf* dbx = nullptr; CKH(dev_upload(h, &dbx, d->bxdfs, (size_t)no)); sv.bxdfs = dbx;
+    h->integrator = d->integrator;
+    if (h->integrator == 1) {
+        // participating media + the world box of tracer/path_tracer.py:130-138 (objects' boxes and the camera, +- 0.1)
+        adapt_medium clear{}; clear.type = -1; clear.ior = 1.f; clear.pdf[0] = 1.f;
+        std::vector<adapt_medium> media((size_t)no, clear);
+        h->vv.world = clear; h->vv.world.ior = d->world_ior;
+        if (d->media) { for (int o = 0; o < no; o++) media[o] = d->media[o]; h->vv.world = d->media[no]; }
+        adapt_medium* dmd = nullptr; CKH(dev_upload(h, &dmd, media.data(), media.size())); h->vv.media = dmd;
+        float mn[3] = {1e3f, 1e3f, 1e3f}, mx[3] = {-1e3f, -1e3f, -1e3f};
+        for (int o = 0; o < no; o++)
+            for (int a = 0; a < 3; a++) { mn[a] = std::min(mn[a], d->obj_aabb[o * 6 + a]); mx[a] = std::max(mx[a], d->obj_aabb[o * 6 + 3 + a]); }
+        h->vv.w_aabb_min = mk3(std::min(d->cam_t[0], mn[0]) - 0.1f, std::min(d->cam_t[1], mn[1]) - 0.1f, std::min(d->cam_t[2], mn[2]) - 0.1f);
+        h->vv.w_aabb_max = mk3(std::max(d->cam_t[0], mx[0]) + 0.1f, std::max(d->cam_t[1], mx[1]) + 0.1f, std::max(d->cam_t[2], mx[2]) + 0.1f);
+    }
     // ---- textures: descriptors, per-primitive uv, RGBA-float atlases
     sv.textures = nullptr; sv.prim_uv = nullptr;
     for (int m = 0; m < 3; m++) { sv.tex_img[m] = nullptr; sv.tex_size[m] = 0; }

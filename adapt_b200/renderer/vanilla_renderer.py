@@ -63,13 +63,15 @@ class _Counter:
 class Renderer:
     def __init__(self, emitters: List, array_info: dict, objects: List, prop: dict, *, seed: int = 0,
                  device_id: int = 0, pixel_list: Optional[np.ndarray] = None, pool_size: int = 0,
-                 max_bounce: Optional[int] = None, bvh_builder=0):
-        """bvh_builder: 0 / "sah" = host binned-SAH build (default), 1 / "lbvh" = linear BVH built on the device."""
+                 max_bounce: Optional[int] = None, bvh_builder=0, integrator: str = "pt"):
+        """bvh_builder: 0 / "sah" = host binned-SAH build (default), 1 / "lbvh" = linear BVH built on the device.
+        integrator: "pt" (renderer/vanilla_renderer.py); "vpt" (renderer/vpt.py, homogeneous media) is refused by the library unless
+        ADAPT_ENABLE_VPT=1 switches on its first, not yet GPU-validated version."""
         self.clock = TicToc()
         self._lib = load_library()
         self._packed = pack_scene(emitters, array_info, objects, prop, seed=seed, device_id=device_id,
                                   pixel_list=pixel_list, pool_size=pool_size, max_bounce=max_bounce,
-                                  bvh_builder=bvh_builder)
+                                  bvh_builder=bvh_builder, integrator=integrator)
         host = self._packed.host
         # attributes the reference driver / watermark / checkpoint code read
         for key in ("w", "h", "crop_x", "crop_y", "crop_rx", "crop_ry", "do_crop", "start_x", "end_x", "start_y",
