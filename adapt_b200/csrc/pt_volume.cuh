@@ -170,6 +170,22 @@ PT_D float vol_world_bound_time(const VolumeView& vv, float3 o, float3 d) {     
     return fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
 }
 
+// albedo texel of a surface hit: get_uv_item (tracer/path_tracer.py:276-289) -- barycentric blend of the vertex uv on a mesh, spherical
+// coordinates of the normal on a sphere (tracer_base.py:219-221) -- then Texture.query
+PT_D float3 vol_albedo_texel(const SceneView& sv, const HitRec& h, int obj, bool sphere, const Surf& sf) {
+    float tu, tv;
+    if (sphere) {
+        tu = (atan2f(sf.n_g.y, sf.n_g.x) + PT_PI) * PT_INV_2PI;
+        tv = acosf(sf.n_g.z) * PT_INV_PI;
+    } else {
+        const float4 q0 = __ldg(sv.prim_uv + (size_t)h.prim * 2), q1 = __ldg(sv.prim_uv + (size_t)h.prim * 2 + 1);
+        const float bu = h.u, bv = h.v, bw = 1.f - bu - bv;
+        tu = q0.z * bu + q1.x * bv + q0.x * bw;
+        tv = q0.w * bu + q1.y * bv + q0.y * bw;
+    }
+    return texture_query(sv, 0, obj, tu, tv);
+}
+
 // ---------------------------------------------------------------- the loop body between two traces
 struct VolPath {                    // what a path slot carries from one iteration to the next
     float3 ray_o, ray_d, throughput, color;
@@ -196,12 +212,11 @@ PT_D VolOutcome vol_shade_step(const SceneView& sv, const VolumeView& vv, VolPat
     // Step 2 (vpt.py:170-179): what the ray found
     Surf sf; sf.n_s = sf.n_g = mk3(0.f, 1.f, 0.f); sf.t = 0.f;
     int obj = -1;
-    bool in_free_space = true;
+    bool in_free_space = true, sphere = false;
     if (h.prim < 0) {
         if (vv.world.type < 0) return VOL_SPLAT_NOW;                       // nothing hit, no fog: break
         sf.t = vol_world_bound_time(vv, p.ray_o, p.ray_d);
     } else {
-        bool sphere;
         load_surface(sv, h.prim, p.ray_o, p.ray_d, h.t, h.u, h.v, sf, obj, sphere);
         in_free_space = dot(sf.n_g, p.ray_d) < 0.f;
     }
@@ -217,7 +232,19 @@ PT_D VolOutcome vol_shade_step(const SceneView& sv, const VolumeView& vv, VolPat
     } else {
         const int hit_light = is_mi ? -1 : __ldg(sv.obj_info + obj).w;
         Bxdf mat; mat.kind = 0; mat.type = 1; mat.is_delta = 0; mat.k_d = mat.k_s = mat.k_g = mat.mean = mk3(0.f); mat.ior = 1.f;
-        if (!is_mi) mat = load_bxdf(sv.bxdfs + obj);
+        if (!is_mi) {
+            mat = load_bxdf(sv.bxdfs + obj);
+            // it.tex = get_uv_item(albedo_map, ...) (vpt.py:197): the texel stands in for k_d wherever the BxDFs read it.  vpt never
+            // calls process_ns, so normal and bump maps do not apply here.
+            if ((MATS & M_TEXTURED) && sv.textures && has_texture(sv, 0, obj)) mat.k_d = vol_albedo_texel(sv, h, obj, sphere, sf);
+        }
+        // brdf_two_sides (tracer/path_tracer.py:449-453,466-470,486-490): the first BRDF call of this vertex flips both normals IN PLACE
+        // when the ray arrives from behind; in vpt `eval` runs for every valid emitter sample, so the flip precedes eval_le exactly when
+        // next-event estimation evaluated at least one sample, and always precedes the sampling of the new direction.
+        const bool flip_pending = (MATS & M_TWOSIDED) && sv.two_sides && !is_mi && mat.kind == 0 && dot(p.ray_d, sf.n_s) > 0.f;
+        Surf sfb = sf;
+        if (flip_pending) { sfb.n_s = -sf.n_s; sfb.n_g = -sf.n_g; }
+        bool flipped_for_le = false;
         Medium med;
         if (is_mi) med = in_free_space ? load_medium(&vv.world) : load_medium(vv.media + obj);
         // Step 4 (:191-232): next-event estimation
@@ -244,11 +271,12 @@ PT_D VolOutcome vol_shade_step(const SceneView& sv, const VolumeView& vv, VolPat
             const float3 light_dir = to_emitter / emitter_d;
             float3 direct_spec;
             if (is_mi) direct_spec = mk3(medium_eval(med, p.ray_d, light_dir));
-            else direct_spec = mat.kind == 0 ? brdf_eval<MATS>(mat, sf, p.ray_d, light_dir) : bsdf_eval(mat, sf, p.ray_d, light_dir, sv.world_ior);
+            else direct_spec = mat.kind == 0 ? brdf_eval<MATS>(mat, sfb, p.ray_d, light_dir) : bsdf_eval(mat, sf, p.ray_d, light_dir, sv.world_ior);
+            flipped_for_le = true;
             float mis_w = 1.f;
             if (sv.use_mis && !(em.bool_bits & 1)) {
                 const float surf_pdf = is_mi ? direct_spec.x
-                                             : (mat.kind == 0 ? brdf_pdf<MATS>(mat, sf, light_dir, p.ray_d) : bsdf_pdf(mat, sf, light_dir, p.ray_d, sv.world_ior));
+                                             : (mat.kind == 0 ? brdf_pdf<MATS>(mat, sfb, light_dir, p.ray_d) : bsdf_pdf(mat, sf, light_dir, p.ray_d, sv.world_ior));
                 mis_w = balance(emitter_pdf * direct_pdf, surf_pdf);
             }
             // direct_int += direct_spec * (shadow_int * tr) * mis_w / emitter_pdf; tr comes from the transmittance pass
@@ -262,11 +290,12 @@ PT_D VolOutcome vol_shade_step(const SceneView& sv, const VolumeView& vv, VolPat
         }
         // Step 5 (:236-239): emission
         float3 emit_int = mk3(0.f);
-        if (hit_light >= 0) emit_int = emitter_eval_le(load_emitter(sv.emitters + hit_light), hit_point - p.ray_o, sf.n_g);
+        if (hit_light >= 0)
+            emit_int = emitter_eval_le(load_emitter(sv.emitters + hit_light), hit_point - p.ray_o, (flip_pending && flipped_for_le) ? sfb.n_g : sf.n_g);
         // Step 6 (:241-250): new direction
         float3 new_dir, indirect_spec; float ray_pdf; bool is_specular = false;
         if (is_mi) medium_sample_new_ray(med, g, p.ray_d, new_dir, indirect_spec, ray_pdf);
-        else if (mat.kind == 0) brdf_sample<MATS>(mat, sf, p.ray_d, g, new_dir, indirect_spec, ray_pdf, is_specular);
+        else if (mat.kind == 0) brdf_sample<MATS>(mat, sfb, p.ray_d, g, new_dir, indirect_spec, ray_pdf, is_specular);
         else bsdf_sample(mat, sf, p.ray_d, sv.world_ior, g, new_dir, indirect_spec, ray_pdf, is_specular);
         p.ray_d = new_dir;
         p.ray_o = hit_point;
@@ -283,7 +312,7 @@ PT_D VolOutcome vol_shade_step(const SceneView& sv, const VolumeView& vv, VolPat
             const int hl = __ldg(sv.obj_info + obj).w;
             float emitter_pdf = 0.f;
             if (hl >= 0 && sv.bxdfs[obj].is_delta == 0 && !is_specular)
-                emitter_pdf = emitter_solid_angle_pdf(load_emitter(sv.emitters + hl), sf, p.ray_d);
+                emitter_pdf = emitter_solid_angle_pdf(load_emitter(sv.emitters + hl), sfb, p.ray_d);
             p.emission_weight = balance(ray_pdf, emitter_pdf);
         }
     }

@@ -52,7 +52,7 @@ class DevHostScene:
         self.packed = packed
         self.h = self.lib.dev_host_create(C.addressof(packed.desc), int(for_vpt))
         if not self.h:
-            raise NotImplementedError("scene uses brdf_two_sides or textures: not covered by the volumetric device code")
+            raise RuntimeError("dev_host_create failed")
         self.w, self.hh = packed.desc.width, packed.desc.height
 
     def render(self, n_spp: int, cnt_start: int = 0):

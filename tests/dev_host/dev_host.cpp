@@ -23,14 +23,15 @@ struct DevHost {
     std::vector<adapt_bxdf> bxdfs;
     std::vector<adapt_emitter> emitters;
     std::vector<adapt_medium> media;
-    std::vector<int> pixels;
+    std::vector<adapt_texture> textures;
+    std::vector<float4> prim_uv, tex_img[3];
 };
 
 extern "C" {
 
-// for_vpt != 0: refuse what the volumetric device code does not cover yet (two-sided BRDFs, textures)
 DevHost* dev_host_create(const adapt_scene_desc* d, int for_vpt) {
-    if (!d || (for_vpt && (d->brdf_two_sides || d->textures))) return nullptr;
+    (void)for_vpt;
+    if (!d) return nullptr;
     DevHost* h = new DevHost();
     const int np = d->n_prims, no = d->n_objects;
     std::vector<uint8_t> sph((size_t)np, 0), obj_class((size_t)no, 0);
@@ -60,11 +61,35 @@ DevHost* dev_host_create(const adapt_scene_desc* d, int for_vpt) {
     sv.cam_t = mk3(d->cam_t[0], d->cam_t[1], d->cam_t[2]);
     sv.inv_focal = d->inv_focal; sv.half_w = d->half_w; sv.half_h = d->half_h; sv.width = d->width; sv.height = d->height;
     sv.max_bounce = d->max_bounce; sv.num_shadow_ray = d->num_shadow_ray; sv.use_rr = d->use_rr; sv.rr_bounce_th = d->rr_bounce_th;
-    sv.use_mis = d->use_mis; sv.anti_alias = d->anti_alias; sv.stratified = d->stratified_sampling; sv.two_sides = 0;
+    sv.use_mis = d->use_mis; sv.anti_alias = d->anti_alias; sv.stratified = d->stratified_sampling; sv.two_sides = d->brdf_two_sides;
     sv.has_v_normal = d->has_v_normal; sv.rr_threshold = d->rr_threshold; sv.world_ior = d->world_ior;
     sv.inv_num_shadow_ray = d->num_shadow_ray > 0 ? 1.f / (float)d->num_shadow_ray : 1.f;
     sv.seed = d->seed;
+    // textures as adapt_create uploads them: descriptors, per-primitive uv (2 x float4), RGBA-float atlases
     sv.textures = nullptr; sv.prim_uv = nullptr;
+    for (int m = 0; m < 3; m++) { sv.tex_img[m] = nullptr; sv.tex_size[m] = 0; }
+    if (d->textures) {
+        bool any = false;
+        for (int m = 0; m < 3; m++) {
+            if (!d->tex_image[m] || d->tex_size[m] <= 0) continue;
+            const size_t sz = (size_t)d->tex_size[m];
+            h->tex_img[m].resize(sz * sz);
+            for (size_t k = 0; k < sz * sz; k++) h->tex_img[m][k] = make_float4(d->tex_image[m][k * 3], d->tex_image[m][k * 3 + 1], d->tex_image[m][k * 3 + 2], 0.f);
+            sv.tex_img[m] = h->tex_img[m].data(); sv.tex_size[m] = (int)sz;
+            any = true;
+        }
+        if (any) {
+            h->textures.assign(d->textures, d->textures + (size_t)3 * no);
+            sv.textures = h->textures.data();
+            h->prim_uv.assign((size_t)np * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (d->uvs) for (int k = 0; k < np; k++) {
+                const float* q = d->uvs + (size_t)k * 6;
+                h->prim_uv[(size_t)k * 2] = make_float4(q[0], q[1], q[2], q[3]);
+                h->prim_uv[(size_t)k * 2 + 1] = make_float4(q[4], q[5], 0.f, 0.f);
+            }
+            sv.prim_uv = h->prim_uv.data();
+        }
+    }
     // media + world box (tracer/path_tracer.py:130-138)
     adapt_medium clear{}; clear.type = -1; clear.ior = 1.f; clear.pdf[0] = 1.f;
     h->media.assign((size_t)no, clear);
@@ -82,7 +107,7 @@ void dev_host_destroy(DevHost* h) { delete h; }
 
 // Samples cnt_start+1 .. cnt_start+n_spp of every pixel, ADDED to accum (w,h,3); stats: [paths, closest-hit traces, transmittance segments]
 void dev_host_render_vpt(DevHost* h, int cnt_start, int n_spp, float* accum, uint64_t* stats) {
-    constexpr int MATS = M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF;
+    constexpr int MATS = M_ALL | M_TEXTURED;                      // every material group, two-sided BRDFs, albedo textures
     const SceneView& sv = h->sv;
     uint64_t n_paths = 0, n_trace = 0, n_seg = 0;
     #pragma omp parallel for schedule(dynamic, 16) reduction(+ : n_paths, n_trace, n_seg)

@@ -27,7 +27,9 @@ def _flip(img, ref):
 CASES = [("cbox", "cbox.xml", 24, 4, {}), ("test", "media.xml", 32, 4, {}), ("test", "media-clear.xml", 32, 4, {}),
          ("test", "media.xml", 24, 3, dict(use_mis=False, use_rr=False, max_bounce=6)),
          ("test", "media-clear.xml", 24, 2, dict(num_shadow_ray=3)),
-         ("csphere", "balls-mono.xml", 24, 3, {})]                      # no media at all: vpt degenerates to surface transport
+         ("csphere", "balls-mono.xml", 24, 3, {}),                     # no media at all: vpt degenerates to surface transport
+         ("test", "allbxdf.xml", 24, 3, {}),                           # every BRDF / BSDF model, brdf_two_sides, five emitter kinds
+         ("test", "textured.xml", 24, 3, {})]                          # albedo textures on meshes and spheres (normal / bump maps: not in vpt)
 
 
 @pytest.mark.parametrize("scene,name,size,spp,kw", CASES)
@@ -102,15 +104,6 @@ def test_medium_functions_equal_the_oracles(oracle_lib, kind, par, pdf):
         np.testing.assert_allclose(b1, b2, rtol=1e-5)
 
 
-def test_two_sided_and_textured_scenes_are_refused(scene_root):
-    """Not covered by the volumetric device code yet: refused, not rendered differently."""
-    from adapt_b200._lib import pack_scene
-    from dev_host import DevHostScene
-    e, a, o, c = load_scene(scene_root, "test", "allbxdf.xml", 8, 8)          # brdf_two_sides = true
-    with pytest.raises(NotImplementedError):
-        DevHostScene(pack_scene(e, a, o, c, integrator="vpt"))
-
-
 @pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="needs nvcc (cross-compiles without a GPU)")
 def test_volume_header_compiles_for_sm_100a(tmp_path):
     """nvcc -gencode arch=compute_100a,code=sm_100a on a kernel that instantiates vol_shade_step / vol_transmit_step: the header is
@@ -125,7 +118,7 @@ __global__ void k_vol_check(SceneView sv, VolumeView vv, VolPath* paths, const H
     if (i >= n) return;
     VolPath p = paths[i];
     VolRequest r[VOL_MAX_REQUESTS]; int nr = 0;
-    outcome[i] = (int)vol_shade_step<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, vv, p, hits[i], r, nr);
+    outcome[i] = (int)vol_shade_step<M_ALL | M_TEXTURED>(sv, vv, p, hits[i], r, nr);
     for (int k = 0; k < nr; k++) {
         VolTransmit t; vol_transmit_begin(t, r[k]);
         HitRec h; unsigned a = 0, b = 0;
