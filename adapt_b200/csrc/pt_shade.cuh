@@ -8,8 +8,8 @@
 //   sampler/general_sampling.py:29-123, sampler/microfacet.py:28-177, la/cam_transform.py:51-105,
 //   la/geo_optics.py:14-75
 // Quirks of the reference estimator are kept on purpose (SURVEY.md section 8(a) "Quirks"): they
-// define the expected image.  Textures are not wired yet, so the diffuse colour is always k_d
-// (Interaction.tex == INVALID, tracer/path_tracer.py:279).
+// define the expected image.  The diffuse colour is m.k_d: the caller replaces it by the albedo texel when the object carries an
+// albedo map (`select(it.is_tex_invalid(), k_d, it.tex)` in every reference model; texture_query below).
 #pragma once
 #include "pt_common.cuh"
 

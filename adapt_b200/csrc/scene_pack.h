@@ -11,6 +11,7 @@
 inline void pack_geometry(const float* primitives, const float* n_g, const float* n_s, int np, const std::vector<uint8_t>& sph,
                           const std::vector<int32_t>& prim_obj, std::vector<float4>& prim_geom, std::vector<float4>& prim_shade) {
     prim_geom.resize((size_t)np * 3); prim_shade.resize((size_t)np * 4);
+    #pragma omp parallel for schedule(static) if (np > 4096)
     for (int k = 0; k < np; k++) {
         const float* v = primitives + (size_t)k * 9;
         if (sph[k]) {
