@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libadapt_b200.so")
 SOURCES = ["adapt_abi.cu", "bvh_device.cu", "bvh_build.cpp"]
-HEADERS = ["pt_common.cuh", "pt_shade.cuh", "pt_trace.cuh", "pt_path.cuh", "scene_pack.h", "bvh_build.h", "bvh_device.h", "bvh_lbvh.h", os.path.join("..", "..", "include", "adapt_b200.h")]
+HEADERS = ["pt_common.cuh", "pt_shade.cuh", "pt_trace.cuh", "pt_path.cuh", "pt_volume.cuh", "pt_kernels.cuh", "scene_pack.h", "bvh_build.h", "bvh_device.h", "bvh_lbvh.h", os.path.join("..", "..", "include", "adapt_b200.h")]
 
 
 def nvcc_path() -> str:

@@ -49,745 +49,7 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-// ================================================================================================
-// device helpers
-// ================================================================================================
-
-#ifndef LOGIC_BLOCK
-#define LOGIC_BLOCK 256
-#endif
-// resident blocks per SM the k_logic instantiations are compiled for (measured on B200, profiles/r01c_ab.txt: the heavy-material
-// kernels gain 20 % going from 2 to 3 blocks and another 4-8 % at 4 although ptxas then spills; the simple one 5 % from 3 to 4)
-#ifndef LOGIC_MIN_BLOCKS
-#define LOGIC_MIN_BLOCKS 4
-#endif
-#ifndef LOGIC_MIN_BLOCKS_SIMPLE
-#define LOGIC_MIN_BLOCKS_SIMPLE 4
-#endif
-#ifndef TRACE_BLOCK
-#define TRACE_BLOCK 128
-#endif
-#ifndef TRACE_MIN_BLOCKS
-#define TRACE_MIN_BLOCKS 9
-#endif
-// sort keys of k_logic's block-local regrouping: material classes 0..10 (BRDF type 0..7, BSDF det-refraction 8, BSDF
-// Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot
-#define LOGIC_NKEY 13
-
-// Block-wide allocation from a global counter: every thread passes `want` (0/1), gets its index.
-// Two barriers, one atomic per block. Must be called by all threads of the block.
-template <typename CounterT>
-__device__ __forceinline__ CounterT block_alloc(bool want, CounterT* counter, unsigned* s_warp, CounterT* s_base) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned ballot = __ballot_sync(0xffffffffu, want);
-    const unsigned rank = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) s_warp[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned tot = 0;
-        #pragma unroll
-        for (int w = 0; w < LOGIC_BLOCK / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
-        *s_base = tot ? atomicAdd(counter, (CounterT)tot) : (CounterT)0;
-    }
-    __syncthreads();
-    CounterT idx = *s_base + (CounterT)(s_warp[warp] + rank);
-    __syncthreads();       // s_warp / s_base are reused by the next call
-    return idx;
-}
-
-// Warp-aggregated allocation: one atomic per warp, no block barrier. Must be called by all 32 lanes.
-template <typename CounterT>
-__device__ __forceinline__ CounterT warp_alloc(bool want, CounterT* counter) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned ballot = __ballot_sync(0xffffffffu, want);
-    if (ballot == 0u) return (CounterT)0;
-    const int leader = __ffs(ballot) - 1;
-    CounterT base = 0;
-    if ((int)lane == leader) base = atomicAdd(counter, (CounterT)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + (CounterT)__popc(ballot & ((1u << lane) - 1u));
-}
-
-__device__ __forceinline__ void block_count(unsigned v, unsigned long long* counter) {
-    // warp reduce then one atomic per warp (only used for statistics)
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
-}
-
-// conservative ray / box test (same slab arithmetic as the traversal, with slack): false only if the ray cannot hit anything inside
-__device__ __forceinline__ bool ray_hits_box(float3 o, float3 d, float3 lo, float3 hi) {
-    const RayPre r = make_ray(o, d);
-    float t0x = fmaf(lo.x, r.idir.x, -r.ood.x), t1x = fmaf(hi.x, r.idir.x, -r.ood.x);
-    float t0y = fmaf(lo.y, r.idir.y, -r.ood.y), t1y = fmaf(hi.y, r.idir.y, -r.ood.y);
-    float t0z = fmaf(lo.z, r.idir.z, -r.ood.z), t1z = fmaf(hi.z, r.idir.z, -r.ood.z);
-    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
-    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), PT_T_INF));
-    return tmin <= tmax * 1.00001f;
-}
-
-// ================================================================================================
-// k_classify: global per-class slot lists (scenes with several material groups)
-// ================================================================================================
-// ncu on orb500k after the block-local regrouping: stall_no_instruction is 46 % of k_logic's stall samples (11 cycles per issue
-// in the worst capture).  The all-model kernel is ~110 KB of SASS against a 32 KB L1.5 instruction cache, and with the blocks of
-// one SM working on every class at once the fetch working set is the whole kernel.  So the classes are separated ACROSS the chip:
-// this kernel sorts each block's 256 slots by class (same keys as the in-kernel sort) and appends the segments to one global
-// index list per class; k_logic then runs once per material group over that group's lists, class after class, so the blocks
-// resident on an SM at any time execute the same few KB of code.  Counters are double-buffered by iteration parity like the
-// shadow queue's.
-struct KeySet { int k[8]; };          // the class keys one k_logic launch covers (-1 = unused)
-
-__global__ void __launch_bounds__(LOGIC_BLOCK)
-k_classify(const PathPool pool, const ShadowQueue sq, Cursors* __restrict__ cur, unsigned* __restrict__ cls_items,
-           CursorStripe* __restrict__ cls_count, const int parity) {
-    __shared__ unsigned s_cnt[LOGIC_NKEY * (LOGIC_BLOCK / 32)];
-    __shared__ unsigned s_base[LOGIC_NKEY];
-    const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
-    if (tslot < PT_NCURSOR) {
-        cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0;
-        cls_count[(parity ^ 1) * 16 + tslot].v = 0;
-    }
-    const uint4 m0 = pool.misc[tslot];
-    int key = LOGIC_NKEY - 1;                                           // free slot
-    if (m0.z & SLOT_ALIVE) {
-        const int hw = __float_as_int(pool.hit[tslot].w);
-        key = ((m0.z & SLOT_FINISH) || hw < 0) ? LOGIC_NKEY - 2          // path ends here: splat, then regenerate
-                                               : min((hw >> PT_HIT_PRIM_BITS) & 15, LOGIC_NKEY - 3);
-    }
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned my_rank = 0;
-    #pragma unroll
-    for (int k = 0; k < LOGIC_NKEY; k++) {
-        const unsigned b = __ballot_sync(0xffffffffu, key == k);
-        if (key == k) my_rank = __popc(b & ((1u << lane) - 1u));
-        if (lane == 0) s_cnt[k * (LOGIC_BLOCK / 32) + warp] = __popc(b);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        constexpr int n_ent = LOGIC_NKEY * (LOGIC_BLOCK / 32);
-        constexpr int EPL = (n_ent + 31) / 32;
-        unsigned v[EPL], sum = 0;
-        #pragma unroll
-        for (int q = 0; q < EPL; q++) { const int e = (int)lane * EPL + q; v[q] = e < n_ent ? s_cnt[e] : 0u; sum += v[q]; }
-        unsigned incl = sum;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-        unsigned run = incl - sum;
-        #pragma unroll
-        for (int q = 0; q < EPL; q++) { const int e = (int)lane * EPL + q; if (e < n_ent) s_cnt[e] = run; run += v[q]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < LOGIC_NKEY) {
-        const unsigned lo = s_cnt[threadIdx.x * (LOGIC_BLOCK / 32)];
-        const unsigned hi = threadIdx.x + 1 < LOGIC_NKEY ? s_cnt[(threadIdx.x + 1) * (LOGIC_BLOCK / 32)] : (unsigned)LOGIC_BLOCK;
-        s_base[threadIdx.x] = hi > lo ? atomicAdd(&cls_count[parity * 16 + threadIdx.x].v, hi - lo) : 0u;
-    }
-    __syncthreads();
-    const unsigned in_key = s_cnt[key * (LOGIC_BLOCK / 32) + warp] + my_rank - s_cnt[key * (LOGIC_BLOCK / 32)];
-    cls_items[(size_t)key * (size_t)pool.n_slots + s_base[key] + in_key] = (unsigned)tslot;
-}
-
-// ================================================================================================
-// k_logic
-// ================================================================================================
-template <int MATS, bool LISTED>
-__global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
-k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
-        Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-        const unsigned long long work_hi, const long long cnt_origin, const int parity, const unsigned rot,
-        const unsigned* __restrict__ cls_items, const CursorStripe* __restrict__ cls_count, const KeySet keys) {
-    const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
-    // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
-    if (!LISTED && tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
-    // work stripe of this warp (pt_common.cuh: WorkStripe).  The window of four stripes a warp probes moves on with every
-    // launch, so a pool with fewer warps than stripes (tiny pools, tests) still reaches every stripe.
-    const int home = (int)(((unsigned)(tslot >> 5) + 4u * rot) % PT_NSTRIPE);
-
-    // Scenes that mix material groups run in "listed" mode: k_classify has sorted the slots into global per-class lists and this
-    // launch covers the classes in `keys` (see k_classify).  Otherwise thread t owns slot t.
-    int slot = tslot;
-    if (LISTED) {
-        // listed mode (k_classify): global thread g works on the g-th entry of this launch's class lists, class after class
-        unsigned g = (unsigned)tslot;
-        slot = -1;
-        #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (keys.k[q] < 0 || slot >= 0) continue;
-            const unsigned n = __ldg(&cls_count[parity * 16 + keys.k[q]].v);
-            if (g < n) slot = (int)__ldg(cls_items + (size_t)keys.k[q] * (size_t)pool.n_slots + g);
-            else g -= n;
-        }
-        if (!__any_sync(0xffffffffu, slot >= 0)) return;              // past the end of the lists
-    }
-    const bool listed_idle = LISTED && slot < 0;                      // only in the last warp of a listed launch
-    uint4 misc = listed_idle ? make_uint4(0u, 0u, 0u, 0u) : pool.misc[slot];
-    bool alive = (misc.z & SLOT_ALIVE) != 0;
-    // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
-    if (!__any_sync(0xffffffffu, alive)) {
-        bool dry = true;
-        if ((threadIdx.x & 31) < 4) {
-            const int c = (home + (int)(threadIdx.x & 31)) % PT_NSTRIPE;
-            dry = *reinterpret_cast<volatile unsigned long long*>(&work[c].claimed) >= stripe_limit(work_hi, c);
-        }
-        if (__all_sync(0xffffffffu, dry)) return;
-    }
-    bool terminate = false;
-    bool shading = false;
-
-    // path registers (valid when shading)
-    float3 ray_o = mk3(0.f), ray_d = mk3(0.f, 0.f, 1.f), contribution = mk3(1.f), color = mk3(0.f);
-    float ray_pdf = 1.f, emission_weight = 1.f;
-    Rng rng; rng.state = 0;
-    Surf sf; sf.n_s = sf.n_g = mk3(1.f, 0.f, 0.f); sf.t = 0.f;
-    Bxdf mat; mat.kind = 0; mat.type = 1; mat.is_delta = 0; mat.k_d = mat.k_s = mat.k_g = mat.mean = mk3(0.f); mat.ior = 1.f;
-    int obj = 0, hit_light = -1, bounce = 0;
-    float3 hit_point = mk3(0.f);
-    bool flip_pending = false;   // brdf_two_sides: normals flip at the first BRDF call of this bounce
-
-    if (alive) {
-        // all per-slot state in one batch of independent 128-bit loads (one memory round trip)
-        const float4 c4 = pool.col[slot];
-        const float4 h4 = pool.hit[slot];
-        const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
-        const uint2 r2 = pool.rng[slot];
-        bounce = (int)(misc.z & 0xffffu);
-        color = mk3(c4.x, c4.y, c4.z);
-        const int hit_word = __float_as_int(h4.w);
-        const int prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
-        if ((misc.z & SLOT_FINISH) || prim < 0) {
-            terminate = true;                                        // finished last bounce / "if it.is_ray_not_hit(): break"
-        } else {
-            ray_o = mk3(o4.x, o4.y, o4.z); ray_d = mk3(d4.x, d4.y, d4.z);
-            contribution = mk3(t4.x, t4.y, t4.z); ray_pdf = t4.w;
-            rng.state = ((uint64_t)r2.y << 32) | r2.x;
-            bool sphere;
-            load_surface(sv, prim, ray_o, ray_d, h4.x, h4.y, h4.z, sf, obj, sphere);
-            const int4 oi = __ldg(sv.obj_info + obj);
-            hit_light = oi.w;
-            mat = load_bxdf(sv.bxdfs + obj);
-            if ((MATS & M_TEXTURED) && sv.textures) {
-                // get_uv_item (path_tracer.py:276-289): local (u, v) = barycentrics, or spherical coordinates on a sphere
-                // (tracer_base.py:219-221); meshes interpolate their per-vertex uv.  process_ns (:291-307) touches the PRIMARY hit
-                // only (vanilla_renderer.py:42, quirk 3); the albedo lookup happens at every bounce (:66) and replaces k_d wherever
-                // the BxDFs read it (`select(it.is_tex_invalid(), k_d, it.tex)` at every use, bxdf/brdf.py, bxdf/bsdf.py).
-                const bool t_alb = has_texture(sv, 0, obj);
-                const bool t_nrm = bounce == 0 && has_texture(sv, 1, obj), t_bmp = bounce == 0 && has_texture(sv, 2, obj);
-                if (t_alb || t_nrm || t_bmp) {
-                    float tu, tv;
-                    if (sphere) {
-                        tu = (atan2f(sf.n_g.y, sf.n_g.x) + PT_PI) * PT_INV_2PI;
-                        tv = acosf(sf.n_g.z) * PT_INV_PI;
-                    } else {
-                        const float4 q0 = __ldg(sv.prim_uv + (size_t)prim * 2), q1 = __ldg(sv.prim_uv + (size_t)prim * 2 + 1);
-                        const float bu = h4.y, bv = h4.z, bw = 1.f - bu - bv;
-                        tu = q0.z * bu + q1.x * bv + q0.x * bw;
-                        tv = q0.w * bu + q1.y * bv + q0.y * bw;
-                    }
-                    if (t_nrm) sf.n_s = to_world(sf.n_g, texture_query(sv, 1, obj, tu, tv));
-                    if (t_bmp) sf.n_s = to_world(sf.n_s, texture_query(sv, 2, obj, tu, tv));
-                    if (t_alb) mat.k_d = texture_query(sv, 0, obj, tu, tv);
-                }
-            }
-            // emission MIS weight for the hit just found (vanilla_renderer.py:111-117); quirk 1/2:
-            // tests is_delta of the *hit* object and the is_specular flag of the previous sample
-            if (bounce > 0 && sv.use_mis) {
-                float emitter_pdf = 0.f;
-                if (hit_light >= 0 && mat.is_delta == 0 && !(misc.z & SLOT_SPECULAR))
-                    emitter_pdf = emitter_solid_angle_pdf(load_emitter(sv.emitters + hit_light), sf, ray_d);
-                emission_weight = balance(ray_pdf, emitter_pdf);
-            }
-            // Russian roulette / cut-off (:50-57)
-            if (sv.use_rr) {
-                float mv = vmax(contribution);
-                if (mv < sv.rr_threshold && bounce >= sv.rr_bounce_th) {
-                    if (rng.rand_f() > mv) terminate = true;
-                    else contribution *= 1.f / (mv + 1e-7f);
-                }
-            } else if (vmax(contribution) < 1e-4f) {
-                terminate = true;
-            }
-            shading = !terminate;
-        }
-    }
-
-    // ---------------------------------------------------------------- next-event estimation (:67-97)
-    float3 direct_inline = mk3(0.f);      // payloads resolved inside this kernel (two-sided corner case)
-    bool flipped_for_le = false;          // has a BRDF call flipped the normals before eval_le?
-    if (shading) {
-        hit_point = ray_d * sf.t + ray_o;
-        flip_pending = (MATS & M_TWOSIDED) && sv.two_sides && mat.kind == 0 && dot(ray_d, sf.n_s) > 0.f;
-    }
-    Surf sfb = sf;                         // normals as the BRDF sees them (flipped when two-sided and back-facing)
-    if (flip_pending) { sfb.n_s = -sf.n_s; sfb.n_g = -sf.n_g; }
-    const bool le_corner = shading && flip_pending && hit_light >= 0;
-    bool break_flag = false;
-    unsigned n_inline = 0;
-    const int q_seg = (int)((unsigned)(tslot >> 5) % PT_NCURSOR);              // this (physical) warp's segment of the shadow queue
-    unsigned* const q_count = &sq.seg_count[parity * PT_NCURSOR + q_seg].v;
-    for (int j = 0; j < sv.num_shadow_ray; j++) {
-        bool want = false;
-        float4 q_o = make_float4(0.f, 0.f, 0.f, 0.f), q_d = q_o, q_c = q_o;
-        if (shading && !break_flag) {
-            // sample_light (path_tracer.py:537-554)
-            int idx = floor_mod(rng.rand_i(), sv.n_emitters);
-            float emitter_pdf = 1.f / (float)sv.n_emitters;
-            bool valid = true;
-            if (hit_light >= 0) {
-                if (sv.n_emitters <= 1) valid = false;
-                else {
-                    idx = floor_mod(rng.rand_i(), sv.n_emitters - 1);
-                    if (idx >= hit_light) idx += 1;
-                    emitter_pdf = 1.f / (float)(sv.n_emitters - 1);
-                }
-            }
-            if (!valid) {
-                break_flag = true;
-            } else {
-                const Emitter em = load_emitter(sv.emitters + idx);
-                float3 emit_pos, shadow_int; float direct_pdf;
-                emitter_sample_hit(sv, em, hit_point, rng, emit_pos, shadow_int, direct_pdf);
-                float3 to_emitter = emit_pos - hit_point;
-                float emitter_d = norm(to_emitter);
-                float3 light_dir = to_emitter / emitter_d;
-                float3 direct_spec = (!(MATS & M_BSDF) || mat.kind == 0) ? brdf_eval<MATS>(mat, sfb, ray_d, light_dir)
-                                                                         : bsdf_eval(mat, sf, ray_d, light_dir, sv.world_ior);
-                float mis_w = 1.f;
-                const bool delta_pos = (em.bool_bits & 1) != 0;
-                if (sv.use_mis && !delta_pos) {
-                    float surf_pdf = (!(MATS & M_BSDF) || mat.kind == 0) ? brdf_pdf<MATS>(mat, sfb, light_dir, ray_d)
-                                                                         : bsdf_pdf(mat, sf, light_dir, ray_d, sv.world_ior);
-                    mis_w = balance(emitter_pdf * direct_pdf, surf_pdf);
-                    flipped_for_le = true;             // surface_pdf always runs -> flip happened
-                }
-                float3 payload = sv.use_mis ? direct_spec * shadow_int * mis_w / emitter_pdf
-                                            : direct_spec * shadow_int / emitter_pdf;
-                payload = payload * sv.inv_num_shadow_ray * contribution;
-                const bool nonzero = !is_zero3(payload);
-                if (!isfinite(mis_w)) {
-                    // The reference multiplies the (zeroed) shadow intensity by mis_w even when the
-                    // shadow ray is occluded, so a NaN/inf MIS weight poisons the whole path either
-                    // way (0 * NaN): no shadow ray needed, and the NaN scrub later drops the sample.
-                    direct_inline += mk3(nanf(""));
-                } else if ((MATS & M_TWOSIDED) && le_corner && !flipped_for_le) {
-                    // eval() only runs (and flips the normals) when the shadow ray is unoccluded: the
-                    // outcome decides which normal eval_le sees, so resolve it here (rare path)
-                    HitRec hr; unsigned nn = 0, np = 0;
-                    float tmax = emitter_d > 0.f ? emitter_d - 1e-4f : PT_T_INF;
-                    bool occluded = trace<true, false>(sv, hit_point, light_dir, tmax, hr, nn, np);
-                    n_inline++;
-                    if (!occluded) { flipped_for_le = true; direct_inline += payload; }
-                } else if (nonzero) {
-                    want = true;
-                    q_o = make_float4(hit_point.x, hit_point.y, hit_point.z, emitter_d);
-                    q_d = make_float4(light_dir.x, light_dir.y, light_dir.z, __int_as_float(slot));
-                    q_c = make_float4(payload.x, payload.y, payload.z, 0.f);
-                }
-            }
-        }
-        const unsigned qi = (unsigned)q_seg * (unsigned)sq.seg_cap + warp_alloc<unsigned>(want, q_count);
-        if (want) { sq.o[qi] = q_o; sq.d[qi] = q_d; sq.c[qi] = q_c; }
-    }
-
-    // ---------------------------------------------------------------- emission, BSDF sampling, throughput (:99-109)
-    if (shading) {
-        float3 emit_int = mk3(0.f);
-        if (hit_light >= 0) {
-            const float3 n_le = (flip_pending && flipped_for_le) ? sfb.n_s : sf.n_s;
-            emit_int = emitter_eval_le(load_emitter(sv.emitters + hit_light), hit_point - ray_o, n_le);
-        }
-        float3 new_dir, indirect_spec; float new_pdf; bool is_specular;
-        if (!(MATS & M_BSDF) || mat.kind == 0) brdf_sample<MATS>(mat, sfb, ray_d, rng, new_dir, indirect_spec, new_pdf, is_specular);
-        else bsdf_sample(mat, sf, ray_d, sv.world_ior, rng, new_dir, indirect_spec, new_pdf, is_specular);
-        color += (direct_inline + emit_int * emission_weight * contribution);
-        contribution *= indirect_spec / new_pdf;
-        bounce += 1;
-        uint32_t flags = SLOT_ALIVE | (is_specular ? SLOT_SPECULAR : 0u);
-        float tmax = PT_T_INF;
-        if (bounce >= sv.max_bounce) { flags |= SLOT_FINISH; tmax = -1.f; }   // the reference's last trace is never used
-        pool.ray_o[slot] = make_float4(hit_point.x, hit_point.y, hit_point.z, tmax);
-        pool.ray_d[slot] = make_float4(new_dir.x, new_dir.y, new_dir.z, 0.f);
-        pool.thr[slot] = make_float4(contribution.x, contribution.y, contribution.z, new_pdf);
-        pool.col[slot] = make_float4(color.x, color.y, color.z, 0.f);
-        pool.rng[slot] = make_uint2((uint32_t)rng.state, (uint32_t)(rng.state >> 32));
-        misc.z = (uint32_t)bounce | flags;
-        pool.misc[slot] = misc;
-    }
-
-    // ---------------------------------------------------------------- termination: NaN scrub + splat (:119)
-    if (alive && terminate) {
-        float* px = accum + (size_t)misc.x * 3;
-        if (!isnan(color.x) && color.x != 0.f) atomicAdd(px + 0, color.x);
-        if (!isnan(color.y) && color.y != 0.f) atomicAdd(px + 1, color.y);
-        if (!isnan(color.z) && color.z != 0.f) atomicAdd(px + 2, color.z);
-        alive = false;
-    }
-    unsigned finished = (alive || !terminate) ? 0u : 1u;
-    block_count(n_inline, &ctr->shadow_inline);
-
-    // ---------------------------------------------------------------- regeneration
-    // A free slot takes the next work id of the warp's stripe: id -> sample cnt_origin + id / n_pixels + 1 of pixel
-    // pixel_list[id % n_pixels].  A stripe never hands out more than stripe_limit(work_hi): a claim that overshoots
-    // gives the excess back, so between launches `claimed` is exact and ids stay gap-free across adapt_render calls.
-    // If the home stripe is dry the warp tries its neighbours (tail of a work range only).
-    // A camera ray that misses the scene's bounding box ends its path on the spot (colour 0, nothing to splat):
-    // the slot immediately takes the next work item instead of spending a whole wavefront iteration on it.
-    bool need = !alive && !shading && !listed_idle;
-    unsigned culled = 0;
-    const bool may_cull = sv.cull_primary && sv.max_bounce > 0;
-    for (int attempt = 0; attempt < 4; attempt++) {
-        const unsigned lane = threadIdx.x & 31;
-        const unsigned ballot = __ballot_sync(0xffffffffu, need);
-        if (ballot == 0u) break;
-        const int leader = __ffs(ballot) - 1;
-        const unsigned want = (unsigned)__popc(ballot);
-        // pick a stripe with work left: lanes 0..3 look at home, home+1, home+2, home+3 (one round trip)
-        const int c_probe = (home + (int)(lane & 3u)) % PT_NSTRIPE;
-        const unsigned long long lim_probe = stripe_limit(work_hi, c_probe);
-        bool has = false;
-        if (lane < 4u) has = *reinterpret_cast<volatile unsigned long long*>(&work[c_probe].claimed) < lim_probe;
-        const unsigned live = __ballot_sync(0xffffffffu, has) & 0xfu;
-        unsigned long long base = 0, limit = 0;
-        int c = home;
-        if (live) {
-            const int pick = __ffs(live) - 1;
-            c = (home + pick) % PT_NSTRIPE;
-            limit = __shfl_sync(0xffffffffu, lim_probe, pick);
-            if ((int)lane == leader) {
-                base = atomicAdd(&work[c].claimed, (unsigned long long)want);
-                if (base + want > limit) {                        // overshoot: hand the excess back
-                    const unsigned long long ok = base < limit ? limit - base : 0ull;
-                    atomicAdd(&work[c].claimed, (unsigned long long)(0ull - ((unsigned long long)want - ok)));
-                }
-            }
-            base = __shfl_sync(0xffffffffu, base, leader);
-        }
-        const unsigned long long v = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
-        if (need) {
-            if (live && v < limit) {
-                const unsigned long long id = stripe_item_id(v, c);
-                const unsigned long long s = id / (unsigned long long)n_pixels;
-                const int k = (int)(id - s * (unsigned long long)n_pixels);
-                const int pixel = __ldg(pixel_list + k);
-                const int cnt = (int)(cnt_origin + (long long)s + 1);
-                Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
-                const int i = pixel / sv.height, jj = pixel - i * sv.height;
-                float3 d = camera_ray(sv, g, i, jj, cnt);
-                if (may_cull && attempt < 3 && !ray_hits_box(sv.cam_t, d, sv.world_lo, sv.world_hi)) {
-                    culled++;                       // path over: ray_intersect would return a miss
-                } else {
-                    // max_bounce <= 0: the reference still traces the primary ray but never enters the loop
-                    const bool no_loop = sv.max_bounce <= 0;
-                    pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, no_loop ? -1.f : PT_T_INF);
-                    pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
-                    pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
-                    need = false;
-                }
-            } else if (!live || attempt == 3) {
-                if (misc.z & SLOT_ALIVE) {
-                    // out of work (for now): park the slot
-                    pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
-                    pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                need = false;
-            }
-            // else: the stripe ran dry under this claim -- try again (next attempt probes the neighbours)
-        }
-    }
-    finished += culled;
-    block_count(finished, &work[home].done);
-    if (may_cull) block_count(culled, &ctr->rays_culled);
-}
-
-// ================================================================================================
-// k_logic_vpt: the volumetric integrator's step between two closest-hit traces (pt_volume.cuh: vol_shade_step), first version.
-// ================================================================================================
-// Thread t owns slot t.  The next-event transmittance (track_ray, up to seven closest-hit segments through null surfaces and
-// media) is resolved INSIDE this kernel with the single-ray traversal, like k_logic's rare two-sided corner case -- correct but
-// divergent; moving it to a re-arming stream of k_trace is the planned second version.  Path continuation rays
-// go through the unchanged k_closest stream.  Slot layout as for `pt`, except that thr.w carries the emission weight.
-// NOT YET RUN ON A GPU: adapt_create only accepts integrator = 1 with ADAPT_ENABLE_VPT=1 (the functions it calls are verified on
-// the CPU, tests/test_vpt_device_code.py; this glue is not).
-template <int MATS>
-__global__ void __launch_bounds__(LOGIC_BLOCK, 2)
-k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
-            Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-            const unsigned long long work_hi, const long long cnt_origin, const unsigned rot) {
-    const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
-    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; }
-    const int home = (int)(((unsigned)(slot >> 5) + 4u * rot) % PT_NSTRIPE);
-    uint4 misc = pool.misc[slot];
-    bool alive = (misc.z & SLOT_ALIVE) != 0;
-    if (!__any_sync(0xffffffffu, alive)) {
-        bool dry = true;
-        if ((threadIdx.x & 31) < 4) {
-            const int c = (home + (int)(threadIdx.x & 31)) % PT_NSTRIPE;
-            dry = *reinterpret_cast<volatile unsigned long long*>(&work[c].claimed) >= stripe_limit(work_hi, c);
-        }
-        if (__all_sync(0xffffffffu, dry)) return;
-    }
-    unsigned finished = 0, n_segments = 0;
-    if (alive) {
-        const float4 c4 = pool.col[slot], h4 = pool.hit[slot], o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
-        const uint2 r2 = pool.rng[slot];
-        VolPath p;
-        p.ray_o = mk3(o4.x, o4.y, o4.z); p.ray_d = mk3(d4.x, d4.y, d4.z);
-        p.throughput = mk3(t4.x, t4.y, t4.z); p.emission_weight = t4.w;
-        p.color = mk3(c4.x, c4.y, c4.z);
-        p.bounce = (int)(misc.z & 0xffffu);
-        p.rng.state = ((uint64_t)r2.y << 32) | r2.x;
-        HitRec h; h.t = h4.x; h.u = h4.y; h.v = h4.z; h.obj = 0; h.cls = 0;
-        const int hit_word = __float_as_int(h4.w);
-        h.prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
-        VolRequest reqs[VOL_MAX_REQUESTS]; int n_req = 0;
-        const VolOutcome out = vol_shade_step<MATS>(sv, vv, p, h, reqs, n_req);
-        for (int r = 0; r < n_req; r++) {
-            VolTransmit t; vol_transmit_begin(t, reqs[r]);
-            while (true) {
-                HitRec sh; unsigned nn = 0, np = 0;
-                trace<false, false>(sv, t.point, t.dir, vol_transmit_tmax(t), sh, nn, np);
-                n_segments++;
-                if (!vol_transmit_step(sv, vv, t, sh)) break;
-            }
-            p.color += reqs[r].payload * t.tr;
-        }
-        if (out == VOL_TRACE) {
-            pool.ray_o[slot] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, PT_T_INF);
-            pool.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.f);
-            pool.thr[slot] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, p.emission_weight);
-            pool.col[slot] = make_float4(p.color.x, p.color.y, p.color.z, 0.f);
-            pool.rng[slot] = make_uint2((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32));
-            misc.z = (uint32_t)p.bounce | SLOT_ALIVE;
-            pool.misc[slot] = misc;
-        } else {
-            // the path is over: NaN scrub + splat (vpt.py:260-261); every transmittance was resolved above
-            float* px = accum + (size_t)misc.x * 3;
-            if (!isnan(p.color.x) && p.color.x != 0.f) atomicAdd(px + 0, p.color.x);
-            if (!isnan(p.color.y) && p.color.y != 0.f) atomicAdd(px + 1, p.color.y);
-            if (!isnan(p.color.z) && p.color.z != 0.f) atomicAdd(px + 2, p.color.z);
-            alive = false;
-            finished = 1;
-        }
-    }
-    block_count(n_segments, &ctr->rays_shadow);
-    // regeneration: as in k_logic (striped work ids, excess handed back, neighbours probed when the home stripe is dry)
-    bool need = !alive;
-    for (int attempt = 0; attempt < 4; attempt++) {
-        const unsigned lane = threadIdx.x & 31;
-        const unsigned ballot = __ballot_sync(0xffffffffu, need);
-        if (ballot == 0u) break;
-        const int leader = __ffs(ballot) - 1;
-        const unsigned want = (unsigned)__popc(ballot);
-        const int c_probe = (home + (int)(lane & 3u)) % PT_NSTRIPE;
-        const unsigned long long lim_probe = stripe_limit(work_hi, c_probe);
-        bool has = false;
-        if (lane < 4u) has = *reinterpret_cast<volatile unsigned long long*>(&work[c_probe].claimed) < lim_probe;
-        const unsigned live = __ballot_sync(0xffffffffu, has) & 0xfu;
-        unsigned long long base = 0, limit = 0;
-        int c = home;
-        if (live) {
-            const int pick = __ffs(live) - 1;
-            c = (home + pick) % PT_NSTRIPE;
-            limit = __shfl_sync(0xffffffffu, lim_probe, pick);
-            if ((int)lane == leader) {
-                base = atomicAdd(&work[c].claimed, (unsigned long long)want);
-                if (base + want > limit) {
-                    const unsigned long long ok = base < limit ? limit - base : 0ull;
-                    atomicAdd(&work[c].claimed, (unsigned long long)(0ull - ((unsigned long long)want - ok)));
-                }
-            }
-            base = __shfl_sync(0xffffffffu, base, leader);
-        }
-        const unsigned long long v = base + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
-        if (need) {
-            if (live && v < limit) {
-                const unsigned long long id = stripe_item_id(v, c);
-                const unsigned long long s = id / (unsigned long long)n_pixels;
-                const int k = (int)(id - s * (unsigned long long)n_pixels);
-                const int pixel = __ldg(pixel_list + k);
-                const int cnt = (int)(cnt_origin + (long long)s + 1);
-                Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
-                const int i = pixel / sv.height, jj = pixel - i * sv.height;
-                const float3 d = camera_ray(sv, g, i, jj, cnt);
-                pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, PT_T_INF);
-                pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
-                pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                     // throughput, emission weight
-                pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-                pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-                pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE, 0u);
-                need = false;
-            } else if (!live || attempt == 3) {
-                if (misc.z & SLOT_ALIVE) {
-                    pool.ray_o[slot] = make_float4(0.f, 0.f, 0.f, -1.f);
-                    pool.misc[slot] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                need = false;
-            }
-        }
-    }
-    block_count(finished, &work[home].done);
-}
-
-// ================================================================================================
-// k_closest / k_shadow: persistent warps over the ray streams.
-//   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements and node counting)
-//   MODE 1: per-lane refill + vote-scheduled traversal of the binary BVH (pt_trace.cuh: trace_stream_vote)
-//   MODE 2: the same over the 4-wide BVH collapsed from it
-// ================================================================================================
-struct ClosestSource {
-    PathPool pool;
-    PT_D unsigned size() const { return (unsigned)pool.n_slots; }
-    PT_D void stripe_range(int k, unsigned& lo, unsigned& hi) const {
-        const unsigned long long n = (unsigned long long)(unsigned)pool.n_slots;
-        lo = (unsigned)((n * (unsigned)k) / PT_NCURSOR); hi = (unsigned)((n * (unsigned)(k + 1)) / PT_NCURSOR);
-    }
-    PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
-        const float4 o4 = pool.ray_o[i];
-        if (!(o4.w > 0.f)) return false;             // parked / finishing slot: nothing to trace
-        const float4 d4 = pool.ray_d[i];
-        o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z); tmax = o4.w;
-        return true;
-    }
-    PT_D void store(unsigned i, const HitRec& h) const { pool.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(pack_hit(h))); }
-};
-struct ShadowSource {
-    PathPool pool; ShadowQueue sq; int parity;
-    PT_D void stripe_range(int k, unsigned& lo, unsigned& hi) const {
-        lo = (unsigned)k * (unsigned)sq.seg_cap;
-        hi = lo + *reinterpret_cast<const volatile unsigned*>(&sq.seg_count[parity * PT_NCURSOR + k].v);
-    }
-    PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) const {
-        const float4 o4 = sq.o[i], d4 = sq.d[i];
-        o = mk3(o4.x, o4.y, o4.z); d = mk3(d4.x, d4.y, d4.z);
-        // does_intersect(light_dir, hit_point, emitter_d): t in (1e-4, emitter_d - 1e-4) (tracer_base.py:242)
-        tmax = o4.w > 0.f ? o4.w - 1e-4f : PT_T_INF;
-        return true;
-    }
-    PT_D void store(unsigned i, const HitRec& h) const {
-        if (h.prim >= 0) return;                     // occluded: shadow_int = 0
-        const float4 c4 = sq.c[i];
-        float* dst = reinterpret_cast<float*>(pool.col + __float_as_int(sq.d[i].w));
-        atomicAdd(dst + 0, c4.x); atomicAdd(dst + 1, c4.y); atomicAdd(dst + 2, c4.z);
-    }
-};
-
-// Mode-0 baseline: one cursor for the whole index range of every stripe in turn
-template <bool ANY_HIT, bool COUNT, typename Source>
-PT_D void trace_stream_simple(const SceneView& sv, Source& src, CursorStripe* __restrict__ cursors, unsigned& traced, unsigned& nn, unsigned& np) {
-    const unsigned lane = threadIdx.x & 31;
-    for (int k = 0; k < PT_NCURSOR; k++) {
-        unsigned lo, hi;
-        src.stripe_range(k, lo, hi);
-        while (true) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&cursors[k].v, 32u);
-            base = __shfl_sync(0xffffffffu, base, 0) + lo;
-            if (base >= hi) break;
-            const unsigned i = base + lane;
-            float3 o, d; float tmax;
-            if (i < hi && src.load(i, o, d, tmax)) {
-                HitRec hr;
-                trace<ANY_HIT, COUNT>(sv, o, d, tmax, hr, nn, np);
-                src.store(i, hr);
-                traced++;
-            }
-        }
-    }
-}
-
-template <bool COUNT, int MODE>
-__global__ void __launch_bounds__(TRACE_BLOCK)
-k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
-          const int refill, const int leaf_t) {
-    unsigned traced = 0, nn = 0, np = 0;
-    ClosestSource src{pool};
-    if (MODE >= 1) trace_stream_vote<false, COUNT, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
-    else trace_stream_simple<false, COUNT>(sv, src, cur->closest, traced, nn, np);
-    block_count(traced, &ctr->rays_closest);
-    if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(TRACE_BLOCK)
-k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
-         const int refill, const int leaf_t, const int parity) {
-    unsigned traced = 0, nn = 0, np = 0;
-    ShadowSource src{pool, sq, parity};
-    if (MODE >= 1) trace_stream_vote<true, false, MODE == 2>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
-    else trace_stream_simple<true, false>(sv, src, cur->shadow, traced, nn, np);
-    block_count(traced, &ctr->rays_shadow);
-}
-
-// Both ray streams of one wavefront iteration in ONE launch: a warp that runs out of shadow rays moves straight on to the
-// closest-hit stream, so the shadow stream's tail (ncu: 17-24 % of a trace kernel's elapsed cycles are ramp + tail, warps
-// waiting for the last long rays) overlaps useful work and one launch per iteration disappears.  The two streams are
-// independent: shadow results are RED-added to pool.col, closest hits are written to pool.hit.
-template <int MODE>
-__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
-k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
-        const int refill, const int leaf_t, const int parity) {
-    unsigned traced = 0, nn = 0, np = 0;
-    {
-        ShadowSource src{pool, sq, parity};
-        trace_stream_vote<true, false, MODE == 2>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
-        block_count(traced, &ctr->rays_shadow);
-    }
-    traced = 0;
-    {
-        ClosestSource src{pool};
-        trace_stream_vote<false, false, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
-        block_count(traced, &ctr->rays_closest);
-    }
-}
-
-// stage-level test hook
-__global__ void k_intersect_batch(const SceneView sv, int n, const float* __restrict__ ro, const float* __restrict__ rd,
-                                  const float* __restrict__ tmax_in, int any_hit, int* __restrict__ hit_obj, int* __restrict__ hit_prim,
-                                  float* __restrict__ hit_t, float* __restrict__ hit_u, float* __restrict__ hit_v) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    float3 o = ld3(ro + (size_t)k * 3), d = ld3(rd + (size_t)k * 3);
-    float tm = tmax_in ? tmax_in[k] : -1.f;
-    float tmax = tm > 0.f ? tm - 1e-4f : PT_T_INF;
-    HitRec hr; unsigned nn = 0, np = 0;
-    if (any_hit) {
-        bool h = trace<true, false>(sv, o, d, tmax, hr, nn, np);
-        hit_prim[k] = h ? 1 : 0;
-        if (hit_obj) hit_obj[k] = h ? 1 : 0;
-    } else {
-        trace<false, false>(sv, o, d, tmax, hr, nn, np);
-        hit_prim[k] = hr.prim;
-        hit_obj[k] = hr.prim >= 0 ? (hr.obj & 0x7fffffff) : -1;
-        hit_t[k] = hr.t; hit_u[k] = hr.u; hit_v[k] = hr.v;
-    }
-}
-
-// stage-level test hook: the surface models as k_logic calls them (all groups compiled in)
-__global__ void k_bxdf_batch(const SceneView sv, const int obj, const int n, const float* __restrict__ ns_in, const float* __restrict__ ng_in,
-                             const float* __restrict__ incid_in, const float* __restrict__ out_in, const int two_sides, const uint64_t seed,
-                             float* __restrict__ ev, float* __restrict__ pdf, float* __restrict__ s_dir, float* __restrict__ s_spec,
-                             float* __restrict__ s_pdf, int* __restrict__ s_flag) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const Bxdf mat = load_bxdf(sv.bxdfs + obj);
-    Surf sf; sf.n_s = ld3(ns_in + (size_t)k * 3); sf.n_g = ld3(ng_in + (size_t)k * 3); sf.t = 1.f;
-    const float3 in = ld3(incid_in + (size_t)k * 3), out = ld3(out_in + (size_t)k * 3);
-    // brdf_two_sides: eval / surface_pdf / sample_new_ray flip both normals when the incident ray arrives from behind (:449-453)
-    Surf sb = sf;
-    if (two_sides && mat.kind == 0 && dot(in, sf.n_s) > 0.f) { sb.n_s = -sf.n_s; sb.n_g = -sf.n_g; }
-    const float3 e = mat.kind == 0 ? brdf_eval<M_ALL>(mat, sb, in, out) : bsdf_eval(mat, sf, in, out, sv.world_ior);
-    ev[(size_t)k * 3] = e.x; ev[(size_t)k * 3 + 1] = e.y; ev[(size_t)k * 3 + 2] = e.z;
-    pdf[k] = mat.kind == 0 ? brdf_pdf<M_ALL>(mat, sb, out, in) : bsdf_pdf(mat, sf, out, in, sv.world_ior);
-    Rng g; g.init(seed, (uint32_t)k, 0u);
-    float3 d, sp; float p; bool fl;
-    if (mat.kind == 0) brdf_sample<M_ALL>(mat, sb, in, g, d, sp, p, fl);
-    else bsdf_sample(mat, sf, in, sv.world_ior, g, d, sp, p, fl);
-    s_dir[(size_t)k * 3] = d.x; s_dir[(size_t)k * 3 + 1] = d.y; s_dir[(size_t)k * 3 + 2] = d.z;
-    s_spec[(size_t)k * 3] = sp.x; s_spec[(size_t)k * 3 + 1] = sp.y; s_spec[(size_t)k * 3 + 2] = sp.z;
-    s_pdf[k] = p; s_flag[k] = fl ? 1 : 0;
-}
+#include "pt_kernels.cuh"
 
 // ================================================================================================
 // handle
