@@ -537,7 +537,12 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKC(cudaMemset(h->pool.misc, 0, (size_t)P * sizeof(uint4)));
     CKC(cudaMemset(h->pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
     // segment k takes the shadow rays of the warps w with w % PT_NCURSOR == k: at most ceil(n_warps / PT_NCURSOR) * 32 * nsr entries
-    const size_t seg_cap = (((size_t)P / 32 + PT_NCURSOR - 1) / PT_NCURSOR) * 32 * (size_t)std::max(1, d->num_shadow_ray);
+    // per k_logic launch.  Scenes with several material groups run up to five launches per iteration (k_classify lists), each
+    // packing its slots from warp 0 on, so every launch can add one more partly filled warp per segment: 8 warps of slack.
+    // (Found by running the kernels under the SIMT emulator of tests/dev_host with a 256-slot pool: without the slack a segment
+    // overflowed into its neighbour and shadow payloads were lost; pools of the default size stay far from the bound.)
+    const bool several_groups = (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) != 0;
+    const size_t seg_cap = (((size_t)P / 32 + PT_NCURSOR - 1) / PT_NCURSOR + (several_groups ? 8 : 0)) * 32 * (size_t)std::max(1, d->num_shadow_ray);
     const size_t Q = seg_cap * PT_NCURSOR;
     h->sq.seg_cap = (int)seg_cap;
     h->sq.capacity = (int)Q;

@@ -189,7 +189,7 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 }
 
 
-#ifdef __CUDACC__      // the stream scheduler below is warp code; the single-ray functions above also compile as host C++ (tests/dev_host)
+#if defined(__CUDACC__) || defined(PT_SIMT_EMU)      // the stream scheduler below is warp code (tests/dev_host runs it under a SIMT emulator); the single-ray functions above compile as plain host C++
 // ------------------------------------------------------------------------------------------------
 // Persistent-warp ray stream with per-lane refill and vote-scheduled traversal.
 //
@@ -348,6 +348,6 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
         }
     }
 }
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || PT_SIMT_EMU
 
 }  // namespace adapt

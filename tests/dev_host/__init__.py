@@ -9,9 +9,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "adapt_b200", "csrc")
 SRC = os.path.join(_HERE, "dev_host.cpp")
-DEPS = [SRC, os.path.join(_HERE, "cuda_host_shim.h")] + [os.path.join(_CSRC, f) for f in (
+DEPS = [SRC, os.path.join(_HERE, "cuda_host_shim.h"), os.path.join(_HERE, "dev_scene.h")] + [os.path.join(_CSRC, f) for f in (
     "pt_common.cuh", "pt_shade.cuh", "pt_trace.cuh", "pt_path.cuh", "pt_volume.cuh", "scene_pack.h", "bvh_build.cpp", "bvh_build.h")]
 LIB = os.path.join(_HERE, "_build", "libdev_host.so")
+WF_SRC = os.path.join(_HERE, "wavefront_host.cpp")
+WF_LIB = os.path.join(_HERE, "_build", "libwavefront_host.so")
+WF_DEPS = [WF_SRC, os.path.join(_HERE, "simt_emu.h"), os.path.join(_HERE, "cuda_host_shim.h"), os.path.join(_HERE, "dev_scene.h"),
+           os.path.join(_CSRC, "pt_kernels.cuh")]
 CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
 _lib = None
 
@@ -24,6 +28,37 @@ def build(force: bool = False) -> str:
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-fopenmp", "-ffp-contract=fast", "-march=x86-64-v3", "-I" + CUDA_INC,
                            "-shared", "-o", LIB, SRC, os.path.join(_CSRC, "bvh_build.cpp")])
     return LIB
+
+
+def build_wavefront(force: bool = False) -> str:
+    """The kernels themselves (pt_kernels.cuh) as host C++ under the SIMT emulator (simt_emu.h); C++20 for nothing but designated habits of
+    the headers, -O2 because the emulated kernels are the hot loop of these tests."""
+    deps = WF_DEPS + DEPS[3:]
+    if not force and os.path.exists(WF_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(WF_LIB) for d in deps):
+        return WF_LIB
+    os.makedirs(os.path.dirname(WF_LIB), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++20", "-w", "-fPIC", "-ffp-contract=fast", "-march=x86-64-v3", "-I" + CUDA_INC,
+                           "-shared", "-o", WF_LIB, WF_SRC, os.path.join(_CSRC, "bvh_build.cpp")])
+    return WF_LIB
+
+
+_wf = None
+
+
+def wavefront_render(packed, n_spp: int, pool_slots: int = 256, trace_grid: int = 2):
+    """Run the library's kernels under the SIMT emulator on one packed scene -> (film sums (w,h,3), stats dict)."""
+    global _wf
+    if _wf is None:
+        _wf = C.CDLL(build_wavefront())
+        _wf.wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    w, h = packed.desc.width, packed.desc.height
+    acc = np.zeros((w, h, 3), np.float32)
+    st = np.zeros(5, np.uint64)
+    rc = _wf.wavefront_render(C.addressof(packed.desc), int(n_spp), int(pool_slots), int(trace_grid), acc.ctypes.data_as(C.POINTER(C.c_float)),
+                              st.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc != 0:
+        raise RuntimeError(f"emulated wavefront failed ({rc}): no progress" if rc == -1 else f"emulated wavefront failed ({rc})")
+    return acc, dict(paths=int(st[0]), rays_closest=int(st[1]), rays_shadow=int(st[2]), iterations=int(st[3]), launches=int(st[4]))
 
 
 def load():

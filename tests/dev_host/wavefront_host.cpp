@@ -1,0 +1,158 @@
+// wavefront_host.cpp -- TEST INFRASTRUCTURE: the KERNELS of libadapt_b200 (adapt_b200/csrc/pt_kernels.cuh: k_classify, k_logic,
+// k_trace, k_closest, k_logic_vpt) compiled as host C++ and run under the SIMT emulator of simt_emu.h, launched in the order
+// adapt_abi.cu::launch_iteration launches them, over pool / queue / counter arrays laid out as adapt_create lays them out.
+// So the CPU suite executes the wavefront itself -- slot state, regeneration, striped work claims, class lists, warp-aggregated queue
+// appends, the vote-scheduled traversal with lane refill -- on tiny scenes, and compares the film with the oracle's.
+// Never linked into libadapt_b200.so; says nothing about performance, races or ptxas' code generation.
+#include "cuda_host_shim.h"
+#include "simt_emu.h"
+#define PT_SIMT_EMU 1
+#include "../../adapt_b200/csrc/pt_kernels.cuh"
+#include "dev_scene.h"
+
+namespace {
+
+template <typename T> T* zeros(std::vector<T>& v, size_t n) { v.assign(n, T()); return v.data(); }
+
+struct Wavefront {
+    DevHost* scene = nullptr;
+    PathPool pool{}; ShadowQueue sq{};
+    std::vector<float4> ray_o, ray_d, hit, thr, col, sq_o, sq_d, sq_c;
+    std::vector<uint4> misc; std::vector<uint2> rng;
+    std::vector<CursorStripe> seg_count, cls_count;
+    std::vector<unsigned> cls_items;
+    std::vector<WorkStripe> work;
+    std::vector<int> pixels;
+    DeviceCounters ctr{}; Cursors cur{};
+    std::vector<float> accum;
+    int mats = M_SIMPLE, logic_lists = 0, integrator = 0, trace_grid = 2;
+    unsigned iter_parity = 0; unsigned long long iterations = 0, launches = 0, work_hi = 0; long long cnt_origin = 0;
+    int refill = 16, leaf_t = 8, node_steps = 4;
+};
+
+// adapt_abi.cu::launch_iteration, with <<<grid, block>>> replaced by simt::launch
+void launch_iteration(Wavefront& w) {
+    const SceneView& sv = w.scene->sv;
+    const int parity = (int)(w.iter_parity & 1u);
+    w.iter_parity ^= 1u;
+    const int lg = w.pool.n_slots / LOGIC_BLOCK;
+    const int lt = w.leaf_t | (w.node_steps << 8);
+    DeviceCounters* ctr = &w.ctr; Cursors* cur = &w.cur;
+    if (w.integrator == 1) {
+        simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, ctr, w.work.data(), cur, w.accum.data(),
+            w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, (unsigned)w.iterations); });
+        simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_closest<false, 1>(sv, w.pool, ctr, cur, w.refill, lt); });
+        w.iterations++; w.launches += 2;
+        return;
+    }
+#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { const KeySet ks_ = (KEYS); simt::launch(lg, LOGIC_BLOCK, [&] { k_logic<M, LISTED>(sv, w.pool, w.sq, ctr, w.work.data(), cur, \
+        w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations, w.cls_items.data(), w.cls_count.data(), ks_); }); \
+        w.launches++; } while (0)
+#define LAUNCH_LOGIC_V(M, LISTED, KEYS) do { \
+        if (ts && tex) LAUNCH_LOGIC_X((M) | M_TWOSIDED | M_TEXTURED, LISTED, KEYS); else if (ts) LAUNCH_LOGIC_X((M) | M_TWOSIDED, LISTED, KEYS); \
+        else if (tex) LAUNCH_LOGIC_X((M) | M_TEXTURED, LISTED, KEYS); else LAUNCH_LOGIC_X(M, LISTED, KEYS); } while (0)
+    const bool ts = (w.mats & M_TWOSIDED) != 0, tex = sv.textures != nullptr;
+    if (!w.logic_lists) {
+        const KeySet no_keys = {{-1, -1, -1, -1, -1, -1, -1, -1}};
+        LAUNCH_LOGIC_V(M_SIMPLE, false, no_keys);
+    } else {
+        simt::launch(lg, LOGIC_BLOCK, [&] { k_classify(w.pool, w.sq, cur, w.cls_items.data(), w.cls_count.data(), parity); });
+        w.launches++;
+        const KeySet k_simple = {{0, 1, 2, 6, LOGIC_NKEY - 2, LOGIC_NKEY - 1, -1, -1}}, k_glossy = {{4, 5, -1, -1, -1, -1, -1, -1}};
+        const KeySet k_coat = {{3, 7, -1, -1, -1, -1, -1, -1}}, k_bsdf = {{8, 9, 10, -1, -1, -1, -1, -1}};
+        LAUNCH_LOGIC_V(M_SIMPLE, true, k_simple);
+        if (w.mats & M_GLOSSY) LAUNCH_LOGIC_V(M_SIMPLE | M_GLOSSY, true, k_glossy);
+        if (w.mats & M_COAT_GGX) LAUNCH_LOGIC_V(M_SIMPLE | M_COAT_GGX, true, k_coat);
+        if (w.mats & M_BSDF) { if (tex) LAUNCH_LOGIC_X(M_SIMPLE | M_BSDF | M_TEXTURED, true, k_bsdf); else LAUNCH_LOGIC_X(M_SIMPLE | M_BSDF, true, k_bsdf); }
+    }
+#undef LAUNCH_LOGIC_V
+#undef LAUNCH_LOGIC_X
+    simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<1>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
+    w.iterations++; w.launches++;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Renders n_spp samples of every pixel of the scene with the emulated kernels; film sums are ADDED to accum (w,h,3).
+// stats: [paths done, closest rays, shadow rays / transmittance segments, iterations, kernel launches].  Returns 0, or -1 when the
+// wavefront stops making progress.
+int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int trace_grid, float* accum, uint64_t* stats) {
+    Wavefront w;
+    w.scene = make_dev_scene(d);
+    if (!w.scene) return -2;
+    const int no = d->n_objects;
+    // which k_logic specialisation covers this scene (adapt_create)
+    int need = M_SIMPLE;
+    for (int o = 0; o < no; o++) {
+        const adapt_bxdf& b = d->bxdfs[o];
+        if (b.kind != 0) need |= M_BSDF;
+        else if (b.type == 4 || b.type == 5) need |= M_GLOSSY;
+        else if (b.type == 7 || b.type == 3) need |= M_COAT_GGX;
+    }
+    if (d->brdf_two_sides) need |= M_TWOSIDED;
+    w.mats = need;
+    w.logic_lists = (need & (M_GLOSSY | M_COAT_GGX | M_BSDF)) != 0;
+    w.integrator = d->integrator;
+    w.trace_grid = trace_grid > 0 ? trace_grid : 2;
+    // the material class travels in the leaf records: rebuild them with the real classes (make_dev_scene passes zeros)
+    {
+        std::vector<uint8_t> sph((size_t)d->n_prims, 0), obj_class((size_t)no, 0);
+        std::vector<int32_t> prim_obj((size_t)d->n_prims, 0);
+        for (int o = 0; o < no; o++) {
+            const adapt_bxdf& b = d->bxdfs[o];
+            obj_class[o] = (uint8_t)(b.kind == 0 ? std::min(std::max(b.type, 0), 7) : (b.type == 0 ? 8 : (b.type == 1 ? 9 : 10)));
+            for (int k = d->obj_info[o * 3]; k < d->obj_info[o * 3] + d->obj_info[o * 3 + 1]; k++) { prim_obj[k] = o; sph[k] = d->obj_info[o * 3 + 2] != 0; }
+        }
+        BuildParams bp; BuildResult br;
+        build_bvh(d->primitives, sph.data(), d->n_prims, bp, br);
+        to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), obj_class.data(), w.scene->bvh);
+        w.scene->sv.nodes = reinterpret_cast<const float4*>(w.scene->bvh.nodes.data());
+        w.scene->sv.leaf_prims = reinterpret_cast<const float4*>(w.scene->bvh.prims.data());
+    }
+    // pixels in 4x8 patches (adapt_create)
+    const int sx = d->do_crop ? std::max(0, d->start_x) : 0, ex = d->do_crop ? std::min(d->width, d->end_x) : d->width;
+    const int sy = d->do_crop ? std::max(0, d->start_y) : 0, ey = d->do_crop ? std::min(d->height, d->end_y) : d->height;
+    for (int bi = sx; bi < ex; bi += 4)
+        for (int bj = sy; bj < ey; bj += 8)
+            for (int i = bi; i < std::min(bi + 4, ex); i++)
+                for (int j = bj; j < std::min(bj + 8, ey); j++) w.pixels.push_back(i * d->height + j);
+    // pool, queues, counters (adapt_create)
+    int P = std::max(pool_slots, LOGIC_BLOCK);
+    P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
+    w.pool.n_slots = P;
+    w.pool.ray_o = zeros(w.ray_o, P); w.pool.ray_d = zeros(w.ray_d, P); w.pool.hit = zeros(w.hit, P); w.pool.thr = zeros(w.thr, P);
+    w.pool.col = zeros(w.col, P); w.pool.misc = zeros(w.misc, P); w.pool.rng = zeros(w.rng, P);
+    memset(w.ray_o.data(), 0xff, (size_t)P * sizeof(float4));                  // NaN tmax: nothing to trace
+    const size_t extra_warps = getenv("WF_OLD_SEGCAP") ? 0 : (w.logic_lists ? 8 : 0);       // adapt_create: slack for the per-group launches
+    const size_t seg_cap = (((size_t)P / 32 + PT_NCURSOR - 1) / PT_NCURSOR + extra_warps) * 32 * (size_t)std::max(1, d->num_shadow_ray);
+    const size_t Q = seg_cap * PT_NCURSOR;
+    w.sq.seg_cap = (int)seg_cap; w.sq.capacity = (int)Q;
+    w.sq.o = zeros(w.sq_o, Q); w.sq.d = zeros(w.sq_d, Q); w.sq.c = zeros(w.sq_c, Q);
+    w.sq.seg_count = zeros(w.seg_count, 2 * PT_NCURSOR);
+    zeros(w.cls_count, 32); zeros(w.cls_items, w.logic_lists ? (size_t)LOGIC_NKEY * (size_t)P : 1);
+    zeros(w.work, PT_NSTRIPE);
+    w.accum.assign((size_t)d->width * d->height * 3, 0.f);
+    // adapt_render + adapt_sync
+    w.work_hi = (unsigned long long)w.pixels.size() * (unsigned long long)n_spp;
+    unsigned long long last_done = ~0ull, last_claimed = ~0ull; int stale = 0;
+    while (true) {
+        unsigned long long done = 0, claimed = 0;
+        for (const WorkStripe& s : w.work) { done += s.done; claimed += s.claimed; }
+        if (done >= w.work_hi) break;
+        stale = (done == last_done && claimed == last_claimed) ? stale + 1 : 0;
+        last_done = done; last_claimed = claimed;
+        if (stale > 64 || w.iterations > 100000) { delete w.scene; return -1; }
+        launch_iteration(w);
+    }
+    for (size_t k = 0; k < w.accum.size(); k++) accum[k] += w.accum[k];
+    if (stats) {
+        unsigned long long done = 0; for (const WorkStripe& s : w.work) done += s.done;
+        stats[0] = done; stats[1] = w.ctr.rays_closest; stats[2] = w.ctr.rays_shadow; stats[3] = w.iterations; stats[4] = w.launches;
+    }
+    delete w.scene;
+    return 0;
+}
+
+}  // extern "C"

@@ -284,3 +284,20 @@ def test_cuda_bxdf_models_match_reference(scene_root, vset):
         assert _relerr(got["s_spec"], g[vset + "/s_spec"][ob]) < 5e-4, name
         assert _relerr(got["s_pdf"], g[vset + "/s_pdf"][ob]) < 5e-4, name
         np.testing.assert_array_equal(got["s_flag"], g[vset + "/s_flag"][ob])
+
+
+@pytest.mark.gpu
+def test_cuda_tiny_pool_with_several_material_groups(scene_root):
+    """Regression for a bug the SIMT emulator found (tests/test_wavefront_emulated.py): scenes with several material groups run one
+    k_logic launch per group, and with a pool of a few hundred slots the shadow queue's segments used to overflow into each other.
+    Kept at the end of the last GPU test file on purpose (it was added after the round's GPU time was spent)."""
+    from adapt_b200._lib import pack_scene
+    from adapt_b200.renderer.vanilla_renderer import Renderer
+    from oracle.pt_oracle import OracleScene
+    e, a, o, c = load_scene(scene_root, "csphere", "balls-mono.xml", 16, 16)
+    r = Renderer(e, a, o, c, seed=5, pool_size=256)
+    r.render_batch(2)
+    img = r.color.to_numpy()
+    ref, _ = OracleScene(pack_scene(e, a, o, c, seed=5)).render(2)
+    match, flipped = _flip_stats(img, ref)
+    assert flipped <= 0.01 and rel_l2(img[match], ref[match]) < 1e-4
