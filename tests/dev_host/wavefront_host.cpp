@@ -111,13 +111,16 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
         w.scene->sv.nodes = reinterpret_cast<const float4*>(w.scene->bvh.nodes.data());
         w.scene->sv.leaf_prims = reinterpret_cast<const float4*>(w.scene->bvh.prims.data());
     }
-    // pixels in 4x8 patches (adapt_create)
+    // pixels owned by this handle: the tile partition's list, or the film / crop window in 4x8 patches (adapt_create)
+    if (d->pixel_list && d->n_pixels > 0) w.pixels.assign(d->pixel_list, d->pixel_list + d->n_pixels);
+    else {
     const int sx = d->do_crop ? std::max(0, d->start_x) : 0, ex = d->do_crop ? std::min(d->width, d->end_x) : d->width;
     const int sy = d->do_crop ? std::max(0, d->start_y) : 0, ey = d->do_crop ? std::min(d->height, d->end_y) : d->height;
     for (int bi = sx; bi < ex; bi += 4)
         for (int bj = sy; bj < ey; bj += 8)
             for (int i = bi; i < std::min(bi + 4, ex); i++)
                 for (int j = bj; j < std::min(bj + 8, ey); j++) w.pixels.push_back(i * d->height + j);
+    }
     // pool, queues, counters (adapt_create)
     int P = std::max(pool_slots, LOGIC_BLOCK);
     P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;

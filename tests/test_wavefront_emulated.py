@@ -68,6 +68,32 @@ def test_shadow_queue_segments_hold_the_per_group_launches(scene_root, oracle_li
     assert _flip(bad, ref)[1] > 0.02
 
 
+def test_tile_partition_and_crop_window(scene_root, oracle_lib):
+    """Multi-GPU tile split on one CPU: two handles that own interleaved 32x32 tiles render disjoint pixels whose sum is the whole film
+    (what the NCCL reduce adds up); a crop window renders exactly its pixels."""
+    from adapt_b200._lib import pack_scene
+    from adapt_b200.dist import tile_partition
+    from dev_host import wavefront_render
+    e, a, o, c = load_scene(scene_root, "csphere", "balls-mono.xml", 40, 36)
+    whole, _ = wavefront_render(pack_scene(e, a, o, c, seed=3), 1, 512)
+    parts = []
+    for rank in range(2):
+        ps = pack_scene(e, a, o, c, seed=3, pixel_list=tile_partition(40, 36, rank, 2))
+        img, st = wavefront_render(ps, 1, 256)
+        assert st["paths"] == ps.desc.n_pixels
+        parts.append(img)
+    assert not np.logical_and(np.abs(parts[0]).sum(-1) > 0, np.abs(parts[1]).sum(-1) > 0).any()
+    assert rel_l2(parts[0] + parts[1], whole) < 1e-6
+    e, a, o, c = load_scene(scene_root, "cbox", "cbox.xml", 24, 24)
+    c["film"].update(crop_x=10, crop_y=12, crop_rx=4, crop_ry=5)
+    ps = pack_scene(e, a, o, c, seed=3)
+    img, st = wavefront_render(ps, 2, 256)
+    full, _ = wavefront_render(pack_scene(*load_scene(scene_root, "cbox", "cbox.xml", 24, 24), seed=3), 2, 256)
+    inside = np.zeros((24, 24), bool); inside[6:14, 7:17] = True
+    assert st["paths"] == inside.sum() * 2 and (img[~inside] == 0).all()
+    assert rel_l2(img[inside], full[inside]) < 1e-6
+
+
 VPT_CASES = [("cbox", "cbox.xml", 16, 2, 256), ("test", "media.xml", 16, 2, 256), ("test", "media-clear.xml", 16, 2, 512),
              ("csphere", "balls-mono.xml", 12, 2, 256)]
 
