@@ -464,21 +464,22 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 }
 
 // ================================================================================================
-// k_logic_vpt: the volumetric integrator's step between two closest-hit traces (pt_volume.cuh: vol_shade_step), first version.
+// k_logic_vpt: the volumetric integrator's step between two closest-hit traces (pt_volume.cuh: vol_shade_step).
 // ================================================================================================
-// Thread t owns slot t.  The next-event transmittance (track_ray, up to seven closest-hit segments through null surfaces and
-// media) is resolved INSIDE this kernel with the single-ray traversal, like k_logic's rare two-sided corner case -- correct but
-// divergent; moving it to a re-arming stream of k_trace is the planned second version.  Path continuation rays
-// go through the unchanged k_closest stream.  Slot layout as for `pt`, except that thr.w carries the emission weight.
-// NOT YET RUN ON A GPU: adapt_create only accepts integrator = 1 with ADAPT_ENABLE_VPT=1 (the functions it calls are verified on
-// the CPU, tests/test_vpt_device_code.py; this glue is not).
+// Thread t owns slot t.  Next-event samples go to the shadow queue exactly as in k_logic (origin | distance, direction | slot,
+// payload); the transmittance stream of k_trace_vpt walks each one through null surfaces and media (track_ray, up to seven
+// closest-hit segments, the lane re-arming itself) and RED-adds payload * transmittance to the path colour.  A path that ends
+// after queueing samples is flagged SLOT_FINISH and splatted by the next launch, like a `pt` path at its last bounce.  Slot layout
+// as for `pt`, except that thr.w carries the emission weight.
+// NOT YET RUN ON A GPU: adapt_create only accepts integrator = 1 with ADAPT_ENABLE_VPT=1.  The functions it calls are verified on
+// the CPU (tests/test_vpt_device_code.py) and the kernel itself runs under the SIMT emulator (tests/test_wavefront_emulated.py).
 template <int MATS>
 __global__ void __launch_bounds__(LOGIC_BLOCK, 2)
-k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
-            Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
-            const unsigned long long work_hi, const long long cnt_origin, const unsigned rot) {
+k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
+            WorkStripe* __restrict__ work, Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list,
+            const int n_pixels, const unsigned long long work_hi, const long long cnt_origin, const int parity, const unsigned rot) {
     const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
-    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; }
+    if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + slot].v = 0; }
     const int home = (int)(((unsigned)(slot >> 5) + 4u * rot) % PT_NSTRIPE);
     uint4 misc = pool.misc[slot];
     bool alive = (misc.z & SLOT_ALIVE) != 0;
@@ -490,50 +491,61 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, Device
         }
         if (__all_sync(0xffffffffu, dry)) return;
     }
-    unsigned finished = 0, n_segments = 0;
+    unsigned finished = 0, n_requests = 0;
+    VolRequest reqs[VOL_MAX_REQUESTS]; int n_req = 0;
     if (alive) {
-        const float4 c4 = pool.col[slot], h4 = pool.hit[slot], o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
-        const uint2 r2 = pool.rng[slot];
+        const float4 c4 = pool.col[slot];
         VolPath p;
-        p.ray_o = mk3(o4.x, o4.y, o4.z); p.ray_d = mk3(d4.x, d4.y, d4.z);
-        p.throughput = mk3(t4.x, t4.y, t4.z); p.emission_weight = t4.w;
         p.color = mk3(c4.x, c4.y, c4.z);
-        p.bounce = (int)(misc.z & 0xffffu);
-        p.rng.state = ((uint64_t)r2.y << 32) | r2.x;
-        HitRec h; h.t = h4.x; h.u = h4.y; h.v = h4.z; h.obj = 0; h.cls = 0;
-        const int hit_word = __float_as_int(h4.w);
-        h.prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
-        VolRequest reqs[VOL_MAX_REQUESTS]; int n_req = 0;
-        const VolOutcome out = vol_shade_step<MATS>(sv, vv, p, h, reqs, n_req);
-        for (int r = 0; r < n_req; r++) {
-            VolTransmit t; vol_transmit_begin(t, reqs[r]);
-            while (true) {
-                HitRec sh; unsigned nn = 0, np = 0;
-                trace<false, false>(sv, t.point, t.dir, vol_transmit_tmax(t), sh, nn, np);
-                n_segments++;
-                if (!vol_transmit_step(sv, vv, t, sh)) break;
-            }
-            p.color += reqs[r].payload * t.tr;
+        VolOutcome out = VOL_SPLAT_NOW;
+        if (!(misc.z & SLOT_FINISH)) {
+            const float4 h4 = pool.hit[slot], o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
+            const uint2 r2 = pool.rng[slot];
+            p.ray_o = mk3(o4.x, o4.y, o4.z); p.ray_d = mk3(d4.x, d4.y, d4.z);
+            p.throughput = mk3(t4.x, t4.y, t4.z); p.emission_weight = t4.w;
+            p.bounce = (int)(misc.z & 0xffffu);
+            p.rng.state = ((uint64_t)r2.y << 32) | r2.x;
+            HitRec h; h.t = h4.x; h.u = h4.y; h.v = h4.z; h.obj = 0; h.cls = 0;
+            const int hit_word = __float_as_int(h4.w);
+            h.prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
+            out = vol_shade_step<MATS>(sv, vv, p, h, reqs, n_req);
+            n_requests = (unsigned)n_req;
         }
-        if (out == VOL_TRACE) {
-            pool.ray_o[slot] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, PT_T_INF);
-            pool.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.f);
-            pool.thr[slot] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, p.emission_weight);
-            pool.col[slot] = make_float4(p.color.x, p.color.y, p.color.z, 0.f);
-            pool.rng[slot] = make_uint2((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32));
-            misc.z = (uint32_t)p.bounce | SLOT_ALIVE;
-            pool.misc[slot] = misc;
-        } else {
-            // the path is over: NaN scrub + splat (vpt.py:260-261); every transmittance was resolved above
+        if (out == VOL_SPLAT_NOW) {
+            // the path is over and nothing is in flight for it: NaN scrub + splat (vpt.py:260-261)
             float* px = accum + (size_t)misc.x * 3;
             if (!isnan(p.color.x) && p.color.x != 0.f) atomicAdd(px + 0, p.color.x);
             if (!isnan(p.color.y) && p.color.y != 0.f) atomicAdd(px + 1, p.color.y);
             if (!isnan(p.color.z) && p.color.z != 0.f) atomicAdd(px + 2, p.color.z);
             alive = false;
             finished = 1;
+        } else {
+            const bool last = out == VOL_FINISH;                 // over, but this step's transmittance samples still have to land
+            pool.ray_o[slot] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, last ? -1.f : PT_T_INF);
+            pool.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.f);
+            pool.thr[slot] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, p.emission_weight);
+            pool.col[slot] = make_float4(p.color.x, p.color.y, p.color.z, 0.f);
+            pool.rng[slot] = make_uint2((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32));
+            misc.z = (uint32_t)p.bounce | SLOT_ALIVE | (last ? SLOT_FINISH : 0u);
+            pool.misc[slot] = misc;
         }
     }
-    block_count(n_segments, &ctr->rays_shadow);
+    // transmittance requests -> this warp's segment of the shadow queue (one warp-aggregated atomic per round, all lanes take part)
+    {
+        const int q_seg = (int)((unsigned)(slot >> 5) % PT_NCURSOR);
+        unsigned* const q_count = &sq.seg_count[parity * PT_NCURSOR + q_seg].v;
+        for (int j = 0; j < sv.num_shadow_ray; j++) {
+            const bool want = j < n_req;
+            const unsigned qi = (unsigned)q_seg * (unsigned)sq.seg_cap + warp_alloc<unsigned>(want, q_count);
+            if (want) {
+                const VolRequest& r = reqs[j];
+                sq.o[qi] = make_float4(r.o.x, r.o.y, r.o.z, r.dist);
+                sq.d[qi] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
+                sq.c[qi] = make_float4(r.payload.x, r.payload.y, r.payload.z, 0.f);
+            }
+        }
+    }
+    block_count(n_requests, &ctr->rays_shadow);
     // regeneration: as in k_logic (striped work ids, excess handed back, neighbours probed when the home stripe is dry)
     bool need = !alive;
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -700,6 +712,54 @@ k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
     {
         ClosestSource src{pool};
         trace_stream_vote<false, false, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        block_count(traced, &ctr->rays_closest);
+    }
+}
+
+// The volumetric transmittance stream (renderer/vpt.py:103-137 track_ray): a queue entry is followed through null surfaces and
+// media one closest-hit segment at a time; the lane keeps the running transmittance and re-arms itself (pt_trace.cuh:
+// source_rearms) until the emitter point is reached, a real surface blocks it or seven segments are spent.
+struct TransmitSource {
+    SceneView sv; VolumeView vv; PathPool pool; ShadowQueue sq; int parity;
+    VolTransmit st; float3 payload; int slot;                       // per-lane state of the ray in flight
+    PT_D void stripe_range(int k, unsigned& lo, unsigned& hi) const {
+        lo = (unsigned)k * (unsigned)sq.seg_cap;
+        hi = lo + *reinterpret_cast<const volatile unsigned*>(&sq.seg_count[parity * PT_NCURSOR + k].v);
+    }
+    PT_D bool load(unsigned i, float3& o, float3& d, float& tmax) {
+        const float4 o4 = sq.o[i], d4 = sq.d[i], c4 = sq.c[i];
+        VolRequest r; r.o = mk3(o4.x, o4.y, o4.z); r.d = mk3(d4.x, d4.y, d4.z); r.dist = o4.w; r.payload = mk3(c4.x, c4.y, c4.z);
+        vol_transmit_begin(st, r);
+        payload = r.payload; slot = __float_as_int(d4.w);
+        o = st.point; d = st.dir; tmax = vol_transmit_tmax(st);
+        return true;
+    }
+    PT_D bool next(unsigned, const HitRec& h, float3& o, float3& d, float& tmax) {
+        if (vol_transmit_step(sv, vv, st, h)) { o = st.point; d = st.dir; tmax = vol_transmit_tmax(st); return true; }
+        const float3 add = payload * st.tr;
+        float* dst = reinterpret_cast<float*>(pool.col + slot);
+        if (add.x != 0.f) atomicAdd(dst + 0, add.x);
+        if (add.y != 0.f) atomicAdd(dst + 1, add.y);
+        if (add.z != 0.f) atomicAdd(dst + 2, add.z);
+        return false;
+    }
+    PT_D void store(unsigned, const HitRec&) const {}
+};
+namespace adapt { template <> struct source_rearms<TransmitSource> { static constexpr bool value = true; }; }
+
+// Both streams of one volumetric iteration in one launch, like k_trace: transmittance samples first, then the paths' own rays.
+__global__ void __launch_bounds__(TRACE_BLOCK, 4)
+k_trace_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
+            Cursors* __restrict__ cur, const int refill, const int leaf_t, const int parity) {
+    unsigned traced = 0, nn = 0, np = 0;
+    {
+        TransmitSource src{sv, vv, pool, sq, parity};
+        trace_stream_vote<false, false, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    }
+    traced = 0;
+    {
+        ClosestSource src{pool};
+        trace_stream_vote<false, false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
         block_count(traced, &ctr->rays_closest);
     }
 }

@@ -212,6 +212,10 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 //                  bool load(unsigned i, float3& o, float3& d, float& tmax);        (false: empty entry)
 //                  void store(unsigned i, const HitRec& h);   (closest hit: the record; any hit: h.prim >= 0 means occluded)
 // ------------------------------------------------------------------------------------------------
+// Sources whose rays continue segment by segment specialise this to true and provide
+//                  bool next(unsigned i, const HitRec& h, float3& o, float3& d, float& tmax);   (true: trace this segment next)
+template <typename Source> struct source_rearms { static constexpr bool value = false; };
+
 template <bool ANY_HIT, bool COUNT, bool WIDE, typename Source>
 PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, const int refill, const int leaf_t_packed,
                             unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
@@ -340,7 +344,22 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
             // retire finished lanes; only then re-evaluate whether the warp should go and refill
             const bool fin = node == PT_NODE_DONE && cur >= 0;
             if (__any_sync(FULL, fin)) {
-                if (fin) { src.store((unsigned)cur, hit); cur = -1; }
+                if (fin) {
+                    if constexpr (source_rearms<Source>::value) {
+                        // multi-segment rays (the volumetric transmittance stream): the source consumes the hit and may hand the
+                        // same lane its next segment, which starts over at the root without going back to the cursor
+                        float3 o2, d2; float tmax2;
+                        if (src.next((unsigned)cur, hit, o2, d2, tmax2)) {
+                            r = make_ray(o2, d2);
+                            hit.prim = -1; hit.t = tmax2; hit.u = 0.f; hit.v = 0.f; hit.obj = 0; hit.cls = 0;
+                            node = 0; sp = 0;
+                        } else {
+                            cur = -1;
+                        }
+                    } else {
+                        src.store((unsigned)cur, hit); cur = -1;
+                    }
+                }
                 const unsigned act = __ballot_sync(FULL, cur >= 0);
                 if (act == 0u) break;
                 if (!exhausted && __popc(act) <= 32 - refill) break;

@@ -13,8 +13,8 @@
 // Both are functions of plain state structs, so the kernels around them only move slots and queue entries.  They also compile as
 // host C++ (tests/dev_host) and are checked there, path by path, against the CPU oracle's restatement of renderer/vpt.py.
 //
-// STATUS: the functions below are verified on the CPU.  The kernel that launches them (adapt_abi.cu: k_logic_vpt, first version:
-// transmittance resolved inside the logic kernel) compiles for sm_100a but has not run on a GPU yet, so adapt_create only accepts
+// STATUS: the functions below are verified on the CPU, and so are the kernels that launch them (pt_kernels.cuh: k_logic_vpt,
+// k_trace_vpt) -- under the SIMT emulator of tests/dev_host.  They have not run on a GPU yet, so adapt_create only accepts
 // integrator = 1 with ADAPT_ENABLE_VPT=1.
 #pragma once
 #include "pt_path.cuh"

@@ -114,8 +114,8 @@ typedef struct {
     const float* tex_image[3];      /* packed atlas per map kind, [tex_size][tex_size][3] floats (row = v, column = u), or NULL */
     int32_t tex_size[3];            /* atlas edge length per map kind                                                      */
     int32_t integrator;             /* 0 = `pt` (renderer/vanilla_renderer.py), 1 = `vpt` (renderer/vpt.py: homogeneous media; implemented by the
-                                       CPU oracle; libadapt_b200 returns ADAPT_ERR_INVALID for it unless ADAPT_ENABLE_VPT=1 switches on the
-                                       first version of its kernel, which has not been validated on a GPU yet)                    */
+                                       CPU oracle; libadapt_b200 returns ADAPT_ERR_INVALID for it unless ADAPT_ENABLE_VPT=1 switches on its
+                                       kernels, which are verified on the CPU but have not been validated on a GPU yet)           */
     /* participating media: renderer/vpt.py:53, bxdf/bsdf.py:37, parsers/world.py:34. Optional (NULL = everything transparent). */
     const adapt_medium* media;      /* [n_objects + 1]: medium of each object's BSDF (ignored for BRDF objects), last entry = world medium */
 } adapt_scene_desc;

@@ -39,9 +39,9 @@ void launch_iteration(Wavefront& w) {
     const int lt = w.leaf_t | (w.node_steps << 8);
     DeviceCounters* ctr = &w.ctr; Cursors* cur = &w.cur;
     if (w.integrator == 1) {
-        simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, ctr, w.work.data(), cur, w.accum.data(),
-            w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, (unsigned)w.iterations); });
-        simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_closest<false, 1>(sv, w.pool, ctr, cur, w.refill, lt); });
+        simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
+            w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
+        simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
         w.iterations++; w.launches += 2;
         return;
     }

@@ -1,6 +1,6 @@
-"""Volumetric integrator -- GPU half, for the round that brings k_logic_vpt up: SKIPPED unless ADAPT_ENABLE_VPT=1, because the
-kernel (adapt_abi.cu: k_logic_vpt, first version) has not run on a GPU yet.  The functions it calls are verified on the CPU
-(tests/test_vpt_device_code.py); what these tests add is the launch glue: slot packing, regeneration, the closest-hit stream."""
+"""Volumetric integrator -- GPU half, for the round that brings its kernels up: SKIPPED unless ADAPT_ENABLE_VPT=1, because k_logic_vpt /
+k_trace_vpt (pt_kernels.cuh) have not run on a GPU yet.  The functions they call are verified on the CPU (tests/test_vpt_device_code.py)
+and the kernels themselves under the SIMT emulator (tests/test_wavefront_emulated.py); what these tests add is the real hardware."""
 import os
 
 import numpy as np

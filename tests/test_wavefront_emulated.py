@@ -94,14 +94,17 @@ def test_tile_partition_and_crop_window(scene_root, oracle_lib):
     assert rel_l2(img[inside], full[inside]) < 1e-6
 
 
-VPT_CASES = [("cbox", "cbox.xml", 16, 2, 256), ("test", "media.xml", 16, 2, 256), ("test", "media-clear.xml", 16, 2, 512),
-             ("csphere", "balls-mono.xml", 12, 2, 256)]
+VPT_CASES = [("cbox", "cbox.xml", 16, 2, 256, {}), ("test", "media.xml", 16, 2, 256, {}), ("test", "media-clear.xml", 16, 2, 512, {}),
+             ("csphere", "balls-mono.xml", 12, 2, 256, {}),                                  # no media: four shadow rays per vertex
+             ("test", "media.xml", 12, 2, 256, dict(num_shadow_ray=3, use_rr=False, max_bounce=5)),
+             ("test", "media.xml", 12, 2, 1024, dict(use_mis=False))]
 
 
-@pytest.mark.parametrize("scene,name,size,spp,pool", VPT_CASES)
-def test_emulated_vpt_kernel_matches_oracle(scene_root, oracle_lib, scene, name, size, spp, pool):
-    """k_logic_vpt (first version) + the unchanged k_closest stream: the kernel that has not run on a GPU yet runs here."""
-    img, st, ref, cn = _run(scene_root, scene, name, size, size, spp, pool, integrator="vpt")
+@pytest.mark.parametrize("scene,name,size,spp,pool,kw", VPT_CASES)
+def test_emulated_vpt_kernels_match_oracle(scene_root, oracle_lib, scene, name, size, spp, pool, kw):
+    """k_logic_vpt + k_trace_vpt (shadow queue -> re-arming transmittance stream, then the closest-hit stream): the kernels that have
+    not run on a GPU yet run here."""
+    img, st, ref, cn = _run(scene_root, scene, name, size, size, spp, pool, integrator="vpt", **kw)
     assert st["paths"] == cn["paths"] == size * size * spp
     match, flipped = _flip(img, ref)
     assert flipped <= 0.02 and rel_l2(img[match], ref[match]) < 2e-5
