@@ -146,12 +146,15 @@ static int launch_iteration(adapt_handle* h) {
     CK(cudaEventRecord(ev.e[0], st));
     if (h->integrator == 1) {
         // volumetric integrator: k_logic_vpt (samples -> shadow queue) + k_trace_vpt (transmittance stream, then the closest-hit stream)
-        // one instantiation for now (every material group).  The two-sided / textured one (M_ALL | M_TEXTURED, verified on the CPU) is
-        // held back: instantiating it changes ptxas' allocation of the shared out-of-line texture_query and with it the SASS of the
-        // GPU-validated textured k_logic kernels -- to be added together with a GPU run.
-        k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
-            h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin,
-            parity, (unsigned)h->stats.iterations);
+        // two instantiations: every material group; the same plus two-sided BRDFs and albedo textures
+        if (h->sv.two_sides || h->sv.textures)
+            k_logic_vpt<M_ALL | M_TEXTURED><<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin,
+                parity, (unsigned)h->stats.iterations);
+        else
+            k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin,
+                parity, (unsigned)h->stats.iterations);
         CK(cudaEventRecord(ev.e[1], st));
         CK(cudaEventRecord(ev.e[2], st));
         k_trace_vpt<<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_cur, h->refill, h->leaf_t | (h->node_steps << 8), parity);
@@ -363,8 +366,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         if (d->integrator != 1 || env_int("ADAPT_ENABLE_VPT", 0) == 0)
             return set_error(ADAPT_ERR_INVALID, "adapt_create: integrator 1 (vpt, participating media) is not enabled in this build -- only `pt` runs on the device "
                                                 "(ADAPT_ENABLE_VPT=1 switches on its kernels, which have run under the CPU-side SIMT emulator but not on a GPU yet); there is no CPU fallback");
-        if (d->brdf_two_sides || d->textures || !d->obj_aabb || d->num_shadow_ray > VOL_MAX_REQUESTS)
-            return set_error(ADAPT_ERR_INVALID, "adapt_create: the first vpt kernel does not cover two-sided BRDFs, textures or more than 8 shadow rays yet (and needs obj_aabb)");
+        if (!d->obj_aabb || d->num_shadow_ray > VOL_MAX_REQUESTS)
+            return set_error(ADAPT_ERR_INVALID, "adapt_create: vpt needs obj_aabb (world box) and at most 8 shadow rays per vertex");
     }
     if (d->n_emitters < 0 || (d->n_emitters > 0 && !d->emitters)) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad emitters");
     if (d->n_emitters == 0 && d->num_shadow_ray > 0)

@@ -183,7 +183,21 @@ PT_D float3 vol_albedo_texel(const SceneView& sv, const HitRec& h, int obj, bool
         tu = q0.z * bu + q1.x * bv + q0.x * bw;
         tv = q0.w * bu + q1.y * bv + q0.y * bw;
     }
-    return texture_query(sv, 0, obj, tu, tv);
+    // Texture.query (bxdf/texture.py:114-139), kept apart from pt_shade.cuh's out-of-line texture_query on purpose: a new caller of that
+    // shared function makes ptxas re-allocate it, which would change the SASS of the GPU-validated textured k_logic kernels
+    const float4* q = reinterpret_cast<const float4*>(sv.textures + obj);              // map 0 = albedo
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    const int off_x = __float_as_int(a.y), off_y = __float_as_int(a.z), w = __float_as_int(a.w), hh = __float_as_int(b.x);
+    const float scaled_u = floor_mod_f(tu * b.y * (float)w, (float)w - 1.f);
+    const float scaled_v = floor_mod_f(tv * b.z * (float)hh, (float)hh - 1.f);
+    const float floor_u = floorf(scaled_u), floor_v = floorf(scaled_v);
+    const float ratio_u = scaled_u - floor_u, ratio_v = scaled_v - floor_v;
+    const int iu = (int)(floor_u + (float)off_x), iv = (int)(floor_v + (float)off_y);
+    const float4* img = sv.tex_img[0];
+    const size_t size = (size_t)sv.tex_size[0];
+    const float4 ff = __ldg(img + (size_t)iv * size + iu), cf = __ldg(img + (size_t)iv * size + iu + 1);
+    const float4 fc = __ldg(img + (size_t)(iv + 1) * size + iu), cc = __ldg(img + (size_t)(iv + 1) * size + iu + 1);
+    return mix3(mix3(mk3(ff.x, ff.y, ff.z), mk3(cf.x, cf.y, cf.z), ratio_u), mix3(mk3(fc.x, fc.y, fc.z), mk3(cc.x, cc.y, cc.z), ratio_u), ratio_v);
 }
 
 // ---------------------------------------------------------------- the loop body between two traces

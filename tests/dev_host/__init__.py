@@ -45,16 +45,16 @@ def build_wavefront(force: bool = False) -> str:
 _wf = None
 
 
-def wavefront_render(packed, n_spp: int, pool_slots: int = 256, trace_grid: int = 2):
+def wavefront_render(packed, n_spp: int, pool_slots: int = 256, trace_grid: int = 2, cnt_start: int = 0):
     """Run the library's kernels under the SIMT emulator on one packed scene -> (film sums (w,h,3), stats dict)."""
     global _wf
     if _wf is None:
         _wf = C.CDLL(build_wavefront())
-        _wf.wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        _wf.wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     w, h = packed.desc.width, packed.desc.height
     acc = np.zeros((w, h, 3), np.float32)
     st = np.zeros(5, np.uint64)
-    rc = _wf.wavefront_render(C.addressof(packed.desc), int(n_spp), int(pool_slots), int(trace_grid), acc.ctypes.data_as(C.POINTER(C.c_float)),
+    rc = _wf.wavefront_render(C.addressof(packed.desc), int(n_spp), int(pool_slots), int(trace_grid), int(cnt_start), acc.ctypes.data_as(C.POINTER(C.c_float)),
                               st.ctypes.data_as(C.POINTER(C.c_uint64)))
     if rc != 0:
         raise RuntimeError(f"emulated wavefront failed ({rc}): no progress" if rc == -1 else f"emulated wavefront failed ({rc})")

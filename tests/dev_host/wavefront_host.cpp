@@ -39,8 +39,12 @@ void launch_iteration(Wavefront& w) {
     const int lt = w.leaf_t | (w.node_steps << 8);
     DeviceCounters* ctr = &w.ctr; Cursors* cur = &w.cur;
     if (w.integrator == 1) {
-        simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
-            w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
+        if (sv.two_sides || sv.textures)
+            simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_ALL | M_TEXTURED>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
+                w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
+        else
+            simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
+                w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
         simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
         w.iterations++; w.launches += 2;
         return;
@@ -78,8 +82,9 @@ extern "C" {
 // Renders n_spp samples of every pixel of the scene with the emulated kernels; film sums are ADDED to accum (w,h,3).
 // stats: [paths done, closest rays, shadow rays / transmittance segments, iterations, kernel launches].  Returns 0, or -1 when the
 // wavefront stops making progress.
-int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int trace_grid, float* accum, uint64_t* stats) {
+int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int trace_grid, int cnt_start, float* accum, uint64_t* stats) {
     Wavefront w;
+    w.cnt_origin = cnt_start;                 // samples cnt_start+1 .. cnt_start+n_spp (a handle resumed from a checkpoint)
     w.scene = make_dev_scene(d);
     if (!w.scene) return -2;
     const int no = d->n_objects;

@@ -31,7 +31,8 @@ def _flip(img, ref):
 @pytest.mark.parametrize("scene,name,size,spp,kw", [("cbox", "cbox.xml", 64, 8, {}), ("test", "media.xml", 64, 8, {}),
                                                     ("test", "media-clear.xml", 64, 8, {}),
                                                     ("test", "media.xml", 48, 4, dict(use_mis=False, use_rr=False, max_bounce=6)),
-                                                    ("csphere", "balls-mono.xml", 48, 4, {})])
+                                                    ("csphere", "balls-mono.xml", 48, 4, {}), ("test", "allbxdf.xml", 48, 4, {}),
+                                                    ("test", "textured.xml", 48, 4, {})])
 def test_vpt_shared_rng_parity_with_oracle(Renderer, scene_root, scene, name, size, spp, kw):
     from adapt_b200._lib import pack_scene
     from oracle.pt_oracle import OracleScene
