@@ -216,6 +216,16 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 //                  bool next(unsigned i, const HitRec& h, float3& o, float3& d, float& tmax);   (true: trace this segment next)
 template <typename Source> struct source_rearms { static constexpr bool value = false; };
 
+// Lane-occupancy counters of the scheduler, only under the CPU-side SIMT emulator (tests/dev_host, tools/emu_trace_stats.py): how
+// many lanes do useful work per scheduling round -- the quantity ncu reports as "threads per instruction" for the node / leaf code.
+#ifdef PT_SIMT_EMU
+struct TraceEmuStats { unsigned long long rounds, node_slots, node_lane_steps, leaf_rounds, leaf_lanes, leaf_lane_prims, refills, rays; };
+inline TraceEmuStats& trace_emu_stats() { static TraceEmuStats s{}; return s; }
+#define PT_EMU_STAT(expr) do { expr; } while (0)
+#else
+#define PT_EMU_STAT(expr) do { } while (0)
+#endif
+
 template <bool ANY_HIT, bool COUNT, bool WIDE, typename Source>
 PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __restrict__ cursors, const int refill, const int leaf_t_packed,
                             unsigned& traced, unsigned& n_nodes, unsigned& n_prims) {
@@ -274,6 +284,7 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                         hit.prim = -1; hit.t = tmax; hit.u = 0.f; hit.v = 0.f; hit.obj = 0; hit.cls = 0;
                         node = 0; sp = 0;
                         traced++;
+                        PT_EMU_STAT(trace_emu_stats().rays++);
                     }
                 }
                 // stream entries can be empty (parked slots, unused queue space): keep fetching until the warp is populated
@@ -282,6 +293,7 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
         }
         if (!__any_sync(FULL, cur >= 0)) continue;        // every fetched slot was empty: go and fetch again (or leave when exhausted)
         while (true) {
+            PT_EMU_STAT(if (lane == 0) { trace_emu_stats().rounds++; trace_emu_stats().node_slots += 32ull * (unsigned)(TRACE_NODE_STEPS_CT > 0 ? TRACE_NODE_STEPS_CT : node_steps); });
 #if TRACE_NODE_STEPS_CT > 0
             #pragma unroll
             for (int step = 0; step < TRACE_NODE_STEPS_CT; step++)
@@ -290,6 +302,7 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
 #endif
             if (node >= 0) {
                 if (COUNT) n_nodes++;
+                PT_EMU_STAT(trace_emu_stats().node_lane_steps++);
                 if (WIDE) {
                     node = wide_step(sc.nodes4 + (size_t)node * 8, r, hit.t, stack, sp);
                 } else {
@@ -318,9 +331,11 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
             if (leaf_mask) {
                 // run the leaf code when enough lanes are parked on a leaf, or nobody has inner work left
                 if (__popc(leaf_mask) >= leaf_t || !__any_sync(FULL, node >= 0)) {
+                    PT_EMU_STAT(if (lane == 0) trace_emu_stats().leaf_rounds++);
                     if (is_leaf) {
                         const int code = ~node;
                         const int first = code >> 3, cnt = (code & 7) + 1;
+                        PT_EMU_STAT(trace_emu_stats().leaf_lanes++; trace_emu_stats().leaf_lane_prims += (unsigned)cnt);
                         bool found = false;
                         for (int k = 0; k < cnt; k++) {
                             const float4 t0 = __ldg(prims + (first + k) * 3 + 0);

@@ -101,6 +101,10 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     w.logic_lists = (need & (M_GLOSSY | M_COAT_GGX | M_BSDF)) != 0;
     w.integrator = d->integrator;
     w.trace_grid = trace_grid > 0 ? trace_grid : 2;
+    // scheduler knobs of adapt_create (ADAPT_REFILL / ADAPT_LEAF_T / ADAPT_NODE_STEPS; the last one needs -DTRACE_NODE_STEPS_CT=0)
+    if (const char* v = getenv("ADAPT_REFILL")) w.refill = std::min(32, std::max(1, atoi(v)));
+    if (const char* v = getenv("ADAPT_LEAF_T")) w.leaf_t = std::min(32, std::max(1, atoi(v)));
+    if (const char* v = getenv("ADAPT_NODE_STEPS")) w.node_steps = std::min(8, std::max(1, atoi(v)));
     // the material class travels in the leaf records: rebuild them with the real classes (make_dev_scene passes zeros)
     {
         std::vector<uint8_t> sph((size_t)d->n_prims, 0), obj_class((size_t)no, 0);
@@ -161,6 +165,14 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     }
     delete w.scene;
     return 0;
+}
+
+// lane-occupancy counters of trace_stream_vote since the last call (pt_trace.cuh: TraceEmuStats, 8 values); resets them
+void wavefront_trace_stats(uint64_t* out) {
+    TraceEmuStats& s = trace_emu_stats();
+    out[0] = s.rounds; out[1] = s.node_slots; out[2] = s.node_lane_steps; out[3] = s.leaf_rounds; out[4] = s.leaf_lanes;
+    out[5] = s.leaf_lane_prims; out[6] = s.refills; out[7] = s.rays;
+    s = TraceEmuStats{};
 }
 
 }  // extern "C"
