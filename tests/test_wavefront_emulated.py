@@ -122,3 +122,26 @@ def test_emulated_vpt_kernels_match_oracle(scene_root, oracle_lib, scene, name, 
     assert st["paths"] == cn["paths"] == size * size * spp
     match, flipped = _flip(img, ref)
     assert flipped <= (0.06 if name == "allbxdf.xml" else 0.02) and rel_l2(img[match], ref[match]) < 3e-5
+
+
+SWEEP_SCENES = [("cbox", "cbox-point.xml"), ("csphere", "mix-balls.xml"), ("test", "allbxdf.xml"), ("test", "media.xml")]
+SWEEP_FLAGS = [dict(num_shadow_ray=0), dict(max_bounce=0), dict(max_bounce=1), dict(use_rr=False, max_bounce=5), dict(use_mis=False),
+               dict(stratified_sampling=False), dict(anti_alias=False), dict(num_shadow_ray=3)]
+
+
+@pytest.mark.parametrize("integrator", ["pt", "vpt"])
+@pytest.mark.parametrize("scene,name", SWEEP_SCENES)
+def test_emulated_kernels_over_integrator_flags(scene_root, oracle_lib, scene, name, integrator):
+    """Every integrator switch the XML / command line can flip (no shadow rays, zero and one bounce, no Russian roulette, no MIS,
+    uniform and no anti-aliasing, three shadow rays) on a 10x9 film in a 256-slot pool, kernels against the oracle.  (A sweep of nine
+    scenes x nine flag sets x both integrators was run once when the emulator was written: 162 combinations, all within these bounds
+    except the Fresnel-blend `pow` noise of balls-multi.xml, 1e-4 on the matching pixels.)"""
+    for kw in SWEEP_FLAGS:
+        img, st, ref, cn = _run(scene_root, scene, name, 10, 9, 2, 256, integrator=integrator, seed=7, **kw)
+        assert st["paths"] == cn["paths"] == 180, kw
+        if integrator == "pt" and kw.get("max_bounce", 1) > 0:          # with zero bounces the primary ray's result is unused too: not traced
+            assert st["rays_closest"] == cn["rays_closest_useful"], kw
+        match, flipped = _flip(img, ref)
+        assert flipped <= 0.08, kw
+        if match.any() and np.abs(ref[match]).sum() > 0:
+            assert rel_l2(img[match], ref[match]) < 5e-5, kw
