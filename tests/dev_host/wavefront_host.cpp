@@ -27,7 +27,7 @@ struct Wavefront {
     std::vector<float> accum;
     int mats = M_SIMPLE, logic_lists = 0, integrator = 0, trace_grid = 2;
     unsigned iter_parity = 0; unsigned long long iterations = 0, launches = 0, work_hi = 0; long long cnt_origin = 0;
-    int refill = 16, leaf_t = 8, node_steps = 4;
+    int refill = 16, leaf_t = 8, node_steps = 4, trace_mode = 1;
 };
 
 // adapt_abi.cu::launch_iteration, with <<<grid, block>>> replaced by simt::launch
@@ -71,7 +71,8 @@ void launch_iteration(Wavefront& w) {
     }
 #undef LAUNCH_LOGIC_V
 #undef LAUNCH_LOGIC_X
-    simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<1>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
+    if (w.trace_mode == 2) simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<2>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
+    else simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<1>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
     w.iterations++; w.launches++;
 }
 
@@ -105,6 +106,7 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     if (const char* v = getenv("ADAPT_REFILL")) w.refill = std::min(32, std::max(1, atoi(v)));
     if (const char* v = getenv("ADAPT_LEAF_T")) w.leaf_t = std::min(32, std::max(1, atoi(v)));
     if (const char* v = getenv("ADAPT_NODE_STEPS")) w.node_steps = std::min(8, std::max(1, atoi(v)));
+    if (const char* v = getenv("ADAPT_TRACE_MODE")) w.trace_mode = atoi(v) == 2 ? 2 : 1;       // 2: the 4-wide tree (pt_trace.cuh: wide_step)
     // the material class travels in the leaf records: rebuild them with the real classes (make_dev_scene passes zeros)
     {
         std::vector<uint8_t> sph((size_t)d->n_prims, 0), obj_class((size_t)no, 0);
@@ -119,6 +121,7 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
         to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), obj_class.data(), w.scene->bvh);
         w.scene->sv.nodes = reinterpret_cast<const float4*>(w.scene->bvh.nodes.data());
         w.scene->sv.leaf_prims = reinterpret_cast<const float4*>(w.scene->bvh.prims.data());
+        w.scene->sv.nodes4 = reinterpret_cast<const float4*>(w.scene->bvh.nodes4.data());
     }
     // pixels owned by this handle: the tile partition's list, or the film / crop window in 4x8 patches (adapt_create)
     if (d->pixel_list && d->n_pixels > 0) w.pixels.assign(d->pixel_list, d->pixel_list + d->n_pixels);
