@@ -149,8 +149,20 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     zeros(w.cls_count, 32); zeros(w.cls_items, w.logic_lists ? (size_t)LOGIC_NKEY * (size_t)P : 1);
     zeros(w.work, PT_NSTRIPE);
     w.accum.assign((size_t)d->width * d->height * 3, 0.f);
-    // adapt_render + adapt_sync
-    w.work_hi = (unsigned long long)w.pixels.size() * (unsigned long long)n_spp;
+    // adapt_render [+ a second adapt_render that raises the limit while stragglers of the first are still in flight] + adapt_sync
+    const unsigned long long total = (unsigned long long)w.pixels.size() * (unsigned long long)n_spp;
+    int first_spp = 0;
+    if (const char* v = getenv("WF_SPLIT_SPP")) first_spp = std::min(n_spp, std::max(0, atoi(v)));
+    if (first_spp > 0) {
+        w.work_hi = (unsigned long long)w.pixels.size() * (unsigned long long)first_spp;
+        for (int guard = 0; guard < 100000; guard++) {       // adapt_render returns once everything is HANDED OUT, not finished
+            unsigned long long claimed = 0;
+            for (const WorkStripe& s : w.work) claimed += s.claimed;
+            if (claimed >= w.work_hi) break;
+            launch_iteration(w);
+        }
+    }
+    w.work_hi = total;
     unsigned long long last_done = ~0ull, last_claimed = ~0ull; int stale = 0;
     while (true) {
         unsigned long long done = 0, claimed = 0;

@@ -80,6 +80,20 @@ def test_samples_split_over_calls_like_a_resumed_checkpoint(scene_root, oracle_l
     assert rel_l2(first + rest, whole) < 1e-6
 
 
+def test_second_render_call_while_paths_are_in_flight(scene_root, oracle_lib, monkeypatch):
+    """adapt_render returns when its samples are handed out; a second call raises the work limit while stragglers are still in the pool.
+    Work ids are absolute and gap-free, so the film equals the one-call film."""
+    from adapt_b200._lib import pack_scene
+    from dev_host import wavefront_render
+    e, a, o, c = load_scene(scene_root, "csphere", "balls-mono.xml", 14, 11)
+    ps = pack_scene(e, a, o, c, seed=4)
+    one, st1 = wavefront_render(ps, 4, 256)
+    monkeypatch.setenv("WF_SPLIT_SPP", "1")
+    two, st2 = wavefront_render(ps, 4, 256)
+    assert st1["paths"] == st2["paths"] == 14 * 11 * 4
+    assert rel_l2(two, one) < 1e-6
+
+
 def test_tile_partition_and_crop_window(scene_root, oracle_lib):
     """Multi-GPU tile split on one CPU: two handles that own interleaved 32x32 tiles render disjoint pixels whose sum is the whole film
     (what the NCCL reduce adds up); a crop window renders exactly its pixels."""
