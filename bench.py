@@ -38,6 +38,8 @@ WORKLOADS = {
     "car290k": ("cbox", "car290k.xml", ("car290k",), "configs[4]: sports-car ~290k tris, 3840x2160, 16 bounces"),
     "balls-mono": ("csphere", "balls-mono.xml", (), "configs[1]: cornell-spheres (film as in the XML unless --width)"),
     "cbox": ("cbox", "cbox.xml", (), "configs[0]: cornell box"),
+    # for --integrator vpt (not a BASELINE config): world fog + media-filled objects (adapt_b200/scenes.py::write_media)
+    "media": ("test", "media.xml", (), "volumetric coverage scene"),
 }
 
 
@@ -108,7 +110,7 @@ def cpu_reference_leg(args, e, a, o, c, budget_s=15.0, n_threads=0):
     from adapt_b200.dist import tile_partition
     from oracle.pt_oracle import OracleScene
     w, h = c["film"]["width"], c["film"]["height"]
-    osc = OracleScene(pack_scene(e, a, o, c, seed=args.seed))
+    osc = OracleScene(pack_scene(e, a, o, c, seed=args.seed, integrator=args.integrator))
     cores = n_threads or (os.cpu_count() or 1)
     # pilot: a 192x192 block in the image centre (run twice: the first call warms caches / the OpenMP pool)
     cw, ch = max(0, (w // 2 - 96)) // 32 * 32, max(0, (h // 2 - 96)) // 32 * 32
@@ -147,7 +149,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Mrays/s (closest-hit rays: primary + secondary)", "value": value, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})",
+        "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})" + ("" if args.integrator == "pt" else f", integrator {args.integrator}"),
                    "spp_per_step": spp, "sample": sample_desc},
         "spp_per_s": paths / dt / (w * h),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample_desc},
@@ -169,7 +171,7 @@ def run_b200(args):
     e, a, o, c = load_workload(args.workload, args.width, args.height, args.max_bounce)
     w, h = c["film"]["width"], c["film"]["height"]
     pixel_list = tile_partition(w, h, rank, world, tile=32) if world > 1 else None
-    rdr = Renderer(e, a, o, c, seed=args.seed, device_id=local_rank, pixel_list=pixel_list, pool_size=args.pool)
+    rdr = Renderer(e, a, o, c, seed=args.seed, device_id=local_rank, pixel_list=pixel_list, pool_size=args.pool, integrator=args.integrator)
     stream = torch.cuda.current_stream()
     rdr.set_stream(stream.cuda_stream)
     ptr, nfl = rdr.accum_device_ptr()
@@ -307,7 +309,7 @@ def run_b200(args):
             "metric": "Mrays/s (closest-hit rays: primary + secondary)", "value": value, "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})",
+            "config": {"workload": f"{args.workload} {w}x{h}, max_bounce {c['max_bounce']}, nsr {c['num_shadow_ray']} ({WORKLOADS[args.workload][3]})" + ("" if args.integrator == "pt" else f", integrator {args.integrator}"),
                        "spp_per_step": spp_step, "pool_slots": pool_slots,
                        "bvh": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in rdr.bvh_export(arrays=False).items()
                                if k in ("builder", "n_nodes", "depth", "build_ms")},
@@ -375,6 +377,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--integrator", default="pt", choices=["pt", "vpt"],
+                    help="vpt: the volumetric integrator (needs ADAPT_ENABLE_VPT=1 until its kernels are GPU-validated; use with --workload cbox or media)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -25,3 +25,4 @@ PY
 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/vpt_tiny.py 2>&1 | tail -25 | tee gpurun_out/vpt_memcheck.log
 if [ "${PIPESTATUS[0]}" != "0" ]; then echo "MEMCHECK FAILED - not running the larger tests"; exit 1; fi
 timeout 400 python -m pytest tests/test_gpu_vpt.py -q -x --timeout 120 2>&1 | tail -15 | tee gpurun_out/pytest_vpt.log
+timeout 300 python bench.py --integrator vpt --workload cbox --width 1024 --steps 3 --warmup 3 --spp-per-step 8 --cpu-budget 8 > gpurun_out/bench_vpt_cbox.json 2> gpurun_out/bench_vpt_cbox.err; tail -c 1500 gpurun_out/bench_vpt_cbox.json
