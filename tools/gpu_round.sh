@@ -3,6 +3,7 @@
 #   bash tools/gpu_round.sh [ncu] [ab] [big] [vpt] [postpone]
 #     vpt       bring-up of the volumetric kernels (tools/vpt_round.sh)
 #     postpone  A/B of the speculative-traversal experiment (pt_trace.cuh: TRACE_POSTPONE_LEAF) on the three workloads
+#     colorred  A/B of the colour-as-RED experiment of k_logic (pt_kernels.cuh: LOGIC_COLOR_RED)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
@@ -32,6 +33,17 @@ print(build(extra_flags=['-DTRACE_POSTPONE_LEAF=1'], out='adapt_b200/lib/postpon
   V="ADAPT_B200_LIB=$PWD/adapt_b200/lib/postpone/libadapt_b200.so"
   ADAPT_B200_LIB=$PWD/adapt_b200/lib/postpone/libadapt_b200.so timeout 300 python -m pytest tests/test_gpu_parity.py -q -x --timeout 90 2>&1 | tail -3
   bash tools/ab.sh "" "$V" "$V ADAPT_LEAF_T=12"
+  bash tools/ab.sh "--workload orb500k --spp-per-step 16" "$V"
+  bash tools/ab.sh "--workload balls-mono --width 1024 --spp-per-step 16" "$V" ;;
+colorred)
+  python -c "
+from adapt_b200.build import build
+import os
+os.makedirs('adapt_b200/lib/colorred', exist_ok=True)
+print(build(extra_flags=['-DLOGIC_COLOR_RED=1'], out='adapt_b200/lib/colorred/libadapt_b200.so'))"
+  V="ADAPT_B200_LIB=$PWD/adapt_b200/lib/colorred/libadapt_b200.so"
+  ADAPT_B200_LIB=$PWD/adapt_b200/lib/colorred/libadapt_b200.so timeout 300 python -m pytest tests/test_gpu_parity.py -q -x --timeout 90 2>&1 | tail -3
+  bash tools/ab.sh "" "$V"
   bash tools/ab.sh "--workload orb500k --spp-per-step 16" "$V"
   bash tools/ab.sh "--workload balls-mono --width 1024 --spp-per-step 16" "$V" ;;
 ncu)
