@@ -14,7 +14,7 @@ timeout 240 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpur
 for arg in "$@"; do
 case $arg in
 ab)
-  for v in "ADAPT_FUSE_TRACE=0" "ADAPT_REFILL=8" "ADAPT_REFILL=24" "ADAPT_TRACE_BLOCKS_PER_SM=6" "ADAPT_POOL=4194304" "ADAPT_POOL=1048576"; do
+  for v in "ADAPT_REFILL=8" "ADAPT_REFILL=12" "ADAPT_LEAF_T=6" "ADAPT_LEAF_T=10" "ADAPT_TRACE_BLOCKS_PER_SM=8" "ADAPT_TRACE_BLOCKS_PER_SM=10" "ADAPT_BVH_MAX_LEAF=3" "ADAPT_POOL=8388608"; do
     echo "== $v"; env $v timeout 200 python bench.py --steps 4 --warmup 3 --no-cpu 2> /dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); print(round(d['value'], 1), 'Mrays/s', round(d['ms_per_step'], 2), 'ms/step', {k: round(v, 2) for k, v in d['stage_ms_per_step'].items()})"
