@@ -79,7 +79,7 @@ struct adapt_handle {
     int trace_mode = 2;
     bool fuse_trace = true;
     bool wide_ok = true;
-    int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt; only with ADAPT_ENABLE_VPT=1, not yet run on a GPU)
+    int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt / k_trace_vpt)
     VolumeView vv{};
     int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH (bvh_device.cu)
     int bvh_nodes = 0, bvh_depth = 0;
@@ -362,10 +362,9 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         return set_error(ADAPT_ERR_INVALID, "adapt_create: empty scene or missing arrays");
     if (d->width <= 0 || d->height <= 0) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad film size");
     if (d->integrator != 0) {
-        // vpt: the device functions are verified on the CPU, the kernel that launches them has not run on a GPU yet
-        if (d->integrator != 1 || env_int("ADAPT_ENABLE_VPT", 0) == 0)
-            return set_error(ADAPT_ERR_INVALID, "adapt_create: integrator 1 (vpt, participating media) is not enabled in this build -- only `pt` runs on the device "
-                                                "(ADAPT_ENABLE_VPT=1 switches on its kernels, which have run under the CPU-side SIMT emulator but not on a GPU yet); there is no CPU fallback");
+        // 1 = vpt over homogeneous media (renderer/vpt.py; k_logic_vpt / k_trace_vpt).  Anything else has no kernels: refuse, never fall back
+        if (d->integrator != 1)
+            return set_error(ADAPT_ERR_INVALID, "adapt_create: unknown integrator (0 = pt, 1 = vpt over homogeneous media; bdpt / ao are not built)");
         if (!d->obj_aabb || d->num_shadow_ray > VOL_MAX_REQUESTS)
             return set_error(ADAPT_ERR_INVALID, "adapt_create: vpt needs obj_aabb (world box) and at most 8 shadow rays per vertex");
     }

@@ -26,12 +26,6 @@ using namespace adapt;
 #ifndef LOGIC_MIN_BLOCKS_SIMPLE
 #define LOGIC_MIN_BLOCKS_SIMPLE 4
 #endif
-// EXPERIMENT (off; verified under the SIMT emulator, not yet measured on a GPU): k_logic leaves the path colour in HBM -- what a vertex
-// adds (emission, rare in-kernel direct light) goes there as a RED, and only a terminating path reads it -- instead of reading and
-// rewriting the 16-byte colour word of every live slot in every iteration (32 of the 192 bytes a slot costs per launch).
-#ifndef LOGIC_COLOR_RED
-#define LOGIC_COLOR_RED 0
-#endif
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif
@@ -214,16 +208,10 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 
     if (alive) {
         // all per-slot state in one batch of independent 128-bit loads (one memory round trip)
-#if !LOGIC_COLOR_RED
-        const float4 c4 = pool.col[slot];
-#endif
         const float4 h4 = pool.hit[slot];
         const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
         const uint2 r2 = pool.rng[slot];
         bounce = (int)(misc.z & 0xffffu);
-#if !LOGIC_COLOR_RED
-        color = mk3(c4.x, c4.y, c4.z);
-#endif
         const int hit_word = __float_as_int(h4.w);
         const int prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
         if ((misc.z & SLOT_FINISH) || prim < 0) {
@@ -370,17 +358,16 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         float3 new_dir, indirect_spec; float new_pdf; bool is_specular;
         if (!(MATS & M_BSDF) || mat.kind == 0) brdf_sample<MATS>(mat, sfb, ray_d, rng, new_dir, indirect_spec, new_pdf, is_specular);
         else bsdf_sample(mat, sf, ray_d, sv.world_ior, rng, new_dir, indirect_spec, new_pdf, is_specular);
-#if LOGIC_COLOR_RED
         {
+            // the path colour stays in HBM: what a vertex adds (emission, rare in-kernel direct light) goes there as a RED and only a
+            // terminating path reads it, instead of every live slot reading and rewriting its colour word in every iteration
+            // (session r02a: k_logic 17.52 -> 17.31 ms/step on bunny90k, 24.39 -> 23.52 on orb500k)
             const float3 delta = direct_inline + emit_int * emission_weight * contribution;
             float* dst = reinterpret_cast<float*>(pool.col + slot);
             if (delta.x != 0.f) atomicAdd(dst + 0, delta.x);              // NaN != 0: a poisoned sample still poisons the path
             if (delta.y != 0.f) atomicAdd(dst + 1, delta.y);
             if (delta.z != 0.f) atomicAdd(dst + 2, delta.z);
         }
-#else
-        color += (direct_inline + emit_int * emission_weight * contribution);
-#endif
         contribution *= indirect_spec / new_pdf;
         bounce += 1;
         uint32_t flags = SLOT_ALIVE | (is_specular ? SLOT_SPECULAR : 0u);
@@ -389,9 +376,6 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         pool.ray_o[slot] = make_float4(hit_point.x, hit_point.y, hit_point.z, tmax);
         pool.ray_d[slot] = make_float4(new_dir.x, new_dir.y, new_dir.z, 0.f);
         pool.thr[slot] = make_float4(contribution.x, contribution.y, contribution.z, new_pdf);
-#if !LOGIC_COLOR_RED
-        pool.col[slot] = make_float4(color.x, color.y, color.z, 0.f);
-#endif
         pool.rng[slot] = make_uint2((uint32_t)rng.state, (uint32_t)(rng.state >> 32));
         misc.z = (uint32_t)bounce | flags;
         pool.misc[slot] = misc;
@@ -399,9 +383,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 
     // ---------------------------------------------------------------- termination: NaN scrub + splat (:119)
     if (alive && terminate) {
-#if LOGIC_COLOR_RED
         { const float4 c4 = pool.col[slot]; color = mk3(c4.x, c4.y, c4.z); }
-#endif
         float* px = accum + (size_t)misc.x * 3;
         if (!isnan(color.x) && color.x != 0.f) atomicAdd(px + 0, color.x);
         if (!isnan(color.y) && color.y != 0.f) atomicAdd(px + 1, color.y);

@@ -17,12 +17,6 @@ namespace adapt {
 #ifndef TRACE_NODE_STEPS_CT
 #define TRACE_NODE_STEPS_CT 4
 #endif
-// EXPERIMENT (off; scored for lane occupancy with tools/emu_trace_stats.py, not yet measured on a GPU): a lane that reaches a leaf while
-// it still has stack entries sets the leaf aside and keeps taking node steps; the leaf is tested when a second one turns up or the
-// stack runs dry ("speculative traversal", Aila & Laine 2009).
-#ifndef TRACE_POSTPONE_LEAF
-#define TRACE_POSTPONE_LEAF 0
-#endif
 #define PT_T_EPS 1e-4f          // "ray_t > 1e-4" self-intersection guard of the reference
 #define PT_T_INF 1e7f           // min_depth initial value (tracer_base.py:176)
 #define PT_NODE_DONE ((int)0x80000000)
@@ -210,7 +204,9 @@ PT_D bool trace(const SceneView& sc, float3 o, float3 d, float tmax, HitRec& hit
 // round against ~56 for one node step), so a scheduling round gives every lane up to `node_steps` node steps before the
 // next vote (default 4: k_trace 39.3 -> 36.4 ms/step on bunny90k, 56.5 -> 53.6 on orb500k, 20.9 -> 19.1 on balls-mono;
 // 3..6 are equal, 8 is slower; unrolled at compile time, TRACE_NODE_STEPS_CT, another 2.6 %).  Replacing the four votes by one warp reduction of packed lane states (`redux.sync.add`)
-// was measured and rejected: -1 % with one step per round, nothing on top of node_steps, +10 % on the sphere scene.
+// was measured and rejected: -1 % with one step per round, nothing on top of node_steps, +10 % on the sphere scene.  So was setting a leaf
+// aside while the stack still has entries (speculative traversal, Aila & Laine 2009; session r02a: +3 % trace time on bunny90k, +5 % on
+// orb500k, -12 % only on the 18-primitive sphere scene; code removed).
 // The cursor is striped (pt_common.cuh: CursorStripe): one cursor for the whole stream cost 15 % of k_shadow's
 // stall samples (131 k same-address atomics per launch).
 //
@@ -244,9 +240,6 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
     int stack[PT_STACK_SIZE];
     int sp = 0, node = PT_NODE_DONE;
     int cur = -1;
-#if TRACE_POSTPONE_LEAF
-    int pend = PT_NODE_DONE;         // leaf set aside by this lane (PT_NODE_DONE: none)
-#endif
     // cursor stripe this warp is drawing from (warp-uniform)
     int stripe = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % PT_NCURSOR);
     unsigned s_lo, s_hi;
@@ -292,9 +285,6 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                         r = make_ray(o, d);
                         hit.prim = -1; hit.t = tmax; hit.u = 0.f; hit.v = 0.f; hit.obj = 0; hit.cls = 0;
                         node = 0; sp = 0;
-#if TRACE_POSTPONE_LEAF
-                        pend = PT_NODE_DONE;
-#endif
                         traced++;
                         PT_EMU_STAT(trace_emu_stats().rays++);
                     }
@@ -337,36 +327,18 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                         node = sp ? stack[--sp] : PT_NODE_DONE;
                     }
                 }
-#if TRACE_POSTPONE_LEAF
-                if (!WIDE && node < 0 && node != PT_NODE_DONE && pend == PT_NODE_DONE && sp > 0) { pend = node; node = stack[--sp]; }
-#endif
             }
-#if TRACE_POSTPONE_LEAF
-            // parked: a leaf in hand (with or without one set aside), or nothing left but the leaf set aside
-            const bool is_leaf = (node < 0 && node != PT_NODE_DONE) || (node == PT_NODE_DONE && pend != PT_NODE_DONE && cur >= 0);
-#else
             const bool is_leaf = node < 0 && node != PT_NODE_DONE;
-#endif
             const unsigned leaf_mask = __ballot_sync(FULL, is_leaf);
             if (leaf_mask) {
                 // run the leaf code when enough lanes are parked on a leaf, or nobody has inner work left
                 if (__popc(leaf_mask) >= leaf_t || !__any_sync(FULL, node >= 0)) {
                     PT_EMU_STAT(if (lane == 0) trace_emu_stats().leaf_rounds++);
                     if (is_leaf) {
-#if TRACE_POSTPONE_LEAF
-                      bool found = false;
-                      for (int which = 0; which < 2 && !(ANY_HIT && found); which++) {
-                        const int leaf = which == 0 ? pend : node;
-                        if (leaf == PT_NODE_DONE || leaf >= 0) continue;
-                        const int code = ~leaf;
-#else
                         const int code = ~node;
-#endif
                         const int first = code >> 3, cnt = (code & 7) + 1;
                         PT_EMU_STAT(trace_emu_stats().leaf_lanes++; trace_emu_stats().leaf_lane_prims += (unsigned)cnt);
-#if !TRACE_POSTPONE_LEAF
                         bool found = false;
-#endif
                         for (int k = 0; k < cnt; k++) {
                             const float4 t0 = __ldg(prims + (first + k) * 3 + 0);
                             const float4 t1 = __ldg(prims + (first + k) * 3 + 1);
@@ -382,23 +354,12 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                                 if (ANY_HIT) break;
                             }
                         }
-#if TRACE_POSTPONE_LEAF
-                      }
-                        pend = PT_NODE_DONE;
-                        // a lane parked with an inner node in hand cannot happen (is_leaf needs a leaf or DONE in `node`)
                         node = (ANY_HIT && found) ? PT_NODE_DONE : (sp ? stack[--sp] : PT_NODE_DONE);
-#else
-                        node = (ANY_HIT && found) ? PT_NODE_DONE : (sp ? stack[--sp] : PT_NODE_DONE);
-#endif
                     }
                 }
             }
             // retire finished lanes; only then re-evaluate whether the warp should go and refill
-#if TRACE_POSTPONE_LEAF
-            const bool fin = node == PT_NODE_DONE && pend == PT_NODE_DONE && cur >= 0;
-#else
             const bool fin = node == PT_NODE_DONE && cur >= 0;
-#endif
             if (__any_sync(FULL, fin)) {
                 if (fin) {
                     if constexpr (source_rearms<Source>::value) {
@@ -409,9 +370,6 @@ PT_D void trace_stream_vote(const SceneView& sc, Source& src, CursorStripe* __re
                             r = make_ray(o2, d2);
                             hit.prim = -1; hit.t = tmax2; hit.u = 0.f; hit.v = 0.f; hit.obj = 0; hit.cls = 0;
                             node = 0; sp = 0;
-#if TRACE_POSTPONE_LEAF
-                            pend = PT_NODE_DONE;
-#endif
                         } else {
                             cur = -1;
                         }

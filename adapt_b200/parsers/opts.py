@@ -40,7 +40,7 @@ def _expand_config(argv):
 
 
 def get_options(delayed_parse: bool = False, argv=None):
-    parser = argparse.ArgumentParser(description="B200-native drop-in for AdaPT's `--type pt` renderer")
+    parser = argparse.ArgumentParser(description="B200-native drop-in for AdaPT's `--type pt` / `--type vpt` renderers")
     parser.add_argument("--config", help="Config file path", type=str, default=None)
     parser.add_argument("--iter_num", default=-1, help="Number of iterations (-1 means from XML / 2000)", type=int)
     parser.add_argument("--normalize", default=0.0, help="Normalize the output picture with its <x> quantile value", type=float)
@@ -51,10 +51,11 @@ def get_options(delayed_parse: bool = False, argv=None):
     parser.add_argument("--img_name", default="pbr", help="Output image name", type=str)
     parser.add_argument("--img_ext", default="png", choices=["png", "jpg", "bmp"], help="Output image extension", type=str)
     parser.add_argument("--scene", default="cbox", help="Name of the scene", type=str)
-    parser.add_argument("--name", default="cbox.xml", help="Scene file name with extension", type=str)
+    parser.add_argument("--name", default="complex.xml", help="Scene file name with extension", type=str)
     parser.add_argument("--arch", default="b200", choices=["b200", "cuda", "gpu"], help="Backend (always the sm_100a CUDA path)")
     parser.add_argument("--save_iter", default=-1, type=int, help="Iteration to save check-point")
-    parser.add_argument("--type", default="pt", choices=["pt"], help="Algorithm to be used (only `pt` is in scope)")
+    parser.add_argument("--type", default="vpt", choices=["vpt", "pt", "bdpt", "ao"],
+                        help="Algorithm to be used (defaults as in the reference, parsers/opts.py:28-31; `pt` and `vpt` run on the device, the others are refused)")
     parser.add_argument("-p", "--profile", default=False, action="store_true", help="Print per-stage device timings")
     parser.add_argument("--no_gui", default=False, action="store_true", help="Accepted for compatibility (there is no GUI)")
     parser.add_argument("-d", "--debug", default=False, action="store_true", help="Accepted for compatibility")

@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--integrator", default="pt", choices=["pt", "vpt"],
-                    help="vpt: the volumetric integrator (needs ADAPT_ENABLE_VPT=1 until its kernels are GPU-validated; use with --workload cbox or media)")
+                    help="vpt: the volumetric integrator over homogeneous media (use with --workload cbox or media)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Rendering main executable -- same flags and flow as the reference's render.py (65-166), driving the
-B200-native `pt` renderer.  Usage (identical to AdaPT):
+B200-native `pt` / `vpt` renderers.  Usage (identical to AdaPT):
 
     python render.py --scene cbox --name cbox.xml --type pt --iter_num 64 --no_gui
 
@@ -39,10 +39,10 @@ def save_check_point(chkpt: dict, opts):
 def main(argv=None):
     opts = get_options(argv=argv)
     from adapt_b200.renderer.vanilla_renderer import Renderer
-    rdr_mapping = {"pt": Renderer}
+    from adapt_b200.renderer.vpt import VolumeRenderer
+    rdr_mapping = {"pt": Renderer, "vpt": VolumeRenderer}             # render.py:33 (bdpt / ao are outside the hot-path scope)
     if opts.type not in rdr_mapping:
-        # `vpt` (the reference's default): oracle + device functions exist, the kernels do not -- and nothing falls back
-        raise NotImplementedError(f"--type {opts.type}: only the unidirectional path tracer `pt` runs on the device in this build")
+        raise NotImplementedError(f"--type {opts.type}: `pt` and `vpt` (homogeneous media) run on the device in this build; nothing falls back")
     input_folder = os.path.join(opts.input_path, opts.scene)
     emitter_configs, array_info, all_objs, configs = scene_parsing(input_folder, opts.name)
     output_folder = folder_path(opts.output_path)

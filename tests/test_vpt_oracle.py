@@ -2,8 +2,8 @@
 homogeneous media (world fog + media attached to BSDF objects; grid volumes are not restated) is held to renders produced by the
 reference's OWN code (tests/golden/make_reference_golden.py vpt -> reference_vpt.npz: the unmodified renderer/vpt.py, bxdf/medium.py,
 bxdf/phase.py, sampler/phase_sampling.py executed on the Taichi stand-in with the shared counter-keyed RNG), plus closed-form checks of
-the phase functions and of the free-flight sampling.  The device kernels for this integrator do not exist yet: libadapt_b200 rejects
-integrator = 1 (tests/test_abi.py), there is no CPU fallback."""
+the phase functions and of the free-flight sampling.  The device kernels are covered by tests/test_gpu_vpt.py (-m gpu) and, without a GPU, by
+tests/test_wavefront_emulated.py; there is no CPU fallback."""
 import ctypes as C
 import os
 
@@ -68,15 +68,16 @@ def test_media_reach_the_c_abi(scene_root):
         pack_scene(e, a, o, c, integrator="bdpt")
 
 
-def test_cuda_library_rejects_vpt_instead_of_falling_back(scene_root):
-    """No device kernels for vpt yet: adapt_create must say so (before looking for a GPU), never render something else."""
+def test_cuda_library_rejects_unknown_integrators_instead_of_falling_back(scene_root):
+    """0 = pt and 1 = vpt have kernels; any other integrator must be refused (before looking for a GPU), never rendered as something else."""
     from adapt_b200._lib import load_library, pack_scene
     lib = load_library()
     e, a, o, c = load_scene(scene_root, "cbox", "cbox.xml", 8, 8)
     ps = pack_scene(e, a, o, c, integrator="vpt")
+    ps.desc.integrator = 2
     h = C.c_void_p()
     assert lib.adapt_create(C.byref(h), C.byref(ps.desc)) == -1 and not h
-    assert b"vpt" in lib.adapt_last_error()
+    assert b"integrator" in lib.adapt_last_error()
 
 
 # ------------------------------------------------------------------------------------------------ closed-form checks of the medium code

@@ -20,21 +20,19 @@ from adapt_b200.scenes import DEFAULT_ROOT, ensure_big_meshes          # noqa: E
 from conftest import load_scene                                       # noqa: E402
 import dev_host                                                       # noqa: E402
 
-POSTPONE = "--postpone" in sys.argv          # build with -DTRACE_POSTPONE_LEAF=1 (the speculative-traversal experiment of pt_trace.cuh)
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 scene, name, size, spp = (argv + ["cbox", "bunny90k.xml", "48", "1"][len(argv):])[:4]
 size, spp = int(size), int(spp)
 if name in ("bunny90k.xml", "orb500k.xml", "car290k.xml"):
     ensure_big_meshes(DEFAULT_ROOT, (name[:-4],))
 # a build with the node steps as a run-time value (the shipped default unrolls four at compile time)
-lib_path = os.path.join(os.path.dirname(dev_host.WF_LIB), "libwavefront_host_rt%s.so" % ("_postpone" if POSTPONE else ""))
+lib_path = os.path.join(os.path.dirname(dev_host.WF_LIB), "libwavefront_host_rt.so")
 deps = dev_host.WF_DEPS + dev_host.DEPS[3:]
 if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
-    subprocess.check_call(["g++", "-O2", "-std=c++20", "-w", "-fPIC", "-ffp-contract=fast", "-march=x86-64-v3", "-DTRACE_NODE_STEPS_CT=0", "-DTRACE_POSTPONE_LEAF=%d" % int(POSTPONE),
+    subprocess.check_call(["g++", "-O2", "-std=c++20", "-w", "-fPIC", "-ffp-contract=fast", "-march=x86-64-v3", "-DTRACE_NODE_STEPS_CT=0",
                            "-I" + dev_host.CUDA_INC, "-shared", "-o", lib_path, dev_host.WF_SRC, os.path.join(ROOT, "adapt_b200", "csrc", "bvh_build.cpp")])
 e, a, o, c = load_scene(DEFAULT_ROOT, scene, name, size, size)
 ps = pack_scene(e, a, o, c, seed=1)
-print("variant: leaves postponed while the stack has entries (TRACE_POSTPONE_LEAF=1)" if POSTPONE else "variant: shipped scheduler")
 print(f"{scene}/{name} {size}x{size} x {spp} spp, {a['primitives'].shape[0]} primitives, pool 2048 slots, 2 trace blocks")
 print(f"{'refill':>6} {'leaf_t':>6} {'steps':>5} | {'node lanes/32':>13} {'leaf lanes/32':>13} {'prims/leaf lane':>15} {'rounds/ray':>10} {'node steps/ray':>14}")
 ref = None

@@ -1,9 +1,7 @@
 #!/bin/bash
 # One GPU-box session: smoke, tests, bench (+ A/B variants), launch list, full ncu captures of the two kernels.
-#   bash tools/gpu_round.sh [ncu] [ab] [big] [vpt] [postpone]
+#   bash tools/gpu_round.sh [ncu] [ab] [big] [vpt]
 #     vpt       bring-up of the volumetric kernels (tools/vpt_round.sh)
-#     postpone  A/B of the speculative-traversal experiment (pt_trace.cuh: TRACE_POSTPONE_LEAF) on the three workloads
-#     colorred  A/B of the colour-as-RED experiment of k_logic (pt_kernels.cuh: LOGIC_COLOR_RED)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
@@ -24,28 +22,6 @@ big)
   timeout 300 python bench.py --workload balls-mono --width 1024 --steps 3 --warmup 3 --spp-per-step 16 --cpu-budget 8 > gpurun_out/bench_balls.json 2> gpurun_out/bench_balls.err; tail -c 2500 gpurun_out/bench_balls.json; tail -3 gpurun_out/bench_balls.err ;;
 vpt)
   bash tools/vpt_round.sh ;;
-postpone)
-  python -c "
-from adapt_b200.build import build
-import os
-os.makedirs('adapt_b200/lib/postpone', exist_ok=True)
-print(build(extra_flags=['-DTRACE_POSTPONE_LEAF=1'], out='adapt_b200/lib/postpone/libadapt_b200.so'))"
-  V="ADAPT_B200_LIB=$PWD/adapt_b200/lib/postpone/libadapt_b200.so"
-  ADAPT_B200_LIB=$PWD/adapt_b200/lib/postpone/libadapt_b200.so timeout 300 python -m pytest tests/test_gpu_parity.py -q -x --timeout 90 2>&1 | tail -3
-  bash tools/ab.sh "" "$V" "$V ADAPT_LEAF_T=12"
-  bash tools/ab.sh "--workload orb500k --spp-per-step 16" "$V"
-  bash tools/ab.sh "--workload balls-mono --width 1024 --spp-per-step 16" "$V" ;;
-colorred)
-  python -c "
-from adapt_b200.build import build
-import os
-os.makedirs('adapt_b200/lib/colorred', exist_ok=True)
-print(build(extra_flags=['-DLOGIC_COLOR_RED=1'], out='adapt_b200/lib/colorred/libadapt_b200.so'))"
-  V="ADAPT_B200_LIB=$PWD/adapt_b200/lib/colorred/libadapt_b200.so"
-  ADAPT_B200_LIB=$PWD/adapt_b200/lib/colorred/libadapt_b200.so timeout 300 python -m pytest tests/test_gpu_parity.py -q -x --timeout 90 2>&1 | tail -3
-  bash tools/ab.sh "" "$V"
-  bash tools/ab.sh "--workload orb500k --spp-per-step 16" "$V"
-  bash tools/ab.sh "--workload balls-mono --width 1024 --spp-per-step 16" "$V" ;;
 ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 240 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu --spp-per-step 8 > gpurun_out/ncu_bench.log 2>&1

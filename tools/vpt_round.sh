@@ -2,7 +2,6 @@
 # GPU session that brings the volumetric integrator's first kernel up: memcheck on a tiny scene first (a hang or an
 # out-of-bounds access must not take the box down), then the gated parity tests, then a short timing of a fog scene.
 mkdir -p gpurun_out
-export ADAPT_ENABLE_VPT=1
 cat > /tmp/vpt_tiny.py <<'PY'
 import os, sys
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
