@@ -330,6 +330,10 @@ def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed
     d.device_id = int(device_id)
     if pixel_list is not None:
         pl = _i32(pixel_list).reshape(-1)
+        if pl.shape[0] == 0:
+            # n_pixels == 0 means "whole film" to adapt_create: an empty list must never turn into that (a rank that owns no tile would
+            # render everything and the framebuffer reduce would count those pixels several times)
+            raise ValueError("pixel_list is empty: this handle would own no pixel (film with fewer tiles than ranks? use a smaller tile)")
         d.n_pixels = pl.shape[0]
         d.pixel_list = ps._ptr("pixel_list", pl, C.c_int32)
     else:

@@ -14,7 +14,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,17 +59,41 @@ static int env_int(const char* name, int dflt) {
 // ================================================================================================
 // handle
 // ================================================================================================
-struct adapt_handle {
-    int device = 0;
-    cudaStream_t stream = nullptr;            // stream in use
-    cudaStream_t own_stream = nullptr;        // created by adapt_create
-    SceneView sv{};
+// A lane is one path pool with its queues, cursors and stream.  A handle can run up to PT_MAX_LANES of them side by side
+// (ADAPT_LANES=2): while lane A's persistent k_trace drains its tail, lane B's k_logic / k_trace blocks take the free SMs.  Lanes share
+// the scene, the work stripes (both claim from the same counters, so the load balances itself), the statistics counters and the film
+// (atomics); everything a kernel resets or double-buffers per iteration is per lane.
+// Measured (sessions r02c / r02d): two HANDLES on two host threads reach +11 % aggregate throughput on bunny90k, but only because each
+// then amortises its end-of-batch drain over twice the samples; two lanes inside one handle at the same samples per batch are within
+// +-1.5 % of one lane on all three workloads (the persistent trace kernel owns every register of the SM while it runs, so the other lane
+// only ever fills its tail), and two lanes double the pool memory.  Default: one lane.
+#define PT_MAX_LANES 2
+struct IterEvents { cudaEvent_t e[4]; };
+struct Lane {
     PathPool pool{};
     ShadowQueue sq{};
+    Cursors* d_cur = nullptr;
+    unsigned* d_cls_items = nullptr;          // [LOGIC_NKEY][n_slots]: global per-class slot lists (k_classify)
+    CursorStripe* d_cls_count = nullptr;      // [2][16]
+    unsigned iter_parity = 0;
+    unsigned long long iterations = 0;
+    cudaStream_t stream = nullptr;            // lane 0: the handle's stream (own or the caller's); other lanes: their own
+    cudaStream_t own_stream = nullptr;
+    std::vector<IterEvents> ev_ring;
+    size_t ev_used = 0;
+};
+
+struct adapt_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;            // stream in use (== lanes[0].stream)
+    cudaStream_t own_stream = nullptr;        // created by adapt_create
+    SceneView sv{};
+    Lane lanes[PT_MAX_LANES];
+    int n_lanes = 1;
+    cudaEvent_t ev_fork = nullptr;            // orders the other lanes' streams after what the caller put on the handle's stream
     DeviceCounters* d_ctr = nullptr;
     WorkStripe* d_work = nullptr;
     WorkStripe* h_work = nullptr;             // pinned copy the host polls
-    Cursors* d_cur = nullptr;
     float* d_accum = nullptr;
     float* d_mean = nullptr;                  // scratch of adapt_read_pixels, allocated on first use
     int* d_pixel_list = nullptr;
@@ -72,13 +101,22 @@ struct adapt_handle {
     int width = 0, height = 0;
     int cnt = 0;                              // spp enqueued so far (the reference's self.cnt)
     long long cnt_origin = 0;                 // work id -> sample number: cnt_origin + id / n_pixels + 1
-    unsigned long long work_hi = 0;           // work ids [0, work_hi) have been enqueued since create (== pixel-samples)
+    std::atomic<unsigned long long> work_hi{0};   // work ids [0, work_hi) have been enqueued since create (== pixel-samples)
+    // adapt_render only raises work_hi and wakes this thread, which launches wavefront iterations until everything enqueued has been handed
+    // out to a path slot; every other entry point first waits for it to go idle (wait_worker), so the handle itself stays single-caller.
+    std::thread worker;
+    std::mutex wk_mutex;
+    std::condition_variable wk_wake, wk_idle;
+    bool wk_stop = false, wk_busy = false;
+    int wk_rc = 0;
+    std::string wk_error;
     std::vector<void*> allocs;
     int trace_grid = 0;
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
-    int trace_mode = 2;
+    int trace_mode = 1;                       // 1 binary BVH, 3 compressed 8-wide BVH, 0 baseline without lane refill
     bool fuse_trace = true;
-    bool wide_ok = true;
+    bool wide_ok = true;                      // the 8-wide tree was built and fits the traversal stack
+    bool want_wide = false;
     int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt / k_trace_vpt)
     VolumeView vv{};
     int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH (bvh_device.cu)
@@ -89,18 +127,16 @@ struct adapt_handle {
     std::vector<uint8_t> sph, obj_class;
     std::vector<int32_t> prim_obj;
     bool has_ns = false;
+    bool poisoned = false;                    // a launch failed or the watchdog fired: counters and film no longer agree, only adapt_destroy is valid
+    std::vector<adapt_emitter> h_emitters;    // host copy (inv_area of mesh lights is refreshed by adapt_update_geometry)
+    std::vector<int4> h_obj_info;
+    adapt_emitter* d_emitters = nullptr;
     float4* d_prim_geom = nullptr;            // writable aliases of sv.prim_geom / sv.prim_shade
     float4* d_prim_shade = nullptr;
     int logic_lists = 0;                      // global per-class slot lists + one k_logic launch per material group (k_classify)
-    unsigned* d_cls_items = nullptr;          // [LOGIC_NKEY][n_slots]
-    CursorStripe* d_cls_count = nullptr;      // [2][16]
-    unsigned iter_parity = 0;
     int refill = 16, leaf_t = 8, node_steps = 4;
     bool count_nodes = false;
-    // timing
-    struct IterEvents { cudaEvent_t e[4]; };
-    std::vector<IterEvents> ev_ring;
-    size_t ev_used = 0;
+    // timing (per-iteration events live in the lanes)
     cudaEvent_t ev_poll = nullptr;
     adapt_stats stats{};
     DeviceCounters ctr_base{};                // counters at the last reset_stats
@@ -124,52 +160,57 @@ static int dev_upload(adapt_handle* h, T** p, const T* src, size_t n) {
 }
 
 static int drain_events(adapt_handle* h) {
-    if (h->ev_used == 0) return 0;
-    CK(cudaEventSynchronize(h->ev_ring[h->ev_used - 1].e[3]));
-    for (size_t i = 0; i < h->ev_used; i++) {
-        float a = 0, b = 0, c = 0;
-        cudaEventElapsedTime(&a, h->ev_ring[i].e[0], h->ev_ring[i].e[1]);
-        cudaEventElapsedTime(&b, h->ev_ring[i].e[1], h->ev_ring[i].e[2]);
-        cudaEventElapsedTime(&c, h->ev_ring[i].e[2], h->ev_ring[i].e[3]);
-        h->stats.ms_logic += a; h->stats.ms_shadow += b; h->stats.ms_closest += c; h->stats.ms_total += a + b + c;
+    for (int l = 0; l < h->n_lanes; l++) {
+        Lane& L = h->lanes[l];
+        if (L.ev_used == 0) continue;
+        CK(cudaEventSynchronize(L.ev_ring[L.ev_used - 1].e[3]));
+        for (size_t i = 0; i < L.ev_used; i++) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, L.ev_ring[i].e[0], L.ev_ring[i].e[1]);
+            cudaEventElapsedTime(&b, L.ev_ring[i].e[1], L.ev_ring[i].e[2]);
+            cudaEventElapsedTime(&c, L.ev_ring[i].e[2], L.ev_ring[i].e[3]);
+            // with two lanes the launches of one overlap those of the other: the stage sums can exceed the wall time of a step
+            h->stats.ms_logic += a; h->stats.ms_shadow += b; h->stats.ms_closest += c; h->stats.ms_total += a + b + c;
+        }
+        L.ev_used = 0;
     }
-    h->ev_used = 0;
     return 0;
 }
 
-static int launch_iteration(adapt_handle* h) {
-    if (h->ev_used == h->ev_ring.size()) { int rc = drain_events(h); if (rc) return rc; }
-    adapt_handle::IterEvents& ev = h->ev_ring[h->ev_used++];
-    cudaStream_t st = h->stream;
-    const int parity = (int)(h->iter_parity & 1u);
-    h->iter_parity ^= 1u;
+static int launch_iteration(adapt_handle* h, Lane& L) {
+    if (L.ev_used == L.ev_ring.size()) { int rc = drain_events(h); if (rc) return rc; }
+    IterEvents& ev = L.ev_ring[L.ev_used++];
+    cudaStream_t st = L.stream;
+    const int parity = (int)(L.iter_parity & 1u);
+    L.iter_parity ^= 1u;
     CK(cudaEventRecord(ev.e[0], st));
     if (h->integrator == 1) {
         // volumetric integrator: k_logic_vpt (samples -> shadow queue) + k_trace_vpt (transmittance stream, then the closest-hit stream)
         // two instantiations: every material group; the same plus two-sided BRDFs and albedo textures
         if (h->sv.two_sides || h->sv.textures)
-            k_logic_vpt<M_ALL | M_TEXTURED><<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
-                h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin,
-                parity, (unsigned)h->stats.iterations);
+            k_logic_vpt<M_ALL | M_TEXTURED><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
+                parity, (unsigned)L.iterations);
         else
-            k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<h->pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
-                h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin,
-                parity, (unsigned)h->stats.iterations);
+            k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
+                parity, (unsigned)L.iterations);
         CK(cudaEventRecord(ev.e[1], st));
         CK(cudaEventRecord(ev.e[2], st));
-        k_trace_vpt<<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, h->pool, h->sq, h->d_ctr, h->d_cur, h->refill, h->leaf_t | (h->node_steps << 8), parity);
+        if (h->trace_mode == 3) k_trace_vpt<3><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, h->leaf_t | (h->node_steps << 8), parity);
+        else k_trace_vpt<1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, h->leaf_t | (h->node_steps << 8), parity);
         CK(cudaEventRecord(ev.e[3], st));
         CK(cudaGetLastError());
-        h->stats.iterations += 1;
+        h->stats.iterations += 1; L.iterations += 1;
         h->stats.kernel_launches += 2;
         return 0;
     }
     int n_logic = 0;
     {
-        const int lg = h->pool.n_slots / LOGIC_BLOCK;
-#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { k_logic<M, LISTED><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_work, h->d_cur, h->d_accum, \
-        h->d_pixel_list, h->n_pixels, h->work_hi, h->cnt_origin, parity, (unsigned)h->stats.iterations, \
-        h->d_cls_items, h->d_cls_count, (KEYS)); n_logic++; } while (0)
+        const int lg = L.pool.n_slots / LOGIC_BLOCK;
+#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { k_logic<M, LISTED><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, \
+        h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin, parity, (unsigned)L.iterations, \
+        L.d_cls_items, L.d_cls_count, (KEYS)); n_logic++; } while (0)
         // two-sided BRDFs and texture lookups are compile-time variants of every instantiation
 #define LAUNCH_LOGIC_V(M, LISTED, KEYS) do { \
         if (ts && tex) LAUNCH_LOGIC_X((M) | M_TWOSIDED | M_TEXTURED, LISTED, KEYS); else if (ts) LAUNCH_LOGIC_X((M) | M_TWOSIDED, LISTED, KEYS); \
@@ -181,7 +222,7 @@ static int launch_iteration(adapt_handle* h) {
             LAUNCH_LOGIC_V(M_SIMPLE, false, no_keys);
         } else {
             // several material groups: global class lists, then one launch per group present (k_classify)
-            k_classify<<<lg, LOGIC_BLOCK, 0, st>>>(h->pool, h->sq, h->d_cur, h->d_cls_items, h->d_cls_count, parity);
+            k_classify<<<lg, LOGIC_BLOCK, 0, st>>>(L.pool, L.sq, L.d_cur, L.d_cls_items, L.d_cls_count, parity);
             n_logic++;
             const KeySet k_simple = {{0, 1, 2, 6, LOGIC_NKEY - 2, LOGIC_NKEY - 1, -1, -1}}, k_glossy = {{4, 5, -1, -1, -1, -1, -1, -1}};
             const KeySet k_coat = {{3, 7, -1, -1, -1, -1, -1, -1}}, k_bsdf = {{8, 9, 10, -1, -1, -1, -1, -1}};
@@ -197,21 +238,21 @@ static int launch_iteration(adapt_handle* h) {
     const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t | (h->node_steps << 8);   // node steps per scheduling round ride in the high bits
     if (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) {
         CK(cudaEventRecord(ev.e[2], st));          // fused: the whole trace time is booked under "closest"
-        if (h->trace_mode == 2) k_trace<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
-        else k_trace<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        if (h->trace_mode == 3) k_trace<3><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, L.d_cur, rf, lt, parity, h->bvh_nodes);
+        else k_trace<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, L.d_cur, rf, lt, parity, h->bvh_nodes);
     } else {
-        if (h->trace_mode == 2) k_shadow<2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
-        else if (h->trace_mode == 1) k_shadow<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
-        else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->sq, h->d_ctr, h->d_cur, rf, lt, parity);
+        if (h->trace_mode == 3) k_shadow<3><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, L.d_cur, rf, lt, parity);
+        else if (h->trace_mode == 1) k_shadow<1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, L.d_cur, rf, lt, parity);
+        else k_shadow<0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, L.d_cur, rf, lt, parity);
         CK(cudaEventRecord(ev.e[2], st));
-        if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
-        else if (h->trace_mode == 2) k_closest<false, 2><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
-        else if (h->trace_mode == 1) k_closest<false, 1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
-        else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, h->pool, h->d_ctr, h->d_cur, rf, lt);
+        if (h->count_nodes) k_closest<true, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, h->d_ctr, L.d_cur, rf, lt);
+        else if (h->trace_mode == 3) k_closest<false, 3><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, h->d_ctr, L.d_cur, rf, lt);
+        else if (h->trace_mode == 1) k_closest<false, 1><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, h->d_ctr, L.d_cur, rf, lt);
+        else k_closest<false, 0><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, h->d_ctr, L.d_cur, rf, lt);
     }
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
-    h->stats.iterations += 1;
+    h->stats.iterations += 1; L.iterations += 1;
     h->stats.kernel_launches += n_logic + ((h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 2);
     return 0;
 }
@@ -233,14 +274,25 @@ static int run_until(adapt_handle* h, Pred done) {
     CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (done(work_totals(h->h_work))) return 0;
+    // the other lanes start after whatever the caller has queued on the handle's stream (film upload, a framebuffer reduce ...)
+    if (h->n_lanes > 1) {
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        for (int l = 1; l < h->n_lanes; l++) CK(cudaStreamWaitEvent(h->lanes[l].stream, h->ev_fork, 0));
+    }
+    // iterations of the lanes alternate in the launch order, so lane B's k_logic is queued right behind lane A's k_trace
+    auto launch_batch = [&]() -> int {
+        for (int k = 0; k < batch; k++)
+            for (int l = 0; l < h->n_lanes; l++) { int rc = launch_iteration(h, h->lanes[l]); if (rc) return rc; }
+        return 0;
+    };
     WorkTotals last{~0ull, ~0ull};
     int stale = 0;
     for (int guard = 0; guard < (1 << 26); guard++) {
-        for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
+        int rc = launch_batch(); if (rc) return rc;
         CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev_poll, h->stream));
         // overlap: queue the next batch before looking at this one's counters
-        for (int k = 0; k < batch; k++) { int rc = launch_iteration(h); if (rc) return rc; }
+        rc = launch_batch(); if (rc) return rc;
         CK(cudaEventSynchronize(h->ev_poll));
         const WorkTotals now = work_totals(h->h_work);
         if (done(now)) return 0;
@@ -250,6 +302,11 @@ static int run_until(adapt_handle* h, Pred done) {
         if (stale > 512) return set_error(ADAPT_ERR_STATE, "wavefront makes no progress (work counters unchanged for 4096 iterations)");
     }
     return set_error(ADAPT_ERR_STATE, "wavefront did not converge");
+}
+// every lane's stream idle (kernels queued behind the last poll included)
+static int sync_lanes(adapt_handle* h) {
+    for (int l = 0; l < h->n_lanes; l++) CK(cudaStreamSynchronize(h->lanes[l].stream));
+    return 0;
 }
 
 // ================================================================================================
@@ -300,42 +357,53 @@ static void dev_release(adapt_handle* h, const void* p) {
 static int build_accel(adapt_handle* h, const float* primitives) {
     SceneView& sv = h->sv;
     const int np = sv.n_prims, no = sv.n_objects;
-    dev_release(h, sv.nodes); dev_release(h, sv.nodes4); dev_release(h, sv.leaf_prims);
-    sv.nodes = nullptr; sv.nodes4 = nullptr; sv.leaf_prims = nullptr;
+    // the new structure is built into temporaries and only swapped in once everything succeeded: after a failed update the handle
+    // still holds its previous, valid structure
+    const float4 *new_nodes = nullptr, *new_prims = nullptr; const uint4* new_nodes8 = nullptr;
+    auto drop_new = [&]() { dev_release(h, new_nodes); dev_release(h, new_nodes8); dev_release(h, new_prims); };
+    bool wide_ok = true; int n_nodes = 0, depth = 0; float build_ms = 0.f;
     float root_lo[3], root_hi[3];
     if (h->bvh_builder == 1) {
-        // device build: linear BVH straight into the traversal layout; no 4-wide tree
+        // device build: linear BVH straight into the traversal layout; no 8-wide tree
         DeviceBvh db; std::string what;
         cudaError_t be = build_bvh_device(primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), np, no, h->bvh_params.max_leaf,
                                           h->stream, db, what);
         if (be != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH build: " + what + ": " + cudaGetErrorString(be));
         h->allocs.push_back(db.nodes); h->allocs.push_back(db.leaf_prims);
-        sv.nodes = db.nodes; sv.leaf_prims = db.leaf_prims;
-        if (db.depth > PT_STACK_SIZE) return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack (use the host builder for this scene)");
-        h->wide_ok = false;
-        h->bvh_nodes = db.n_nodes; h->bvh_depth = db.depth; h->bvh_build_ms = db.build_ms;
+        new_nodes = db.nodes; new_prims = db.leaf_prims;
+        if (db.depth > PT_STACK_SIZE) { drop_new(); return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack (use the host builder for this scene)"); }
+        wide_ok = false;
+        n_nodes = db.n_nodes; depth = db.depth; build_ms = db.build_ms;
         for (int a = 0; a < 3; a++) { root_lo[a] = db.root_lo[a]; root_hi[a] = db.root_hi[a]; }
     } else {
         const auto t0 = std::chrono::steady_clock::now();
         BuildResult br;
-        build_bvh(primitives, h->sph.data(), np, h->bvh_params, br);
+        BuildParams bp = h->bvh_params;
+        if (h->want_wide) bp.max_leaf = std::min(bp.max_leaf, 3);        // a leaf child of an 8-wide node holds at most 3 primitives
+        build_bvh(primitives, h->sph.data(), np, bp, br);
         GpuBvh gb;
-        to_gpu_layout(br, primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), gb);
-        h->bvh_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        to_gpu_layout(br, primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), gb, h->want_wide);
+        build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (gb.depth > PT_STACK_SIZE) return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack");
         float4* tmp4 = nullptr;
         int rc;
-        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes.data()), gb.nodes.size() * 4))) return rc;
-        sv.nodes = tmp4;
-        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes4.data()), gb.nodes4.size() * 8))) return rc;
-        sv.nodes4 = tmp4;
-        h->wide_ok = 3 * gb.depth4 + 1 <= PT_STACK_SIZE;         // a 4-wide step can push three entries
-        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3))) return rc;
-        sv.leaf_prims = tmp4;
-        h->bvh_nodes = (int)gb.nodes.size(); h->bvh_depth = gb.depth;
+        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.nodes.data()), gb.nodes.size() * 4))) { drop_new(); return rc; }
+        new_nodes = tmp4;
+        wide_ok = h->want_wide && !gb.nodes8.empty() && gb.depth8 + 1 <= PT_STACK8;      // one stack entry per level
+        if (wide_ok) {
+            uint4* tmp8 = nullptr;
+            if ((rc = dev_upload(h, &tmp8, reinterpret_cast<const uint4*>(gb.nodes8.data()), gb.nodes8.size() * 5))) { drop_new(); return rc; }
+            new_nodes8 = tmp8;
+        }
+        if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3))) { drop_new(); return rc; }
+        new_prims = tmp4;
+        n_nodes = (int)gb.nodes.size(); depth = gb.depth;
         const Aabb& rb = br.nodes[0].box;
         for (int a = 0; a < 3; a++) { root_lo[a] = rb.lo[a]; root_hi[a] = rb.hi[a]; }
     }
+    dev_release(h, sv.nodes); dev_release(h, sv.nodes8); dev_release(h, sv.leaf_prims);
+    sv.nodes = new_nodes; sv.nodes8 = new_nodes8; sv.leaf_prims = new_prims;
+    h->wide_ok = wide_ok; h->bvh_nodes = n_nodes; h->bvh_depth = depth; h->bvh_build_ms = build_ms;
     // scene bounds (root of the BVH), padded: used to finish camera rays that cannot hit anything
     const float pad = 1e-3f;
     sv.world_lo = mk3(root_lo[0] - pad, root_lo[1] - pad, root_lo[2] - pad);
@@ -343,13 +411,25 @@ static int build_accel(adapt_handle* h, const float* primitives) {
     return 0;
 }
 
+static void worker_main(adapt_handle* h);
+
 void adapt_destroy(adapt_handle* h) {
     if (!h) return;
+    if (h->worker.joinable()) {
+        { std::unique_lock<std::mutex> lk(h->wk_mutex); h->wk_idle.wait(lk, [h] { return !h->wk_busy; }); h->wk_stop = true; }
+        h->wk_wake.notify_all();
+        h->worker.join();
+    }
     cudaSetDevice(h->device);
+    for (Lane& L : h->lanes) if (L.stream) cudaStreamSynchronize(L.stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
-    for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) if (ev.e[k]) cudaEventDestroy(ev.e[k]);
+    for (Lane& L : h->lanes) {
+        for (auto& ev : L.ev_ring) for (int k = 0; k < 4; k++) if (ev.e[k]) cudaEventDestroy(ev.e[k]);
+        if (L.own_stream) cudaStreamDestroy(L.own_stream);
+    }
     if (h->ev_poll) cudaEventDestroy(h->ev_poll);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->h_work) cudaFreeHost(h->h_work);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -386,6 +466,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     CKC(cudaSetDevice(h->device));
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    h->lanes[0].stream = h->stream;
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, h->device));
 
@@ -435,6 +516,10 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     if (h->bvh_builder != 0 && h->bvh_builder != 1) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (host SAH) or 1 (device LBVH)"));
     SceneView& sv = h->sv;
     sv.n_objects = no; sv.n_prims = np;
+    // traversal: 1 = binary BVH (default), 3 = compressed 8-wide BVH collapsed from it (host builder only), 0 = baseline without lane refill
+    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);
+    if (h->trace_mode != 0 && h->trace_mode != 3) h->trace_mode = 1;
+    h->want_wide = h->trace_mode == 3 && h->bvh_builder == 0;
     CKH(build_accel(h, d->primitives));
     float4* tmp4 = nullptr;
     CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4; h->d_prim_geom = tmp4;
@@ -486,7 +571,9 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
             float4* duv = nullptr; CKH(dev_upload(h, &duv, puv.data(), puv.size())); sv.prim_uv = duv;
         }
     }
-    adapt_emitter* dem = nullptr; CKH(dev_upload(h, &dem, d->emitters, (size_t)d->n_emitters)); sv.emitters = dem;
+    adapt_emitter* dem = nullptr; CKH(dev_upload(h, &dem, d->emitters, (size_t)d->n_emitters)); sv.emitters = dem; h->d_emitters = dem;
+    h->h_emitters.assign(d->emitters, d->emitters + d->n_emitters);
+    h->h_obj_info = obj_info;
     int4* doi = nullptr; CKH(dev_upload(h, &doi, obj_info.data(), obj_info.size())); sv.obj_info = doi;
     sv.n_objects = no; sv.n_emitters = d->n_emitters; sv.n_prims = np;
     sv.cam_r.r0 = mk3(d->cam_r[0], d->cam_r[1], d->cam_r[2]);
@@ -524,20 +611,19 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     h->n_pixels = (int)pixels.size();
     CKH(dev_upload(h, &h->d_pixel_list, pixels.data(), pixels.size()));
 
-    // ---- path pool
-    // default pool: 4 Mi slots (fewer only for films under 128 Ki owned pixels: 32 per pixel, at least 64 Ki) (measured on bunny90k 1080p: 1 Mi slots 2.42,
-    // 2 Mi 2.92, 4 Mi 3.18, 8 Mi 3.19 Grays/s -- a bigger pool amortises the per-launch ramp and tail of the persistent kernels)
+    // ---- path pools
+    // default pool: 4 Mi slots per lane (fewer only for films under 128 Ki owned pixels: 32 per pixel, at least 64 Ki) (measured on bunny90k 1080p: 1 Mi slots 2.42,
+    // 2 Mi 2.92, 4 Mi 3.18, 8 Mi 3.19 Grays/s -- a bigger pool amortises the per-launch ramp and tail of the persistent kernels).
+    // An explicit pool_size / ADAPT_POOL is the total over the lanes; pools under 128 Ki slots (tests) run as one lane.
+    h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
     int P = d->pool_size > 0 ? d->pool_size : env_int("ADAPT_POOL", 0);
+    const bool explicit_pool = P > 0;
     if (P <= 0) P = (int)std::min<long long>(1ll << 22, std::max<long long>(1ll << 16, 32ll * (long long)h->n_pixels));
+    h->n_lanes = std::min(PT_MAX_LANES, std::max(1, env_int("ADAPT_LANES", 1)));
+    if (h->count_nodes || (explicit_pool ? P < (1 << 17) : P < (1 << 22))) h->n_lanes = 1;
+    if (explicit_pool) P /= h->n_lanes;
     P = std::max(P, LOGIC_BLOCK);
     P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
-    h->pool.n_slots = P;
-    CKH(dev_alloc(h, &h->pool.ray_o, (size_t)P)); CKH(dev_alloc(h, &h->pool.ray_d, (size_t)P));
-    CKH(dev_alloc(h, &h->pool.hit, (size_t)P)); CKH(dev_alloc(h, &h->pool.thr, (size_t)P));
-    CKH(dev_alloc(h, &h->pool.col, (size_t)P)); CKH(dev_alloc(h, &h->pool.misc, (size_t)P));
-    CKH(dev_alloc(h, &h->pool.rng, (size_t)P));
-    CKC(cudaMemset(h->pool.misc, 0, (size_t)P * sizeof(uint4)));
-    CKC(cudaMemset(h->pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
     // segment k takes the shadow rays of the warps w with w % PT_NCURSOR == k: at most ceil(n_warps / PT_NCURSOR) * 32 * nsr entries
     // per k_logic launch.  Scenes with several material groups run up to five launches per iteration (k_classify lists), each
     // packing its slots from warp 0 on, so every launch can add one more partly filled warp per segment: 8 warps of slack.
@@ -546,68 +632,124 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     const bool several_groups = (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) != 0;
     const size_t seg_cap = (((size_t)P / 32 + PT_NCURSOR - 1) / PT_NCURSOR + (several_groups ? 8 : 0)) * 32 * (size_t)std::max(1, d->num_shadow_ray);
     const size_t Q = seg_cap * PT_NCURSOR;
-    h->sq.seg_cap = (int)seg_cap;
-    h->sq.capacity = (int)Q;
-    CKH(dev_alloc(h, &h->sq.o, Q)); CKH(dev_alloc(h, &h->sq.d, Q)); CKH(dev_alloc(h, &h->sq.c, Q));
-    CKH(dev_alloc(h, &h->sq.seg_count, (size_t)2 * PT_NCURSOR));
-    CKC(cudaMemset(h->sq.seg_count, 0, sizeof(CursorStripe) * 2 * PT_NCURSOR));
+    h->logic_lists = several_groups;
+    for (int l = 0; l < h->n_lanes; l++) {
+        Lane& L = h->lanes[l];
+        if (l > 0) { CKC(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking)); L.stream = L.own_stream; }
+        L.pool.n_slots = P;
+        CKH(dev_alloc(h, &L.pool.ray_o, (size_t)P)); CKH(dev_alloc(h, &L.pool.ray_d, (size_t)P));
+        CKH(dev_alloc(h, &L.pool.hit, (size_t)P)); CKH(dev_alloc(h, &L.pool.thr, (size_t)P));
+        CKH(dev_alloc(h, &L.pool.col, (size_t)P)); CKH(dev_alloc(h, &L.pool.misc, (size_t)P));
+        CKH(dev_alloc(h, &L.pool.rng, (size_t)P));
+        CKC(cudaMemset(L.pool.misc, 0, (size_t)P * sizeof(uint4)));
+        CKC(cudaMemset(L.pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
+        L.sq.seg_cap = (int)seg_cap;
+        L.sq.capacity = (int)Q;
+        CKH(dev_alloc(h, &L.sq.o, Q)); CKH(dev_alloc(h, &L.sq.d, Q)); CKH(dev_alloc(h, &L.sq.c, Q));
+        CKH(dev_alloc(h, &L.sq.seg_count, (size_t)2 * PT_NCURSOR));
+        CKC(cudaMemset(L.sq.seg_count, 0, sizeof(CursorStripe) * 2 * PT_NCURSOR));
+        CKH(dev_alloc(h, &L.d_cur, (size_t)1)); CKC(cudaMemset(L.d_cur, 0, sizeof(Cursors)));
+        CKH(dev_alloc(h, &L.d_cls_count, (size_t)32)); CKC(cudaMemset(L.d_cls_count, 0, sizeof(CursorStripe) * 32));
+        if (h->logic_lists) CKH(dev_alloc(h, &L.d_cls_items, (size_t)LOGIC_NKEY * (size_t)P));
+        L.ev_ring.resize(512);
+        for (auto& ev : L.ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
+    }
+    CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CKH(dev_alloc(h, &h->d_ctr, (size_t)1)); CKC(cudaMemset(h->d_ctr, 0, sizeof(DeviceCounters)));
     CKH(dev_alloc(h, &h->d_work, (size_t)PT_NSTRIPE)); CKC(cudaMemset(h->d_work, 0, sizeof(WorkStripe) * PT_NSTRIPE));
-    CKH(dev_alloc(h, &h->d_cur, (size_t)1)); CKC(cudaMemset(h->d_cur, 0, sizeof(Cursors)));
     CKC(cudaHostAlloc((void**)&h->h_work, sizeof(WorkStripe) * PT_NSTRIPE, cudaHostAllocDefault));
     std::memset(h->h_work, 0, sizeof(WorkStripe) * PT_NSTRIPE);
     CKH(dev_alloc(h, &h->d_accum, (size_t)d->width * d->height * 3));
     CKC(cudaMemset(h->d_accum, 0, (size_t)d->width * d->height * 3 * sizeof(float)));
 
     // ---- launch shape: persistent trace kernels, a multiple of the SM count
-    h->count_nodes = env_int("ADAPT_COUNT_NODES", 0) != 0;
-    // 2 = 4-wide tree: measured on B200 equal on orb500k, 6 % slower on bunny90k, 10 % faster only on the 18-primitive balls scene
-    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);
-    if (h->trace_mode == 2 && !h->wide_ok) h->trace_mode = 1;    // 4-wide tree too deep for the per-lane stack: binary tree
+    if (h->trace_mode == 3 && !h->wide_ok) h->trace_mode = 1;    // no 8-wide tree (device builder, or deeper than its stack): binary tree
     {
         // persistent trace kernels: exactly as many blocks as are resident at once (one wave), at most ADAPT_TRACE_BLOCKS_PER_SM per SM
         int occ = 0;
-        cudaError_t oe = h->trace_mode == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<2>, TRACE_BLOCK, 0)
-                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<1>, TRACE_BLOCK, 0);
+        cudaError_t oe = h->integrator == 1
+            ? (h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_vpt<3>, TRACE_BLOCK, 0)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_vpt<1>, TRACE_BLOCK, 0))
+            : (h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<3>, TRACE_BLOCK, 0)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<1>, TRACE_BLOCK, 0));
         if (oe != cudaSuccess || occ < 1) occ = 8;
         const int per_sm = std::max(1, std::min(occ, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 16)));
         h->trace_grid = prop.multiProcessorCount * per_sm;
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
-    h->logic_lists = (h->mats & (M_GLOSSY | M_COAT_GGX | M_BSDF)) != 0;
-    CKH(dev_alloc(h, &h->d_cls_count, (size_t)32)); CKC(cudaMemset(h->d_cls_count, 0, sizeof(CursorStripe) * 32));
-    if (h->logic_lists) CKH(dev_alloc(h, &h->d_cls_items, (size_t)LOGIC_NKEY * (size_t)h->pool.n_slots));
     h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
     h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 8)));
     h->node_steps = std::min(8, std::max(1, env_int("ADAPT_NODE_STEPS", 4)));
-    h->ev_ring.resize(512);
-    for (auto& ev : h->ev_ring) for (int k = 0; k < 4; k++) CKC(cudaEventCreate(&ev.e[k]));
     CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));
     CKC(cudaDeviceSynchronize());
 #undef CKH
 #undef CKC
+    h->worker = std::thread(worker_main, h);
     *out = h;
+    return 0;
+}
+
+static int poisoned_error() { return set_error(ADAPT_ERR_STATE, "handle unusable: an earlier adapt_render / adapt_sync failed (see that call's error); destroy it"); }
+
+// ---- the launch thread ------------------------------------------------------------------------------------------------------------
+static void worker_main(adapt_handle* h) {
+    cudaSetDevice(h->device);
+    std::unique_lock<std::mutex> lk(h->wk_mutex);
+    while (true) {
+        h->wk_wake.wait(lk, [h] { return h->wk_stop || h->wk_busy; });
+        if (h->wk_stop) return;
+        // hand out all work; the limit is re-read at every poll, so samples enqueued meanwhile are picked up without a bubble, and
+        // stragglers keep flowing into the next call (adapt_sync drains them)
+        int rc = 0; std::string err;
+        while (true) {
+            lk.unlock();
+            unsigned long long served = 0;
+            rc = run_until(h, [h, &served](const WorkTotals& t) { served = h->work_hi.load(); return t.claimed >= served; });
+            if (rc) err = g_last_error;
+            lk.lock();
+            if (rc || h->work_hi.load() == served) break;          // adapt_render raises work_hi under this lock: nothing slipped in
+        }
+        // a failed launch or the watchdog leaves `cnt` / `work_hi` ahead of what the film holds: no later call may divide by that count
+        if (rc) { h->wk_rc = rc; h->wk_error = err; h->poisoned = true; }
+        h->wk_busy = false;
+        h->wk_idle.notify_all();
+    }
+}
+// every entry point other than adapt_render: wait until the launch thread has handed out everything enqueued so far
+static int wait_worker(adapt_handle* h) {
+    std::unique_lock<std::mutex> lk(h->wk_mutex);
+    h->wk_idle.wait(lk, [h] { return !h->wk_busy; });
+    if (h->wk_rc) return set_error(h->wk_rc, "adapt_render (asynchronous) failed: " + h->wk_error);
     return 0;
 }
 
 int adapt_render(adapt_handle* h, int32_t n_spp) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_render: null handle");
+    if (h->poisoned) return poisoned_error();
     if (n_spp <= 0) return 0;
-    CK(cudaSetDevice(h->device));
-    // work ids are absolute and gap-free (pt_common.cuh: WorkStripe): a new batch just raises the limit
-    h->work_hi += (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
-    h->cnt += n_spp;
-    const unsigned long long target = h->work_hi;
-    // hand out all work; stragglers keep flowing into the next call (adapt_sync drains them)
-    return run_until(h, [target](const WorkTotals& t) { return t.claimed >= target; });
+    // work ids are absolute and gap-free (pt_common.cuh: WorkStripe): a new batch just raises the limit.  The call returns at once; the
+    // handle's launch thread does the rest and adapt_sync (or any read) is the synchronisation point, where a failure is reported.
+    {
+        std::lock_guard<std::mutex> lk(h->wk_mutex);
+        if (h->wk_rc) return set_error(h->wk_rc, "adapt_render (asynchronous) failed: " + h->wk_error);
+        h->work_hi.fetch_add((unsigned long long)h->n_pixels * (unsigned long long)n_spp);
+        h->cnt += n_spp;
+        h->wk_busy = true;
+    }
+    h->wk_wake.notify_one();
+    return 0;
 }
 
 int adapt_sync(adapt_handle* h) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_sync: null handle");
-    const unsigned long long target = h->work_hi;
-    int rc = run_until(h, [target](const WorkTotals& t) { return t.done >= target; });
+    int rc = wait_worker(h);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));
+    if (h->poisoned) return poisoned_error();
+    const unsigned long long target = h->work_hi.load();
+    rc = run_until(h, [target](const WorkTotals& t) { return t.done >= target; });
+    if (rc) { h->poisoned = true; return rc; }
+    rc = sync_lanes(h);
+    if (rc) return rc;
     return drain_events(h);
 }
 
@@ -650,14 +792,17 @@ void* adapt_host_alloc(uint64_t bytes) {
 void adapt_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int adapt_load_accum(adapt_handle* h, const float* src, int32_t spp) {
-    if (!h || !src || spp < 0) return set_error(ADAPT_ERR_INVALID, "adapt_load_accum: bad argument");
+    if (!h || spp < 0) return set_error(ADAPT_ERR_INVALID, "adapt_load_accum: bad argument");
     int rc = adapt_sync(h);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_accum, src, (size_t)h->width * h->height * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const size_t bytes = (size_t)h->width * h->height * 3 * sizeof(float);
+    // src == NULL: start from an empty film (cleared on the device, no host buffer involved)
+    if (src) CK(cudaMemcpyAsync(h->d_accum, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->d_accum, 0, bytes, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     // everything enqueued so far is finished (adapt_sync above): the next work id, work_hi, becomes sample spp + 1
     h->cnt = spp;
-    h->cnt_origin = (long long)spp - (long long)(h->work_hi / (unsigned long long)h->n_pixels);
+    h->cnt_origin = (long long)spp - (long long)(h->work_hi.load() / (unsigned long long)h->n_pixels);
     return 0;
 }
 
@@ -671,18 +816,25 @@ int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats) {
 int adapt_set_stream(adapt_handle* h, void* cuda_stream) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_set_stream: null handle");
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
-    int rc = drain_events(h);
+    int rc = wait_worker(h);
+    if (rc) return rc;
+    rc = sync_lanes(h);
+    if (rc) return rc;
+    rc = drain_events(h);
     if (rc) return rc;
     h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->lanes[0].stream = h->stream;
     return 0;
 }
 
 int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     if (!h || !out) return set_error(ADAPT_ERR_INVALID, "adapt_get_stats: null argument");
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
-    int rc = drain_events(h);
+    int rc = wait_worker(h);
+    if (rc) return rc;
+    rc = sync_lanes(h);
+    if (rc) return rc;
+    rc = drain_events(h);
     if (rc) return rc;
     DeviceCounters c;
     CK(cudaMemcpy(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
@@ -694,7 +846,8 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     out->rays_closest = (c.rays_closest - h->ctr_base.rays_closest) + (c.rays_culled - h->ctr_base.rays_culled);
     out->reserved[0] = c.rays_culled - h->ctr_base.rays_culled;
     out->reserved[1] = (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 0;
-    out->reserved[2] = (uint64_t)h->pool.n_slots;
+    out->reserved[2] = (uint64_t)h->lanes[0].pool.n_slots * (uint64_t)h->n_lanes;
+    out->reserved[3] = (uint64_t)h->n_lanes;
     out->rays_shadow = (c.rays_shadow - h->ctr_base.rays_shadow) + (c.shadow_inline - h->ctr_base.shadow_inline);
     out->nodes_visited = c.nodes_visited - h->ctr_base.nodes_visited;
     out->prims_tested = c.prims_tested - h->ctr_base.prims_tested;
@@ -704,8 +857,11 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
 int adapt_reset_stats(adapt_handle* h) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_reset_stats: null handle");
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
-    int rc = drain_events(h);
+    int rc = wait_worker(h);
+    if (rc) return rc;
+    rc = sync_lanes(h);
+    if (rc) return rc;
+    rc = drain_events(h);
     if (rc) return rc;
     CK(cudaMemcpy(&h->ctr_base, h->d_ctr, sizeof(DeviceCounters), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(h->h_work, h->d_work, sizeof(WorkStripe) * PT_NSTRIPE, cudaMemcpyDeviceToHost));
@@ -720,6 +876,7 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
     if (!any_hit && (!hit_obj || !hit_t || !hit_u || !hit_v)) return set_error(ADAPT_ERR_INVALID, "adapt_intersect_batch: closest-hit needs all outputs");
     if (n == 0) return 0;
     CK(cudaSetDevice(h->device));
+    { int rcw = wait_worker(h); if (rcw) return rcw; }
     float *d_o = nullptr, *d_d = nullptr, *d_tm = nullptr, *d_t = nullptr, *d_u = nullptr, *d_v = nullptr;
     int *d_obj = nullptr, *d_prim = nullptr;
     auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_tm); cudaFree(d_t); cudaFree(d_u); cudaFree(d_v); cudaFree(d_obj); cudaFree(d_prim); };
@@ -727,18 +884,21 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
     size_t n3 = (size_t)n * 3 * sizeof(float), n1 = (size_t)n * sizeof(float);
     CKF(cudaMalloc(&d_o, n3)); CKF(cudaMalloc(&d_d, n3)); CKF(cudaMalloc(&d_t, n1)); CKF(cudaMalloc(&d_u, n1)); CKF(cudaMalloc(&d_v, n1));
     CKF(cudaMalloc(&d_obj, n1)); CKF(cudaMalloc(&d_prim, n1));
-    CKF(cudaMemcpy(d_o, rays_o, n3, cudaMemcpyHostToDevice)); CKF(cudaMemcpy(d_d, rays_d, n3, cudaMemcpyHostToDevice));
-    if (tmax) { CKF(cudaMalloc(&d_tm, n1)); CKF(cudaMemcpy(d_tm, tmax, n1, cudaMemcpyHostToDevice)); }
-    k_intersect_batch<<<(n + 127) / 128, 128, 0, h->stream>>>(h->sv, n, d_o, d_d, d_tm, any_hit, d_obj, d_prim, d_t, d_u, d_v);
+    // every copy is ordered on the handle's stream: a pageable cudaMemcpy may return before its DMA has landed, and the (non-blocking)
+    // stream the kernel runs on is not ordered behind the legacy stream -- a flaky 10 % of stale rays in session r02d
+    cudaStream_t st = h->stream;
+    CKF(cudaMemcpyAsync(d_o, rays_o, n3, cudaMemcpyHostToDevice, st)); CKF(cudaMemcpyAsync(d_d, rays_d, n3, cudaMemcpyHostToDevice, st));
+    if (tmax) { CKF(cudaMalloc(&d_tm, n1)); CKF(cudaMemcpyAsync(d_tm, tmax, n1, cudaMemcpyHostToDevice, st)); }
+    k_intersect_batch<<<(n + 127) / 128, 128, 0, st>>>(h->sv, n, d_o, d_d, d_tm, any_hit, d_obj, d_prim, d_t, d_u, d_v);
     CKF(cudaGetLastError());
-    CKF(cudaStreamSynchronize(h->stream));
     h->stats.kernel_launches += 1;
-    CKF(cudaMemcpy(hit_prim, d_prim, n1, cudaMemcpyDeviceToHost));
-    if (hit_obj) CKF(cudaMemcpy(hit_obj, d_obj, n1, cudaMemcpyDeviceToHost));
+    CKF(cudaMemcpyAsync(hit_prim, d_prim, n1, cudaMemcpyDeviceToHost, st));
+    if (hit_obj) CKF(cudaMemcpyAsync(hit_obj, d_obj, n1, cudaMemcpyDeviceToHost, st));
     if (!any_hit) {
-        CKF(cudaMemcpy(hit_t, d_t, n1, cudaMemcpyDeviceToHost)); CKF(cudaMemcpy(hit_u, d_u, n1, cudaMemcpyDeviceToHost));
-        CKF(cudaMemcpy(hit_v, d_v, n1, cudaMemcpyDeviceToHost));
+        CKF(cudaMemcpyAsync(hit_t, d_t, n1, cudaMemcpyDeviceToHost, st)); CKF(cudaMemcpyAsync(hit_u, d_u, n1, cudaMemcpyDeviceToHost, st));
+        CKF(cudaMemcpyAsync(hit_v, d_v, n1, cudaMemcpyDeviceToHost, st));
     }
+    CKF(cudaStreamSynchronize(st));
 #undef CKF
     cleanup();
     return 0;
@@ -758,7 +918,31 @@ int adapt_update_geometry(adapt_handle* h, const float* primitives, const float*
     CK(cudaStreamSynchronize(h->stream));
     rc = build_accel(h, primitives);
     if (rc) return rc;
-    if (h->trace_mode == 2 && !h->wide_ok) h->trace_mode = 1;
+    if (h->trace_mode == 3 && !h->wide_ok) h->trace_mode = 1;
+    // area emitters on deforming meshes: inv_area = 1 / surface area of the attached object (parsers/obj_loader.py:82-93 as called from
+    // parsers/xml_parser.py:103; a sphere counts 4 pi r^2), recomputed for the new vertices
+    bool any_area = false;
+    for (adapt_emitter& em : h->h_emitters) {
+        if (em.type != 1 || em.obj_ref_id < 0 || em.obj_ref_id >= h->sv.n_objects) continue;
+        const int4 oi = h->h_obj_info[(size_t)em.obj_ref_id];
+        double area = 0.0;
+        if (oi.z != 0) {
+            const float r = primitives[(size_t)oi.x * 9 + 3];
+            area = 4.0 * 3.14159265358979323846 * (double)r * (double)r;
+        } else {
+            for (int k = oi.x; k < oi.x + oi.y; k++) {
+                const float* v = primitives + (size_t)k * 9;
+                const double a[3] = {(double)v[3] - v[0], (double)v[4] - v[1], (double)v[5] - v[2]}, b[3] = {(double)v[6] - v[0], (double)v[7] - v[1], (double)v[8] - v[2]};
+                const double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+                area += 0.5 * std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+            }
+        }
+        if (area > 0.0) { em.inv_area = (float)(1.0 / area); any_area = true; }
+    }
+    if (any_area) CK(cudaMemcpy(h->d_emitters, h->h_emitters.data(), h->h_emitters.size() * sizeof(adapt_emitter), cudaMemcpyHostToDevice));
+    // the uploads above are pageable cudaMemcpy calls (they may return before their DMA has landed) and the render streams are
+    // non-blocking: make sure everything is in place before the next adapt_render
+    CK(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -783,6 +967,7 @@ int adapt_bxdf_batch(adapt_handle* h, int32_t obj, int32_t n, const float* n_s, 
     if (obj < 0 || obj >= h->sv.n_objects) return set_error(ADAPT_ERR_INVALID, "adapt_bxdf_batch: object index out of range");
     if (n == 0) return 0;
     CK(cudaSetDevice(h->device));
+    { int rcw = wait_worker(h); if (rcw) return rcw; }
     const size_t n3 = (size_t)n * 3 * sizeof(float), n1 = (size_t)n * sizeof(float);
     float* d_in = nullptr;      // [n_s | n_g | incid | out] then outputs [eval | s_dir | s_spec | pdf | s_pdf | flag]
     CK(cudaMalloc(&d_in, 4 * n3 + 3 * n3 + 3 * n1));
@@ -791,16 +976,18 @@ int adapt_bxdf_batch(adapt_handle* h, int32_t obj, int32_t n, const float* n_s, 
     float* d_pdf = d_ss + (size_t)n * 3; float* d_sp = d_pdf + n; int* d_fl = reinterpret_cast<int*>(d_sp + n);
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    step(cudaMemcpy(d_ns, n_s, n3, cudaMemcpyHostToDevice)); step(cudaMemcpy(d_ng, n_g, n3, cudaMemcpyHostToDevice));
-    step(cudaMemcpy(d_inc, incid, n3, cudaMemcpyHostToDevice)); step(cudaMemcpy(d_out, out, n3, cudaMemcpyHostToDevice));
+    cudaStream_t st = h->stream;              // stream-ordered copies, see adapt_intersect_batch
+    step(cudaMemcpyAsync(d_ns, n_s, n3, cudaMemcpyHostToDevice, st)); step(cudaMemcpyAsync(d_ng, n_g, n3, cudaMemcpyHostToDevice, st));
+    step(cudaMemcpyAsync(d_inc, incid, n3, cudaMemcpyHostToDevice, st)); step(cudaMemcpyAsync(d_out, out, n3, cudaMemcpyHostToDevice, st));
     if (e == cudaSuccess) {
-        k_bxdf_batch<<<(n + 127) / 128, 128, 0, h->stream>>>(h->sv, obj, n, d_ns, d_ng, d_inc, d_out, two_sides, seed, d_ev, d_pdf, d_sd, d_ss, d_sp, d_fl);
-        step(cudaGetLastError()); step(cudaStreamSynchronize(h->stream));
+        k_bxdf_batch<<<(n + 127) / 128, 128, 0, st>>>(h->sv, obj, n, d_ns, d_ng, d_inc, d_out, two_sides, seed, d_ev, d_pdf, d_sd, d_ss, d_sp, d_fl);
+        step(cudaGetLastError());
         h->stats.kernel_launches += 1;
     }
-    step(cudaMemcpy(eval3, d_ev, n3, cudaMemcpyDeviceToHost)); step(cudaMemcpy(s_dir3, d_sd, n3, cudaMemcpyDeviceToHost));
-    step(cudaMemcpy(s_spec3, d_ss, n3, cudaMemcpyDeviceToHost)); step(cudaMemcpy(pdf, d_pdf, n1, cudaMemcpyDeviceToHost));
-    step(cudaMemcpy(s_pdf, d_sp, n1, cudaMemcpyDeviceToHost)); step(cudaMemcpy(s_flag, d_fl, n1, cudaMemcpyDeviceToHost));
+    step(cudaMemcpyAsync(eval3, d_ev, n3, cudaMemcpyDeviceToHost, st)); step(cudaMemcpyAsync(s_dir3, d_sd, n3, cudaMemcpyDeviceToHost, st));
+    step(cudaMemcpyAsync(s_spec3, d_ss, n3, cudaMemcpyDeviceToHost, st)); step(cudaMemcpyAsync(pdf, d_pdf, n1, cudaMemcpyDeviceToHost, st));
+    step(cudaMemcpyAsync(s_pdf, d_sp, n1, cudaMemcpyDeviceToHost, st)); step(cudaMemcpyAsync(s_flag, d_fl, n1, cudaMemcpyDeviceToHost, st));
+    step(cudaStreamSynchronize(st));
     cudaFree(d_in);
     if (e != cudaSuccess) return set_error(ADAPT_ERR_CUDA, std::string("adapt_bxdf_batch: ") + cudaGetErrorString(e));
     return 0;

@@ -151,13 +151,140 @@ void build_bvh(const float* primitives, const uint8_t* is_sphere, int32_t n, con
     out.nodes.resize((size_t)B.next_node.load());
 }
 
+namespace {
+
+// ---- 8-wide collapse ---------------------------------------------------------------------------------------------------------------
+struct Wide8 { int32_t child[8]; int n; };                        // binary node ids, in slot order after assign_slots (-1: empty slot)
+
+// Children -> octant-ordered slots: slot s stands for the corner (s & 1 ? +x : -x, s & 2 ? +y : -y, s & 4 ? +z : -z); greedy assignment of
+// the (child, slot) pair whose centre offset from the node's centre points most towards that corner.  Any assignment is correct (the
+// traversal culls against the running hit); a good one visits near children first.
+void assign_slots(const BuildResult& br, const Aabb& nb, Wide8& w) {
+    int32_t in[8]; const int n = w.n;
+    for (int k = 0; k < n; k++) in[k] = w.child[k];
+    float cost[8][8];
+    for (int k = 0; k < n; k++) {
+        const Aabb& cb = br.nodes[in[k]].box;
+        float d[3];
+        for (int a = 0; a < 3; a++) d[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+        for (int s = 0; s < 8; s++) cost[k][s] = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
+    }
+    bool child_done[8] = {false}, slot_done[8] = {false};
+    for (int s = 0; s < 8; s++) w.child[s] = -1;
+    for (int it = 0; it < n; it++) {
+        int bk = -1, bs = -1; float best = -3.0e38f;
+        for (int k = 0; k < n; k++) if (!child_done[k])
+            for (int s = 0; s < 8; s++) if (!slot_done[s] && cost[k][s] > best) { best = cost[k][s]; bk = k; bs = s; }
+        child_done[bk] = true; slot_done[bs] = true; w.child[bs] = in[bk];
+    }
+    w.n = 8;
+}
+
+// One node of the compressed tree: grid origin a quarter step below the node's box, the smallest power-of-two step that covers the box
+// in 254 steps, child planes rounded outwards with 1/64 step of margin (the traversal's 8-bit -> float trick costs 2^-9 of a step).
+void quantise_node(const BuildResult& br, const Aabb& nb, const Wide8& w, const int32_t* wide_index, const int32_t* leaf_pos,
+                   uint32_t child_base, uint32_t prim_base, GpuNode8& g) {
+    std::memset(&g, 0, sizeof(g));
+    float p[3], step[3]; uint32_t ebits[3];
+    for (int a = 0; a < 3; a++) {
+        const float ext = std::max(nb.hi[a] - nb.lo[a], 1e-30f);
+        int e = (int)std::ceil(std::log2((double)ext / 254.0));
+        e = std::min(std::max(e, -100), 100);
+        while (std::ldexp(1.0f, e) * 254.0f < ext) e++;               // log2 rounding
+        step[a] = std::ldexp(1.0f, e);
+        ebits[a] = (uint32_t)(e + 127);
+        p[a] = nb.lo[a] - 0.25f * step[a];
+    }
+    uint32_t imask = 0;
+    uint8_t meta[8] = {0}, q[6][8];
+    for (int s = 0; s < 8; s++) for (int a = 0; a < 3; a++) { q[a][s] = 255; q[3 + a][s] = 0; }     // empty slot: inverted box, never hit
+    for (int s = 0; s < 8; s++) {
+        const int32_t c = w.child[s];
+        if (c < 0) continue;
+        const BuildNode& cn = br.nodes[c];
+        if (cn.left >= 0) { imask |= 1u << s; meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s)); }
+        else {
+            const uint32_t cnt = (uint32_t)std::max(1, cn.count), off = (uint32_t)leaf_pos[c] - prim_base;
+            meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | off);
+        }
+        for (int a = 0; a < 3; a++) {
+            int lo = (int)std::floor((double)(cn.box.lo[a] - p[a]) / step[a] - 1.0 / 64.0);
+            int hi = (int)std::ceil((double)(cn.box.hi[a] - p[a]) / step[a] + 1.0 / 64.0);
+            lo = std::min(std::max(lo, 0), 255); hi = std::min(std::max(hi, 0), 255);
+            // float re-check of what the traversal evaluates: p + q * step must enclose the child's box
+            while (lo > 0 && p[a] + (float)lo * step[a] > cn.box.lo[a]) lo--;
+            while (hi < 255 && p[a] + (float)hi * step[a] < cn.box.hi[a]) hi++;
+            if (hi <= lo) { if (hi < 255) hi = lo + 1; else lo = hi - 1; }
+            q[a][s] = (uint8_t)lo; q[3 + a][s] = (uint8_t)hi;
+        }
+    }
+    std::memcpy(&g.q[0], &p[0], 4); std::memcpy(&g.q[1], &p[1], 4); std::memcpy(&g.q[2], &p[2], 4);
+    g.q[3] = ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24);
+    g.q[4] = child_base; g.q[5] = prim_base;
+    auto pack4 = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
+    g.q[6] = pack4(meta); g.q[7] = pack4(meta + 4);
+    g.q[8] = pack4(q[0]); g.q[9] = pack4(q[0] + 4); g.q[10] = pack4(q[1]); g.q[11] = pack4(q[1] + 4);      // qlo.x, qlo.y
+    g.q[12] = pack4(q[2]); g.q[13] = pack4(q[2] + 4); g.q[14] = pack4(q[3]); g.q[15] = pack4(q[3] + 4);    // qlo.z, qhi.x
+    g.q[16] = pack4(q[4]); g.q[17] = pack4(q[4] + 4); g.q[18] = pack4(q[5]); g.q[19] = pack4(q[5] + 4);    // qhi.y, qhi.z
+    (void)wide_index;
+}
+
+}  // namespace
+
 void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj,
-                   const uint8_t* obj_class, GpuBvh& out) {
+                   const uint8_t* obj_class, GpuBvh& out, bool eight) {
     const int32_t n = (int32_t)br.order.size();
+    // ---- 8-wide collapse first: it decides the order of the primitive records (node by node, a node's leaf children back to back).
+    // A node adopts the two children of its inner child with the largest surface area until it has eight children or only leaves.
+    std::vector<Wide8> wides; std::vector<int32_t> wide_root;         // binary id of each wide node's root, breadth-first
+    std::vector<int32_t> wide_index(br.nodes.size(), -1), leaf_pos(br.nodes.size(), -1), wide_depth;
+    std::vector<uint32_t> wide_prim_base, wide_child_base;
+    std::vector<int32_t> emit;                                       // emit[k] = index into br.order of the k-th primitive record
+    out.nodes8.clear(); out.depth8 = 0;
+    if (eight && n > 0) {
+        wide_root.push_back(0); wide_index[0] = 0; wide_depth.push_back(1);
+        for (size_t hd = 0; hd < wide_root.size(); hd++) {
+            const BuildNode& nd = br.nodes[wide_root[hd]];
+            Wide8 w; w.n = 0;
+            if (nd.left < 0) w.child[w.n++] = wide_root[hd];          // the whole scene is one leaf
+            else { w.child[w.n++] = nd.left; w.child[w.n++] = nd.right; }
+            while (w.n < 8) {
+                int best = -1; float best_area = -1.f;
+                for (int k = 0; k < w.n; k++) {
+                    const BuildNode& c = br.nodes[w.child[k]];
+                    if (c.left >= 0 && c.box.half_area() > best_area) { best_area = c.box.half_area(); best = k; }
+                }
+                if (best < 0) break;
+                const BuildNode& c = br.nodes[w.child[best]];
+                w.child[best] = c.left;
+                w.child[w.n++] = c.right;
+            }
+            assign_slots(br, nd.box, w);
+            wide_child_base.push_back((uint32_t)wide_root.size());
+            wide_prim_base.push_back((uint32_t)emit.size());
+            for (int s = 0; s < 8; s++) {
+                const int32_t c = w.child[s];
+                if (c < 0) continue;
+                const BuildNode& cn = br.nodes[c];
+                if (cn.left >= 0) {
+                    if (c != wide_root[hd]) { wide_index[c] = (int32_t)wide_root.size(); wide_root.push_back(c); wide_depth.push_back(wide_depth[hd] + 1); }
+                } else {
+                    leaf_pos[c] = (int32_t)emit.size();
+                    for (int32_t i = cn.first; i < cn.first + std::max(1, cn.count); i++) emit.push_back(i);
+                }
+            }
+            wides.push_back(w);
+        }
+        for (int32_t dd : wide_depth) out.depth8 = std::max(out.depth8, dd);
+    } else {
+        emit.resize((size_t)n);
+        for (int32_t k = 0; k < n; k++) emit[k] = k;
+        for (size_t b = 0; b < br.nodes.size(); b++) if (br.nodes[b].left < 0) leaf_pos[b] = br.nodes[b].first;
+    }
     out.prims.resize((size_t)std::max(1, n));
     std::memset(out.prims.data(), 0, out.prims.size() * sizeof(GpuPrim));
     for (int32_t k = 0; k < n; k++) {
-        int32_t p = br.order[k];
+        int32_t p = br.order[emit[k]];
         const float* v = primitives + (size_t)p * 9;
         GpuPrim& g = out.prims[k];
         bool sph = is_sphere && is_sphere[p];
@@ -175,11 +302,14 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
         int32_t cls = obj_class ? (int32_t)obj_class[prim_obj[p]] : 0;
         std::memcpy(&g.v[11], &cls, 4);
     }
-    // inner nodes get compact indices in DFS order (children of a node adjacent in memory)
+    if (eight && n > 0) {
+        out.nodes8.resize(wides.size());
+        for (size_t i = 0; i < wides.size(); i++)
+            quantise_node(br, br.nodes[wide_root[i]].box, wides[i], wide_index.data(), leaf_pos.data(), wide_child_base[i], wide_prim_base[i], out.nodes8[i]);
+    }
+    // inner nodes get compact indices, top of the tree first (keeps the hot upper levels in few cache lines)
     std::vector<int32_t> inner_index(br.nodes.size(), -1);
-    std::vector<int32_t> stack;
     int32_t n_inner = 0;
-    // BFS-ish numbering: top of the tree first (keeps the hot upper levels in few cache lines)
     {
         std::vector<int32_t> q; q.push_back(0);
         for (size_t h = 0; h < q.size(); h++) {
@@ -187,9 +317,10 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
             if (nd.left >= 0) { inner_index[q[h]] = n_inner++; q.push_back(nd.left); q.push_back(nd.right); }
         }
     }
-    auto leaf_code = [&](const BuildNode& nd) -> int32_t {
+    auto leaf_code = [&](int32_t id) -> int32_t {
+        const BuildNode& nd = br.nodes[id];
         int32_t cnt = nd.count < 1 ? 1 : nd.count;
-        return ~((nd.first << 3) | (cnt - 1));
+        return ~((leaf_pos[id] << 3) | (cnt - 1));
     };
     auto put_box = [](GpuNode& g, int child, const Aabb& b) {
         // widen by one ulp-ish step so float rounding in the slab test can never cull a true hit
@@ -209,21 +340,8 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
         put_box(g, 0, br.nodes[0].box);
         Aabb e; for (int a = 0; a < 3; a++) { e.lo[a] = 3.0e38f; e.hi[a] = -3.0e38f; }
         g.v[4] = e.lo[0]; g.v[5] = e.hi[0]; g.v[6] = e.lo[1]; g.v[7] = e.hi[1]; g.v[10] = e.lo[2]; g.v[11] = e.hi[2];
-        g.c[0] = leaf_code(br.nodes[0]); g.c[1] = g.c[0];
+        g.c[0] = leaf_code(0); g.c[1] = g.c[0];
         out.depth = 1;
-        out.nodes4.resize(1);
-        GpuNode4& g4 = out.nodes4[0];
-        std::memset(&g4, 0, sizeof(g4));
-        for (int k = 0; k < 4; k++) {
-            for (int a = 0; a < 6; a++) g4.v[a * 4 + k] = 1.0e30f;
-            g4.c[k] = -1;
-        }
-        for (int a = 0; a < 3; a++) {
-            g4.v[(2 * a) * 4] = std::nextafterf(br.nodes[0].box.lo[a], -3.0e38f);
-            g4.v[(2 * a + 1) * 4] = std::nextafterf(br.nodes[0].box.hi[a], 3.0e38f);
-        }
-        g4.c[0] = leaf_code(br.nodes[0]);
-        out.depth4 = 1;
         return;
     }
     out.nodes.resize((size_t)n_inner);
@@ -240,69 +358,12 @@ void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t
         const BuildNode& l = br.nodes[nd.left];
         const BuildNode& r = br.nodes[nd.right];
         put_box(g, 0, l.box); put_box(g, 1, r.box);
-        g.c[0] = l.left >= 0 ? inner_index[nd.left] : leaf_code(l);
-        g.c[1] = r.left >= 0 ? inner_index[nd.right] : leaf_code(r);
+        g.c[0] = l.left >= 0 ? inner_index[nd.left] : leaf_code(nd.left);
+        g.c[1] = r.left >= 0 ? inner_index[nd.right] : leaf_code(nd.right);
         g.c[2] = nd.axis;
         st.push_back({nd.left, it.depth + 1}); st.push_back({nd.right, it.depth + 1});
     }
     out.depth = max_depth + 1;
-
-    // ---- 4-wide collapse: a node adopts its grandchildren in place of the inner child with the largest surface area
-    // until it has four children (or only leaves are left).  Same leaves, same primitive order.
-    {
-        struct Wide { int32_t child[4]; int n; };                 // binary node ids
-        std::vector<int32_t> wide_index(br.nodes.size(), -1);     // binary node id -> 4-wide node index (for collapsed roots)
-        std::vector<Wide> wides;
-        std::vector<int32_t> order;                               // binary ids of the wide nodes' roots, BFS
-        order.push_back(0);
-        wide_index[0] = 0;
-        for (size_t hd = 0; hd < order.size(); hd++) {
-            const BuildNode& nd = br.nodes[order[hd]];
-            Wide w; w.n = 0;
-            w.child[w.n++] = nd.left; w.child[w.n++] = nd.right;
-            while (w.n < 4) {
-                int best = -1; float best_area = -1.f;
-                for (int k = 0; k < w.n; k++) {
-                    const BuildNode& c = br.nodes[w.child[k]];
-                    if (c.left >= 0 && c.box.half_area() > best_area) { best_area = c.box.half_area(); best = k; }
-                }
-                if (best < 0) break;
-                const BuildNode& c = br.nodes[w.child[best]];
-                w.child[best] = c.left;
-                w.child[w.n++] = c.right;
-            }
-            for (int k = 0; k < w.n; k++)
-                if (br.nodes[w.child[k]].left >= 0) { wide_index[w.child[k]] = (int32_t)order.size(); order.push_back(w.child[k]); }
-            wides.push_back(w);
-        }
-        out.nodes4.resize(wides.size());
-        std::vector<int32_t> depth_of(wides.size(), 1);
-        int32_t max_depth4 = 1;
-        for (size_t i = 0; i < wides.size(); i++) {
-            GpuNode4& g = out.nodes4[i];
-            std::memset(&g, 0, sizeof(g));
-            for (int k = 0; k < 4; k++) {
-                if (k < wides[i].n) {
-                    const BuildNode& c = br.nodes[wides[i].child[k]];
-                    for (int a = 0; a < 3; a++) {
-                        g.v[(2 * a) * 4 + k] = std::nextafterf(c.box.lo[a], -3.0e38f);
-                        g.v[(2 * a + 1) * 4 + k] = std::nextafterf(c.box.hi[a], 3.0e38f);
-                    }
-                    if (c.left >= 0) {
-                        g.c[k] = wide_index[wides[i].child[k]];
-                        depth_of[g.c[k]] = depth_of[i] + 1;
-                        max_depth4 = std::max(max_depth4, depth_of[g.c[k]]);
-                    } else {
-                        g.c[k] = leaf_code(c);
-                    }
-                } else {
-                    for (int a = 0; a < 6; a++) g.v[a * 4 + k] = 1.0e30f;        // point box far away: never hit
-                    g.c[k] = -1;
-                }
-            }
-        }
-        out.depth4 = max_depth4 + 1;
-    }
 }
 
 void to_reference_layout(const BuildResult& br, const int32_t* prim_obj, const float* world_min, const float* world_max,

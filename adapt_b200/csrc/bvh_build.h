@@ -57,20 +57,29 @@ struct alignas(16) GpuNode { float v[12]; int32_t c[4]; };
 //   sphere: t0 = (center.xyz, radius)
 struct alignas(16) GpuPrim { float v[12]; };
 
-// ---- 4-wide layout collapsed from the binary tree: 128-byte nodes, child boxes as structure-of-arrays -------------
-// q0 = lo.x of children 0..3, q1 = hi.x, q2 = lo.y, q3 = hi.y, q4 = lo.z, q5 = hi.z, q6 = child codes (same encoding as the
-// binary layout), q7 = unused.  An unused child slot holds a far-away point box that no ray hits.
-struct alignas(16) GpuNode4 { float v[24]; int32_t c[4]; int32_t pad[4]; };
+// ---- compressed 8-wide layout collapsed from the binary tree (Ylitie, Karras, Laine 2017): 80-byte nodes ------------------------------
+// q0 = (p.x, p.y, p.z, e.x | e.y << 8 | e.z << 16 | imask << 24)   grid origin, biased power-of-two exponent per axis (2^(e-127) per
+//                                                                   grid step), bit s of imask: slot s holds an inner node
+// q1 = (child_base, prim_base, meta[0..3], meta[4..7])              index of the first inner child (the others follow in slot order), of the
+//                                                                   first primitive record; meta per slot: 0 empty; inner 0b001 << 5 | 24 + s;
+//                                                                   leaf (unary primitive count) << 5 | offset of its first primitive from prim_base
+// q2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])         8-bit child boxes on the node's grid, lower planes rounded down and upper
+// q3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])         planes rounded up with 1/64 grid step of margin
+// q4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
+// Slot s holds the child whose centre lies towards the corner (s & 1 ? +x : -x, s & 2 ? +y : -y, s & 4 ? +z : -z) of the node, so a ray
+// visits the slots in descending order of s ^ (its direction's sign bits).  A leaf child holds at most 3 primitives, the leaf children of
+// one node at most 24, stored back to back from prim_base (the primitive records are emitted node by node).
+struct alignas(16) GpuNode8 { uint32_t q[20]; };
 
 struct GpuBvh {
     std::vector<GpuNode> nodes;
-    std::vector<GpuNode4> nodes4;
-    std::vector<GpuPrim> prims;   // leaf order
+    std::vector<GpuNode8> nodes8; // only with `eight` (needs leaves of at most 3 primitives)
+    std::vector<GpuPrim> prims;   // leaf order (with `eight`: node by node of the 8-wide tree; the binary leaves point into the same array)
     int32_t depth = 0;            // binary tree
-    int32_t depth4 = 0;           // 4-wide tree
+    int32_t depth8 = 0;           // 8-wide tree
 };
 void to_gpu_layout(const BuildResult& br, const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj,
-                   const uint8_t* obj_class, GpuBvh& out);
+                   const uint8_t* obj_class, GpuBvh& out, bool eight = false);
 
 // ---- reference layout (tracer/bvh/bvh.cpp:215-251): DFS order with sub-tree skip offsets --------
 struct RefLayout {

@@ -100,7 +100,7 @@ PT_HD int floor_mod(int32_t a, int32_t n) { int r = a % n; return r < 0 ? r + n 
 struct SceneView {
     // BVH (bvh_build.h layouts)
     const float4* nodes;        // 4 x float4 per node
-    const float4* nodes4;       // 8 x float4 per node of the 4-wide tree (bvh_build.h: GpuNode4)
+    const uint4* nodes8;        // 5 x uint4 per node of the compressed 8-wide tree (bvh_build.h: GpuNode8), NULL when not built
     const float4* leaf_prims;   // 3 x float4 per primitive, leaf order
     // primitives in original order
     const float4* prim_geom;    // 3 x float4: (v0, e1.x) (e1.yz, e2.xy) (e2.z, -, -, -); sphere: (center, r)

@@ -26,11 +26,21 @@ using namespace adapt;
 #ifndef LOGIC_MIN_BLOCKS_SIMPLE
 #define LOGIC_MIN_BLOCKS_SIMPLE 4
 #endif
+// 1: the non-listed k_logic stages its slot tile in shared memory with bulk copies (TMA path, see k_logic).  Measured and left off
+// (sessions r02d / r02e, bunny90k): k_logic 17.3 -> 18.5 ms/step -- the 23 KB of shared memory per block come out of L1, every warp waits
+// for the whole tile instead of its own 128-byte lines, and the loads were never short of bytes in flight (the kernel issues all six
+// per-slot loads back to back already).
+#ifndef LOGIC_BULK_TILE
+#define LOGIC_BULK_TILE 0
+#endif
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 9
+#endif
+#ifndef TRACE_MIN_BLOCKS8
+#define TRACE_MIN_BLOCKS8 8
 #endif
 // sort keys of k_logic's block-local regrouping: material classes 0..10 (BRDF type 0..7, BSDF det-refraction 8, BSDF
 // Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot
@@ -86,6 +96,51 @@ __device__ __forceinline__ bool ray_hits_box(float3 o, float3 d, float3 lo, floa
     float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), PT_T_INF));
     return tmin <= tmax * 1.00001f;
 }
+
+// ================================================================================================
+// Bulk copies global -> shared memory (cp.async.bulk, the 1-D form of the TMA path: SASS UBLKCP; completion on an mbarrier, no tensor
+// map needed).  Thread 0 of the block issues them; bytes must be multiples of 16, addresses 16-byte aligned.
+// ================================================================================================
+struct BulkLoad {
+    unsigned bar_a;
+    // every thread of the block; `bar` is a shared-memory word used for nothing else
+    __device__ __forceinline__ void init(unsigned long long* bar) {
+#if defined(__CUDA_ARCH__)
+        bar_a = (unsigned)__cvta_generic_to_shared(bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+#else
+        bar_a = 0;
+#endif
+    }
+    // thread 0 only: announce the byte total, then one copy() per piece
+    __device__ __forceinline__ void expect(const unsigned total_bytes) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total_bytes) : "memory");
+#endif
+    }
+    __device__ __forceinline__ void copy(void* smem_dst, const void* gmem_src, const unsigned bytes) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(bar_a) : "memory");
+#else
+        memcpy(smem_dst, gmem_src, bytes);          // SIMT emulator (tests/dev_host): thread 0 runs first up to the next collective
+#endif
+    }
+    // every thread: returns once all announced bytes have landed
+    __device__ __forceinline__ void wait() const {
+#if defined(__CUDA_ARCH__)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_a) : "memory");
+#else
+        __syncthreads();
+#endif
+    }
+};
 
 // ================================================================================================
 // k_classify: global per-class slot lists (scenes with several material groups)
@@ -182,7 +237,30 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         if (!__any_sync(0xffffffffu, slot >= 0)) return;              // past the end of the lists
     }
     const bool listed_idle = LISTED && slot < 0;                      // only in the last warp of a listed launch
+#if LOGIC_BULK_TILE
+    // Thread t owns slot t (not listed): the block's 256-slot tile of the pool -- six contiguous pieces, 22 KB -- comes in with six bulk
+    // copies (TMA path) issued by one thread the moment the block starts, so the whole tile is in flight at once and costs no registers
+    // while it travels; before, every thread read its misc word, waited, and only then issued the other five loads (two dependent HBM
+    // round trips per slot).
+    alignas(128) __shared__ uint4 s_misc[LISTED ? 1 : LOGIC_BLOCK];
+    alignas(128) __shared__ float4 s_hit[LISTED ? 1 : LOGIC_BLOCK], s_ro[LISTED ? 1 : LOGIC_BLOCK], s_rd[LISTED ? 1 : LOGIC_BLOCK], s_thr[LISTED ? 1 : LOGIC_BLOCK];
+    alignas(128) __shared__ uint2 s_rng[LISTED ? 1 : LOGIC_BLOCK];
+    alignas(8) __shared__ unsigned long long s_bar;
+    if (!LISTED) {
+        BulkLoad bl; bl.init(&s_bar);
+        if (threadIdx.x == 0) {
+            const size_t b0 = (size_t)blockIdx.x * LOGIC_BLOCK;
+            bl.expect(LOGIC_BLOCK * (16u * 5u + 8u));
+            bl.copy(s_misc, pool.misc + b0, LOGIC_BLOCK * 16u); bl.copy(s_hit, pool.hit + b0, LOGIC_BLOCK * 16u);
+            bl.copy(s_ro, pool.ray_o + b0, LOGIC_BLOCK * 16u); bl.copy(s_rd, pool.ray_d + b0, LOGIC_BLOCK * 16u);
+            bl.copy(s_thr, pool.thr + b0, LOGIC_BLOCK * 16u); bl.copy(s_rng, pool.rng + b0, LOGIC_BLOCK * 8u);
+        }
+        bl.wait();
+    }
+    uint4 misc = listed_idle ? make_uint4(0u, 0u, 0u, 0u) : (LISTED ? pool.misc[slot] : s_misc[threadIdx.x]);
+#else
     uint4 misc = listed_idle ? make_uint4(0u, 0u, 0u, 0u) : pool.misc[slot];
+#endif
     bool alive = (misc.z & SLOT_ALIVE) != 0;
     // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
     if (!__any_sync(0xffffffffu, alive)) {
@@ -208,9 +286,16 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 
     if (alive) {
         // all per-slot state in one batch of independent 128-bit loads (one memory round trip)
+#if LOGIC_BULK_TILE
+        const float4 h4 = LISTED ? pool.hit[slot] : s_hit[threadIdx.x];
+        const float4 o4 = LISTED ? pool.ray_o[slot] : s_ro[threadIdx.x], d4 = LISTED ? pool.ray_d[slot] : s_rd[threadIdx.x];
+        const float4 t4 = LISTED ? pool.thr[slot] : s_thr[threadIdx.x];
+        const uint2 r2 = LISTED ? pool.rng[slot] : s_rng[threadIdx.x];
+#else
         const float4 h4 = pool.hit[slot];
         const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
         const uint2 r2 = pool.rng[slot];
+#endif
         bounce = (int)(misc.z & 0xffffu);
         const int hit_word = __float_as_int(h4.w);
         const int prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
@@ -615,7 +700,8 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
 // k_closest / k_shadow: persistent warps over the ray streams.
 //   MODE 0: a warp takes 32 rays and waits for the slowest (baseline, kept for A/B measurements and node counting)
 //   MODE 1: per-lane refill + vote-scheduled traversal of the binary BVH (pt_trace.cuh: trace_stream_vote)
-//   MODE 2: the same over the 4-wide BVH collapsed from it
+//   MODE 3: the same scheduler over the compressed 8-wide BVH collapsed from it (pt_trace.cuh: trace_stream_cw8)
+//   (MODE 2 was an uncompressed 4-wide tree: measured equal on orb500k and 6 % slower on bunny90k in round 1, removed)
 // ================================================================================================
 struct ClosestSource {
     PathPool pool;
@@ -684,7 +770,8 @@ k_closest(const SceneView sv, const PathPool pool, DeviceCounters* __restrict__ 
           const int refill, const int leaf_t) {
     unsigned traced = 0, nn = 0, np = 0;
     ClosestSource src{pool};
-    if (MODE >= 1) trace_stream_vote<false, COUNT, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+    if (MODE == 3) trace_stream_cw8<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+    else if (MODE >= 1) trace_stream_vote<false, COUNT>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
     else trace_stream_simple<false, COUNT>(sv, src, cur->closest, traced, nn, np);
     block_count(traced, &ctr->rays_closest);
     if (COUNT) { block_count(nn, &ctr->nodes_visited); block_count(np, &ctr->prims_tested); }
@@ -696,7 +783,8 @@ k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCo
          const int refill, const int leaf_t, const int parity) {
     unsigned traced = 0, nn = 0, np = 0;
     ShadowSource src{pool, sq, parity};
-    if (MODE >= 1) trace_stream_vote<true, false, MODE == 2>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    if (MODE == 3) trace_stream_cw8<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    else if (MODE >= 1) trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
     else trace_stream_simple<true, false>(sv, src, cur->shadow, traced, nn, np);
     block_count(traced, &ctr->rays_shadow);
 }
@@ -706,19 +794,36 @@ k_shadow(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCo
 // waiting for the last long rays) overlaps useful work and one launch per iteration disappears.  The two streams are
 // independent: shadow results are RED-added to pool.col, closest hits are written to pool.hit.
 template <int MODE>
-__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(TRACE_BLOCK, MODE == 3 ? TRACE_MIN_BLOCKS8 : TRACE_MIN_BLOCKS)
 k_trace(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, Cursors* __restrict__ cur,
-        const int refill, const int leaf_t, const int parity) {
+        const int refill, const int leaf_t, const int parity, const int n_nodes_total) {
     unsigned traced = 0, nn = 0, np = 0;
+    const float4* top = nullptr; int top_n = 0;
+#if TRACE_TOP_NODES > 0
+    // north-star item "BVH nodes staged through shared memory with TMA bulk loads": the nodes are stored breadth-first (bvh_build.cpp:
+    // to_gpu_layout), so the top levels are the first TRACE_TOP_NODES entries -- one bulk copy per persistent block.  Measured slower
+    // than leaving the top of the tree to L1 (pt_trace.cuh), hence compiled out by default.
+    alignas(128) __shared__ float4 s_top[TRACE_TOP_NODES * 4];
+    alignas(8) __shared__ unsigned long long s_bar;
+    if (MODE == 1) {
+        top_n = min(TRACE_TOP_NODES, n_nodes_total);
+        BulkLoad bl; bl.init(&s_bar);
+        if (threadIdx.x == 0) { bl.expect((unsigned)top_n * 64u); bl.copy(s_top, sv.nodes, (unsigned)top_n * 64u); }
+        bl.wait();
+        top = s_top;
+    }
+#endif
     {
         ShadowSource src{pool, sq, parity};
-        trace_stream_vote<true, false, MODE == 2>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        if (MODE == 3) trace_stream_cw8<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        else trace_stream_vote<true, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np, top, top_n);
         block_count(traced, &ctr->rays_shadow);
     }
     traced = 0;
     {
         ClosestSource src{pool};
-        trace_stream_vote<false, false, MODE == 2>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        if (MODE == 3) trace_stream_cw8<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        else trace_stream_vote<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np, top, top_n);
         block_count(traced, &ctr->rays_closest);
     }
 }
@@ -755,18 +860,21 @@ struct TransmitSource {
 namespace adapt { template <> struct source_rearms<TransmitSource> { static constexpr bool value = true; }; }
 
 // Both streams of one volumetric iteration in one launch, like k_trace: transmittance samples first, then the paths' own rays.
+template <int MODE>
 __global__ void __launch_bounds__(TRACE_BLOCK, 4)
 k_trace_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
             Cursors* __restrict__ cur, const int refill, const int leaf_t, const int parity) {
     unsigned traced = 0, nn = 0, np = 0;
     {
         TransmitSource src{sv, vv, pool, sq, parity};
-        trace_stream_vote<false, false, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        if (MODE == 3) trace_stream_cw8<false, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+        else trace_stream_vote<false, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
     }
     traced = 0;
     {
         ClosestSource src{pool};
-        trace_stream_vote<false, false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        if (MODE == 3) trace_stream_cw8<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
+        else trace_stream_vote<false, false>(sv, src, cur->closest, refill, leaf_t, traced, nn, np);
         block_count(traced, &ctr->rays_closest);
     }
 }

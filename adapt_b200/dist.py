@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["tile_partition", "dist_env", "init_process_group", "reduce_framebuffer", "device_tensor_view"]
+__all__ = ["tile_partition", "auto_tile", "dist_env", "init_process_group", "reduce_framebuffer", "device_tensor_view"]
 
 
 def tile_partition(w: int, h: int, rank: int, world: int, tile: int = 32,
@@ -41,6 +41,14 @@ def tile_partition(w: int, h: int, rank: int, world: int, tile: int = 32,
     if not out:
         return np.zeros((0,), np.int32)
     return np.concatenate(out).astype(np.int32)
+
+
+def auto_tile(w: int, h: int, world: int, window: Optional[Tuple[int, int, int, int]] = None, tile: int = 32) -> int:
+    """Largest tile edge <= ``tile`` (halving down to 4) that leaves every rank at least one tile of the film / crop window."""
+    sx, ex, sy, ey = window if window is not None else (0, w, 0, h)
+    while tile > 4 and (-(-(ex - sx) // tile)) * (-(-(ey - sy) // tile)) < world:
+        tile //= 2
+    return tile
 
 
 def dist_env():

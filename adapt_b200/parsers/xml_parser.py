@@ -205,7 +205,9 @@ def scene_parsing(directory: str, file: str):
     volume_node = root_node.findall("volume")
     assert sensor_node is not None
     teximgs, textures = parse_texture(texture_nodes, directory)
-    # the reference flips microfacet support with a source-level flag (bxdf/brdf.py:8); here a sensor key
+    # the reference flips microfacet support with a source-level flag (bxdf/brdf.py:8); here a sensor key, default off like the
+    # reference's, and reset for every scene so that one scene's setting never leaks into the next one parsed by this process
+    _brdf_mod.set_enable_microfacet(False)
     for elem in sensor_node:
         if elem.tag == "boolean" and elem.get("name") == "enable_microfacet":
             _brdf_mod.set_enable_microfacet(elem.get("value", "false").lower() == "true")

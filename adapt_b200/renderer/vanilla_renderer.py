@@ -195,6 +195,7 @@ class Renderer:
         check(self._lib, self._lib.adapt_get_stats(self._handle, C.byref(st)), "adapt_get_stats")
         out = st.as_dict()
         out["rays_culled"], out["fused_trace"], out["pool_slots"] = int(st.reserved[0]), bool(st.reserved[1]), int(st.reserved[2])
+        out["lanes"] = max(1, int(st.reserved[3]))
         if reset:
             check(self._lib, self._lib.adapt_reset_stats(self._handle), "adapt_reset_stats")
         return out
@@ -233,8 +234,10 @@ class Renderer:
         check(self._lib, self._lib.adapt_update_geometry(self._handle, pr.ctypes.data_as(fp), ng.ctypes.data_as(fp),
                                                          None if ns is None else ns.ctypes.data_as(fp)), "adapt_update_geometry")
 
-    def reset_accumulation(self):
-        self._load_accum(np.zeros((self.w, self.h, 3), np.float32), 0)
+    def reset_accumulation(self, spp: int = 0):
+        """Empty film (cleared on the device); the next sample rendered is number ``spp + 1``."""
+        check(self._lib, self._lib.adapt_load_accum(self._handle, None, int(spp)), "adapt_load_accum")
+        self._cnt = int(spp)
 
     def bvh_export(self, arrays: bool = True) -> dict:
         """Stage-level hook: the device acceleration structure (64-byte nodes, 48-byte leaf records), its builder and build time."""

@@ -133,7 +133,7 @@ typedef struct {
     uint64_t prims_tested;
     uint64_t reserved[4];       /* [0]: camera rays answered by the scene-box test (included in rays_closest);
                                    [1]: 1 when both ray streams run in one fused launch (all trace time is booked under ms_closest);
-                                   [2]: path-pool slots */
+                                   [2]: path-pool slots (all lanes); [3]: lanes (pools running side by side on their own streams) */
 } adapt_stats;
 
 typedef struct adapt_handle adapt_handle;
@@ -150,7 +150,7 @@ int adapt_sync(adapt_handle* h);
 /* Framebuffer: `color` sum in the reference layout (w,h,3) indexed [i=x][j=y], and the sample
  * counter `cnt` (tracer/path_tracer.py:81, tracer_base.py:102). */
 int adapt_read_accum(adapt_handle* h, float* dst_whc, int32_t* spp);
-int adapt_load_accum(adapt_handle* h, const float* src_whc, int32_t spp);   /* checkpoint resume */
+int adapt_load_accum(adapt_handle* h, const float* src_whc, int32_t spp);   /* checkpoint resume; src_whc == NULL: empty film, cleared on the device */
 /* `pixels.to_numpy()` of the reference (tracer_base.py:85, vanilla_renderer.py:120): the running mean color / cnt, divided on
  * the device, then copied to dst_whc. */
 int adapt_read_pixels(adapt_handle* h, float* dst_whc, int32_t* spp);
@@ -180,8 +180,9 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
  * n_s [n_prims*9] (required iff the scene was created with vertex normals) as in adapt_scene_desc.  Waits for enqueued work,
  * replaces the per-primitive tables of load_primitives (tracer/tracer_base.py:117-134) and rebuilds the acceleration structure
  * with the handle's builder (bvh_process, tracer/path_tracer.py:143-179; with bvh_builder = 1 entirely on the device).  The
- * reference has no counterpart: it re-creates the renderer.  Emitter descriptors (inv_area of mesh lights) and the accumulation
- * buffer are left as they are -- reset the latter with adapt_load_accum when the image should start over. */
+ * reference has no counterpart: it re-creates the renderer.  inv_area of area emitters is recomputed from the new vertices of the
+ * object they are attached to; the accumulation buffer is left as it is -- reset it with adapt_load_accum(h, NULL, 0) when the image
+ * should start over.  On failure the handle keeps its previous acceleration structure. */
 int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s);
 
 /* Stage-level hook for the acceleration structure that replaces LinearBVH / LinearNode (tracer/ti_bvh.py:10-53) on the device:

@@ -47,10 +47,20 @@ def main(argv=None):
     emitter_configs, array_info, all_objs, configs = scene_parsing(input_folder, opts.name)
     output_folder = folder_path(opts.output_path)
     # multi-GPU: one process per GPU (torchrun); each rank owns interleaved film tiles
-    from adapt_b200.dist import device_tensor_view, init_process_group, reduce_framebuffer, tile_partition
+    from adapt_b200.dist import auto_tile, device_tensor_view, init_process_group, reduce_framebuffer, tile_partition
     rank, local_rank, world = init_process_group() if int(os.environ.get("WORLD_SIZE", "1")) > 1 else (0, 0, 1)
     film = configs["film"]
-    pixel_list = tile_partition(film["width"], film["height"], rank, world) if world > 1 else None
+    pixel_list = None
+    if world > 1:
+        # the ranks split the crop window when the film has one (tracer_base.py:64-75), not the whole film
+        w, h = film["width"], film["height"]
+        window = None
+        if film.get("crop_rx", 0) > 0 and film.get("crop_ry", 0) > 0:
+            cx, cy, rx, ry = film.get("crop_x", 0), film.get("crop_y", 0), film["crop_rx"], film["crop_ry"]
+            window = (max(0, cx - rx), min(w, cx + rx), max(0, cy - ry), min(h, cy + ry))
+        pixel_list = tile_partition(w, h, rank, world, tile=auto_tile(w, h, world, window), window=window)
+        if (opts.save_iter > 0 or opts.output_freq > 0) and rank == 0:
+            CONSOLE.log("[yellow]--save_iter / --output_freq are ignored under torchrun (the film is only assembled at the end)")
     rdr = rdr_mapping[opts.type](emitter_configs, array_info, all_objs, configs, seed=opts.seed, device_id=local_rank,
                                  pixel_list=pixel_list, max_bounce=opts.max_bounce)
     max_iter_num = opts.iter_num if opts.iter_num > 0 else configs.get("iter_num", 2000)

@@ -34,12 +34,15 @@ def build_wavefront(force: bool = False) -> str:
     """The kernels themselves (pt_kernels.cuh) as host C++ under the SIMT emulator (simt_emu.h); C++20 for nothing but designated habits of
     the headers, -O2 because the emulated kernels are the hot loop of these tests."""
     deps = WF_DEPS + DEPS[3:]
-    if not force and os.path.exists(WF_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(WF_LIB) for d in deps):
-        return WF_LIB
-    os.makedirs(os.path.dirname(WF_LIB), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++20", "-w", "-fPIC", "-ffp-contract=fast", "-march=x86-64-v3", "-I" + CUDA_INC,
-                           "-shared", "-o", WF_LIB, WF_SRC, os.path.join(_CSRC, "bvh_build.cpp")])
-    return WF_LIB
+    # DEV_HOST_CXXFLAGS="-DTRACE_LEAF_ONE=1 ...": a compile-time variant of the kernels (own library file per flag set)
+    extra = os.environ.get("DEV_HOST_CXXFLAGS", "").split()
+    lib = WF_LIB if not extra else WF_LIB[:-3] + "_" + "".join(c if c.isalnum() else "_" for c in "".join(extra)) + ".so"
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++20", "-w", "-fPIC", "-ffp-contract=fast", "-march=x86-64-v3", "-I" + CUDA_INC] + extra +
+                          ["-shared", "-o", lib, WF_SRC, os.path.join(_CSRC, "bvh_build.cpp")])
+    return lib
 
 
 _wf = None

@@ -43,7 +43,7 @@ inline DevHost* make_dev_scene(const adapt_scene_desc* d) {
     h->emitters.assign(d->emitters, d->emitters + d->n_emitters);
     SceneView& sv = h->sv;
     sv.nodes = reinterpret_cast<const float4*>(h->bvh.nodes.data());
-    sv.nodes4 = nullptr;
+    sv.nodes8 = nullptr;
     sv.leaf_prims = reinterpret_cast<const float4*>(h->bvh.prims.data());
     sv.prim_geom = h->prim_geom.data(); sv.prim_shade = h->prim_shade.data();
     sv.bxdfs = h->bxdfs.data(); sv.emitters = h->emitters.data(); sv.obj_info = h->obj_info.data();

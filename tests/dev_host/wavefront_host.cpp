@@ -45,7 +45,8 @@ void launch_iteration(Wavefront& w) {
         else
             simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
                 w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
-        simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
+        if (w.trace_mode == 3) simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt<3>(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
+        else simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt<1>(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
         w.iterations++; w.launches += 2;
         return;
     }
@@ -71,8 +72,8 @@ void launch_iteration(Wavefront& w) {
     }
 #undef LAUNCH_LOGIC_V
 #undef LAUNCH_LOGIC_X
-    if (w.trace_mode == 2) simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<2>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
-    else simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<1>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
+    if (w.trace_mode == 3) simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<3>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity, (int)w.scene->bvh.nodes.size()); });
+    else simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace<1>(sv, w.pool, w.sq, ctr, cur, w.refill, lt, parity, (int)w.scene->bvh.nodes.size()); });
     w.iterations++; w.launches++;
 }
 
@@ -106,7 +107,7 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     if (const char* v = getenv("ADAPT_REFILL")) w.refill = std::min(32, std::max(1, atoi(v)));
     if (const char* v = getenv("ADAPT_LEAF_T")) w.leaf_t = std::min(32, std::max(1, atoi(v)));
     if (const char* v = getenv("ADAPT_NODE_STEPS")) w.node_steps = std::min(8, std::max(1, atoi(v)));
-    if (const char* v = getenv("ADAPT_TRACE_MODE")) w.trace_mode = atoi(v) == 2 ? 2 : 1;       // 2: the 4-wide tree (pt_trace.cuh: wide_step)
+    if (const char* v = getenv("ADAPT_TRACE_MODE")) w.trace_mode = atoi(v) == 3 ? 3 : 1;       // 3: the compressed 8-wide tree (pt_trace.cuh: trace_stream_cw8)
     // the material class travels in the leaf records: rebuild them with the real classes (make_dev_scene passes zeros)
     {
         std::vector<uint8_t> sph((size_t)d->n_prims, 0), obj_class((size_t)no, 0);
@@ -117,11 +118,12 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
             for (int k = d->obj_info[o * 3]; k < d->obj_info[o * 3] + d->obj_info[o * 3 + 1]; k++) { prim_obj[k] = o; sph[k] = d->obj_info[o * 3 + 2] != 0; }
         }
         BuildParams bp; BuildResult br;
+        if (w.trace_mode == 3) bp.max_leaf = 3;                      // adapt_abi.cu::build_accel
         build_bvh(d->primitives, sph.data(), d->n_prims, bp, br);
-        to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), obj_class.data(), w.scene->bvh);
+        to_gpu_layout(br, d->primitives, sph.data(), prim_obj.data(), obj_class.data(), w.scene->bvh, w.trace_mode == 3);
         w.scene->sv.nodes = reinterpret_cast<const float4*>(w.scene->bvh.nodes.data());
         w.scene->sv.leaf_prims = reinterpret_cast<const float4*>(w.scene->bvh.prims.data());
-        w.scene->sv.nodes4 = reinterpret_cast<const float4*>(w.scene->bvh.nodes4.data());
+        w.scene->sv.nodes8 = w.trace_mode == 3 ? reinterpret_cast<const uint4*>(w.scene->bvh.nodes8.data()) : nullptr;
     }
     // pixels owned by this handle: the tile partition's list, or the film / crop window in 4x8 patches (adapt_create)
     if (d->pixel_list && d->n_pixels > 0) w.pixels.assign(d->pixel_list, d->pixel_list + d->n_pixels);

@@ -67,9 +67,11 @@ def test_shared_rng_parity(Renderer, scene_root, scene, name, seed):
     match, flipped = _flip_stats(img, ref)
     assert flipped < 0.05                                       # a few % of pixels contain a flipped sample at most
     assert rel_l2(img[match], ref[match]) < 1e-4                # everything else agrees to fp rounding
-    # whole-image relative L2 (north_star tolerance); allbxdf has a directly visible sphere light whose
-    # NEE rays are exactly the chaotic case above, so single flips there carry emitter-sized radiance
-    assert rel_l2(img, ref) < (TOL if scene != "test" else 3e-2)
+    # whole-image relative L2 (north_star tolerance).  allbxdf has a directly visible sphere light whose NEE rays are exactly the chaotic
+    # case above, so at 16 spp single flips carry emitter-sized radiance: its whole-image figure is asserted at convergence
+    # (tests/test_gpu_baseline_configs.py::test_allbxdf_converged_whole_image)
+    if scene != "test":
+        assert rel_l2(img, ref) < TOL
     assert st["paths"] == cn["paths"] == size * size * spp
     # closest-hit rays: the GPU skips the reference's unused trace after the last bounce
     assert abs(st["rays_closest"] - cn["rays_closest_useful"]) <= 2e-3 * cn["rays_closest_useful"]

@@ -185,3 +185,29 @@ def test_texture_errors(scene_root, tmp_path):
                                    .replace('<ref type="texture" id="paint2" tag="albedo"/>', '<ref type="texture" id="chk" tag="albedo"/>', 1))
     with pytest.raises(NotImplementedError):
         scene_parsing(str(d), "checker.xml")
+
+
+def test_microfacet_flag_does_not_leak_between_scenes(scene_root):
+    """The reference compiles GGX out unless its source flag is flipped (bxdf/brdf.py:8); here a sensor key of the scene switches it on,
+    and the next scene parsed by the same process starts from the reference's default (off) again."""
+    from adapt_b200.bxdf import brdf
+    load_scene(scene_root, "test", "allbxdf.xml", 8, 8)            # <boolean name="enable_microfacet" value="true"/>
+    assert brdf.microfacet_enabled()
+    load_scene(scene_root, "cbox", "cbox.xml", 8, 8)
+    assert not brdf.microfacet_enabled()
+
+
+def test_every_rank_owns_a_tile_and_empty_lists_are_refused(scene_root):
+    """A 64 x 64 film has four 32 x 32 tiles: eight ranks need a smaller tile (auto_tile), and a handle must never be created from an
+    empty pixel list (n_pixels = 0 means `whole film` to adapt_create: the reduce would count those pixels once per rank)."""
+    from adapt_b200._lib import pack_scene
+    from adapt_b200.dist import auto_tile, tile_partition
+    assert tile_partition(64, 64, 5, 8).size == 0
+    t = auto_tile(64, 64, 8)
+    assert t == 16
+    parts = [tile_partition(64, 64, r, 8, tile=t) for r in range(8)]
+    assert all(p.size > 0 for p in parts) and np.array_equal(np.sort(np.concatenate(parts)), np.arange(64 * 64))
+    assert auto_tile(1920, 1080, 8) == 32 and auto_tile(640, 480, 2, window=(100, 120, 100, 120)) == 16
+    e, a, o, c = load_scene(scene_root, "cbox", "cbox.xml", 64, 64)
+    with pytest.raises(ValueError):
+        pack_scene(e, a, o, c, pixel_list=tile_partition(64, 64, 5, 8))

@@ -159,3 +159,33 @@ def test_emulated_kernels_over_integrator_flags(scene_root, oracle_lib, scene, n
         assert flipped <= 0.08, kw
         if match.any() and np.abs(ref[match]).sum() > 0:
             assert rel_l2(img[match], ref[match]) < 5e-5, kw
+
+
+# ---------------------------------------------------------------------------------------------- compressed 8-wide BVH (ADAPT_TRACE_MODE=3)
+@pytest.mark.parametrize("scene,name,film,spp,pool,max_flipped", [
+    ("cbox", "cbox.xml", (16, 16), 2, 256, 0.0),
+    ("csphere", "balls-mono.xml", (16, 16), 2, 256, 0.01),       # spheres and triangles in the same leaves
+    ("test", "allbxdf.xml", (16, 16), 2, 512, 0.05),
+    ("cbox", "bunny90k.xml", (10, 10), 1, 256, 0.02),            # 89 900 primitives: seven levels of 8-wide nodes
+])
+def test_emulated_wavefront_over_the_8_wide_tree(scene_root, oracle_lib, monkeypatch, scene, name, film, spp, pool, max_flipped):
+    """k_trace<3>: trace_stream_cw8 over the 80-byte quantised nodes collapsed from the binary tree (bvh_build.cpp: to_gpu_layout with
+    `eight`) -- same rays, ray for ray, and the same film as the oracle's brute-force / skip-pointer intersectors."""
+    if name == "bunny90k.xml":
+        from adapt_b200.scenes import ensure_big_meshes
+        ensure_big_meshes(scene_root, ("bunny90k",))
+    monkeypatch.setenv("ADAPT_TRACE_MODE", "3")
+    img, st, ref, cn = _run(scene_root, scene, name, film[0], film[1], spp, pool)
+    assert st["paths"] == cn["paths"] == film[0] * film[1] * spp
+    assert st["rays_closest"] == cn["rays_closest_useful"]
+    match, flipped = _flip(img, ref)
+    assert flipped <= max_flipped
+    assert rel_l2(img[match], ref[match]) < 2e-5
+
+
+def test_8_wide_tree_volumetric_streams(scene_root, oracle_lib, monkeypatch):
+    """k_trace_vpt<3>: the transmittance stream re-arms its lanes segment by segment over the 8-wide tree too."""
+    monkeypatch.setenv("ADAPT_TRACE_MODE", "3")
+    img, st, ref, cn = _run(scene_root, "test", "media.xml", 12, 12, 2, 256, integrator="vpt")
+    match, flipped = _flip(img, ref)
+    assert st["paths"] == cn["paths"] and flipped <= 0.02 and rel_l2(img[match], ref[match]) < 2e-5

@@ -36,11 +36,11 @@ ps = pack_scene(e, a, o, c, seed=1)
 print(f"{scene}/{name} {size}x{size} x {spp} spp, {a['primitives'].shape[0]} primitives, pool 2048 slots, 2 trace blocks")
 print(f"{'refill':>6} {'leaf_t':>6} {'steps':>5} | {'node lanes/32':>13} {'leaf lanes/32':>13} {'prims/leaf lane':>15} {'rounds/ray':>10} {'node steps/ray':>14}")
 ref = None
-WIDE4 = "--wide4" in sys.argv                # ADAPT_TRACE_MODE=2: the 4-wide tree collapsed from the binary one
-if WIDE4:
-    print("tree: 4-wide (128-byte nodes, wide_step)")
+WIDE8 = "--cw8" in sys.argv                  # ADAPT_TRACE_MODE=3: the compressed 8-wide tree collapsed from the binary one
+if WIDE8:
+    print("tree: compressed 8-wide (80-byte nodes, cw8_step)")
 for refill, leaf_t, steps in [(16, 12, 1), (16, 12, 2), (16, 12, 4), (16, 8, 4), (16, 8, 8), (16, 4, 4), (16, 16, 4), (8, 8, 4), (24, 8, 4)]:
-    os.environ.update(ADAPT_REFILL=str(refill), ADAPT_LEAF_T=str(leaf_t), ADAPT_NODE_STEPS=str(steps), ADAPT_TRACE_MODE="2" if WIDE4 else "1")
+    os.environ.update(ADAPT_REFILL=str(refill), ADAPT_LEAF_T=str(leaf_t), ADAPT_NODE_STEPS=str(steps), ADAPT_TRACE_MODE="3" if WIDE8 else "1")
     L = C.CDLL(lib_path)
     L.wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     acc = np.zeros((size, size, 3), np.float32); st = np.zeros(5, np.uint64); ts = np.zeros(8, np.uint64)
