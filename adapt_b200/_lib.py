@@ -95,6 +95,8 @@ class adapt_scene_desc(C.Structure):
         ("tex_size", C.c_int32 * 3),
         ("integrator", C.c_int32),
         ("media", C.POINTER(adapt_medium)),
+        ("n_devices", C.c_int32),
+        ("device_ids", _ip),
     ]
 
 
@@ -113,11 +115,11 @@ class adapt_stats(C.Structure):
 
 # every symbol include/adapt_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "adapt_create", "adapt_destroy", "adapt_render", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
+    "adapt_create", "adapt_destroy", "adapt_render", "adapt_wait_enqueued", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
     "adapt_read_pixels", "adapt_host_alloc", "adapt_host_free",
     "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch", "adapt_bxdf_batch",
     "adapt_bvh_export", "adapt_update_geometry",
-    "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version",
+    "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version", "adapt_tile_partition",
 ]
 
 _lib = None
@@ -145,6 +147,10 @@ def load_library(path: Optional[str] = None):
     lib.adapt_sync.restype = C.c_int
     lib.adapt_read_accum.argtypes = [H, _fp, _ip]
     lib.adapt_read_accum.restype = C.c_int
+    lib.adapt_tile_partition.argtypes = [C.c_int32] * 5 + [_ip, _ip, C.c_int32]
+    lib.adapt_tile_partition.restype = C.c_int32
+    lib.adapt_wait_enqueued.argtypes = [H]
+    lib.adapt_wait_enqueued.restype = C.c_int
     lib.adapt_load_accum.argtypes = [H, _fp, C.c_int32]
     lib.adapt_load_accum.restype = C.c_int
     lib.adapt_read_pixels.argtypes = [H, _fp, _ip]
@@ -212,7 +218,7 @@ class PackedScene:
 
 def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed: int = 0, device_id: int = 0,
                pixel_list: Optional[np.ndarray] = None, pool_size: int = 0, max_bounce: Optional[int] = None,
-               bvh_builder=0, integrator="pt") -> PackedScene:
+               bvh_builder=0, integrator="pt", device_ids=None) -> PackedScene:
     ps = PackedScene()
     d = ps.desc
     film = prop["film"]
@@ -328,6 +334,19 @@ def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed
     # ---- back-end knobs ----
     d.seed = int(seed)
     d.device_id = int(device_id)
+    # several GPUs behind one handle: the library splits the film into interleaved tiles itself (include/adapt_b200.h: n_devices)
+    if device_ids is not None and len(device_ids) > 1:
+        if pixel_list is not None:
+            raise ValueError("device_ids and pixel_list are exclusive: a multi-device handle partitions the film itself")
+        ids = _i32(np.asarray(list(device_ids))).reshape(-1)
+        d.n_devices = ids.shape[0]
+        d.device_ids = ps._ptr("device_ids", ids, C.c_int32)
+        d.device_id = int(ids[0])
+    else:
+        d.n_devices = 0
+        d.device_ids = None
+        if device_ids is not None and len(device_ids) == 1:
+            d.device_id = int(device_ids[0])
     if pixel_list is not None:
         pl = _i32(pixel_list).reshape(-1)
         if pl.shape[0] == 0:

@@ -127,6 +127,13 @@ struct adapt_handle {
     std::vector<uint8_t> sph, obj_class;
     std::vector<int32_t> prim_obj;
     bool has_ns = false;
+    // several GPUs behind one handle (adapt_scene_desc.n_devices > 1): this handle is then only the head of a group -- it owns no pool;
+    // members[r] renders the tiles of device_ids[r] and members[0]'s film receives everybody's pixels at read time
+    std::vector<adapt_handle*> members;
+    std::vector<int*> d_member_pix;           // on members[0]'s device: the pixel list of member r (r >= 1)
+    std::vector<int> member_npix;
+    std::string iter_log_path;                // ADAPT_ITER_LOG: rays per k_trace launch (profiling aid: one sync per iteration)
+    std::vector<unsigned long long> iter_log; // (closest, shadow) counter values after every iteration
     bool poisoned = false;                    // a launch failed or the watchdog fired: counters and film no longer agree, only adapt_destroy is valid
     std::vector<adapt_emitter> h_emitters;    // host copy (inv_area of mesh lights is refreshed by adapt_update_geometry)
     std::vector<int4> h_obj_info;
@@ -252,6 +259,14 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
     }
     CK(cudaEventRecord(ev.e[3], st));
     CK(cudaGetLastError());
+    if (!h->iter_log_path.empty()) {
+        // profiling aid (tools/profile_summary.py): which launch traced how many rays, so an ncu capture of launch k can be matched with
+        // its ray counts.  Synchronises every iteration -- never set for a timed run.
+        DeviceCounters c;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+        h->iter_log.push_back(c.rays_closest); h->iter_log.push_back(c.rays_shadow);
+    }
     h->stats.iterations += 1; L.iterations += 1;
     h->stats.kernel_launches += n_logic + ((h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 2);
     return 0;
@@ -310,6 +325,34 @@ static int sync_lanes(adapt_handle* h) {
 }
 
 // ================================================================================================
+// several GPUs behind one handle
+// ================================================================================================
+// film indices i * h + j of the tiles owned by `rank`: tile k (row-major over tile x tile pixel tiles of the window) -> rank k % world,
+// pixels inside a tile in 4 x 8 patches (adapt_b200/dist.py::tile_partition is the same rule for the one-process-per-GPU set-up)
+static std::vector<int> tile_partition_host(int w, int h, int rank, int world, int tile, int sx, int ex, int sy, int ey) {
+    std::vector<int> out; (void)w;
+    int k = 0;
+    for (int ti = sx; ti < ex; ti += tile)
+        for (int tj = sy; tj < ey; tj += tile, k++) {
+            if (k % world != rank) continue;
+            const int ie = std::min(ti + tile, ex), je = std::min(tj + tile, ey);
+            for (int bi = ti; bi < ie; bi += 4)
+                for (int bj = tj; bj < je; bj += 8)
+                    for (int i = bi; i < std::min(bi + 4, ie); i++)
+                        for (int j = bj; j < std::min(bj + 8, je); j++) out.push_back(i * h + j);
+        }
+    return out;
+}
+
+// device_ids[0] pulls the pixels a peer owns out of the peer's film: peer-to-peer loads over NVLink, only the owned pixels move
+__global__ void k_gather_owned(float* __restrict__ dst, const float* __restrict__ peer_film, const int* __restrict__ pix, const int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t p = (size_t)pix[i] * 3;
+    dst[p] = peer_film[p]; dst[p + 1] = peer_film[p + 1]; dst[p + 2] = peer_film[p + 2];
+}
+
+// ================================================================================================
 // C ABI
 // ================================================================================================
 extern "C" {
@@ -317,6 +360,16 @@ extern "C" {
 const char* adapt_last_error(void) { return g_last_error.c_str(); }
 const char* adapt_version(void) { return "adapt_b200 0.1.0 (sm_100a)"; }
 void adapt_free(void* p) { std::free(p); }
+
+int32_t adapt_tile_partition(int32_t width, int32_t height, int32_t rank, int32_t world, int32_t tile, const int32_t* window,
+                             int32_t* out, int32_t capacity) {
+    if (width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world || tile <= 0) { set_error(ADAPT_ERR_INVALID, "adapt_tile_partition: bad argument"); return ADAPT_ERR_INVALID; }
+    const int sx = window ? std::max(0, window[0]) : 0, ex = window ? std::min(width, window[1]) : width;
+    const int sy = window ? std::max(0, window[2]) : 0, ey = window ? std::min(height, window[3]) : height;
+    const std::vector<int> pix = tile_partition_host(width, height, rank, world, tile, sx, ex, sy, ey);
+    if (out) std::memcpy(out, pix.data(), sizeof(int32_t) * (size_t)std::min<long long>((long long)pix.size(), std::max(0, capacity)));
+    return (int32_t)pix.size();
+}
 
 int adapt_bvh_build(const float* primitives, int32_t n_prims, const int32_t* obj_info, int32_t n_objects,
                     const float* world_min, const float* world_max,
@@ -412,15 +465,34 @@ static int build_accel(adapt_handle* h, const float* primitives) {
 }
 
 static void worker_main(adapt_handle* h);
+static int group_create(adapt_handle** out, const adapt_scene_desc* d, int n_dev);
 
 void adapt_destroy(adapt_handle* h) {
     if (!h) return;
+    if (!h->members.empty() || !h->d_member_pix.empty()) {
+        for (adapt_handle* m : h->members) adapt_destroy(m);
+        cudaSetDevice(h->device);
+        for (int* p : h->d_member_pix) if (p) cudaFree(p);
+        delete h;
+        return;
+    }
     if (h->worker.joinable()) {
         { std::unique_lock<std::mutex> lk(h->wk_mutex); h->wk_idle.wait(lk, [h] { return !h->wk_busy; }); h->wk_stop = true; }
         h->wk_wake.notify_all();
         h->worker.join();
     }
     cudaSetDevice(h->device);
+    if (!h->iter_log_path.empty()) {
+        if (FILE* f = std::fopen(h->iter_log_path.c_str(), "a")) {
+            unsigned long long pc = 0, ps = 0;
+            std::fprintf(f, "# handle %p: k_trace launch index, closest-hit rays, shadow rays in that launch\n", (void*)h);
+            for (size_t i = 0; i + 1 < h->iter_log.size(); i += 2) {
+                std::fprintf(f, "%zu %llu %llu\n", i / 2, h->iter_log[i] - pc, h->iter_log[i + 1] - ps);
+                pc = h->iter_log[i]; ps = h->iter_log[i + 1];
+            }
+            std::fclose(f);
+        }
+    }
     for (Lane& L : h->lanes) if (L.stream) cudaStreamSynchronize(L.stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -455,6 +527,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
         return set_error(ADAPT_ERR_NO_DEVICE, "no CUDA device visible: libadapt_b200 has no CPU fallback");
+    if (d->n_devices > 1) return group_create(out, d, n_dev);
     if (d->device_id < 0 || d->device_id >= n_dev) return set_error(ADAPT_ERR_INVALID, "adapt_create: bad device_id");
 
     adapt_handle* h = new adapt_handle();
@@ -516,8 +589,14 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     if (h->bvh_builder != 0 && h->bvh_builder != 1) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (host SAH) or 1 (device LBVH)"));
     SceneView& sv = h->sv;
     sv.n_objects = no; sv.n_prims = np;
-    // traversal: 1 = binary BVH (default), 3 = compressed 8-wide BVH collapsed from it (host builder only), 0 = baseline without lane refill
-    h->trace_mode = env_int("ADAPT_TRACE_MODE", 1);
+    // traversal: 1 = binary BVH, 3 = compressed 8-wide BVH collapsed from it (host builder only), 0 = baseline without lane refill.
+    // Default by scene size, from the A/B of sessions r02e / r02f (trace ms/step binary -> 8-wide): orb500k 50.9 -> 45.2 and the
+    // 18-primitive sphere scene 18.6 -> 16.8 gain (a tree far larger than L1, where a third of the node fetches per ray pays; a tree
+    // that is a single wide node), bunny90k 34.8 -> 35.7 and car290k 18.1 -> 18.1 do not (the wide step costs ~4x the instructions of
+    // a binary step and those trees' hot levels sit in L1 anyway).
+    h->trace_mode = env_int("ADAPT_TRACE_MODE", -1);
+    const bool auto_mode = h->trace_mode < 0;
+    if (auto_mode) h->trace_mode = (np <= 64 || np >= 400000) ? 3 : 1;
     if (h->trace_mode != 0 && h->trace_mode != 3) h->trace_mode = 1;
     h->want_wide = h->trace_mode == 3 && h->bvh_builder == 0;
     CKH(build_accel(h, d->primitives));
@@ -677,8 +756,12 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         h->trace_grid = prop.multiProcessorCount * per_sm;
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
-    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", 16)));
-    h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", 8)));
+    if (const char* lp = std::getenv("ADAPT_ITER_LOG")) h->iter_log_path = lp;
+    // scheduler knobs (pt_trace.cuh): lanes idle before a warp refills, lanes parked on a leaf before the leaf code runs.  Binary tree:
+    // 16 / 8 (round 1); 8-wide tree: leaf threshold 4, refill 8 on large trees (orb500k 47.4 -> 45.2 ms/step, session r02f)
+    const bool cw8 = h->trace_mode == 3;
+    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", cw8 && np >= 400000 ? 8 : 16)));
+    h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", cw8 ? 4 : 8)));
     h->node_steps = std::min(8, std::max(1, env_int("ADAPT_NODE_STEPS", 4)));
     CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));
     CKC(cudaDeviceSynchronize());
@@ -688,6 +771,75 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     *out = h;
     return 0;
 }
+
+// ---- group head: one member handle per device, film split into interleaved tiles ------------------------------------------------
+static int group_create(adapt_handle** out, const adapt_scene_desc* d, int n_dev) {
+    if (!d->device_ids) return set_error(ADAPT_ERR_INVALID, "adapt_create: n_devices > 1 needs device_ids");
+    const int n = d->n_devices;
+    for (int r = 0; r < n; r++) {
+        if (d->device_ids[r] < 0 || d->device_ids[r] >= n_dev) return set_error(ADAPT_ERR_INVALID, "adapt_create: device_ids entry out of range");
+        for (int q = 0; q < r; q++) if (d->device_ids[q] == d->device_ids[r]) return set_error(ADAPT_ERR_INVALID, "adapt_create: device_ids must be distinct");
+    }
+    // the gather at read time is done by device_ids[0] with peer-to-peer loads: no silent staging through the host
+    CK(cudaSetDevice(d->device_ids[0]));
+    for (int r = 1; r < n; r++) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, d->device_ids[0], d->device_ids[r]));
+        if (!can) return set_error(ADAPT_ERR_INVALID, "adapt_create: device_ids[0] has no peer access to the other devices (NVLink / PCIe P2P needed)");
+        cudaError_t pe = cudaDeviceEnablePeerAccess(d->device_ids[r], 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return set_error(ADAPT_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+        cudaGetLastError();
+    }
+    const int w = d->width, hh = d->height;
+    const int sx = d->do_crop ? std::max(0, d->start_x) : 0, ex = d->do_crop ? std::min(w, d->end_x) : w;
+    const int sy = d->do_crop ? std::max(0, d->start_y) : 0, ey = d->do_crop ? std::min(hh, d->end_y) : hh;
+    if (ex <= sx || ey <= sy) return set_error(ADAPT_ERR_INVALID, "adapt_create: no pixels to render");
+    int tile = 32;
+    while (tile > 4 && ((ex - sx + tile - 1) / tile) * ((ey - sy + tile - 1) / tile) < n) tile /= 2;
+    adapt_handle* g = new adapt_handle();
+    g->device = d->device_ids[0]; g->width = w; g->height = hh;
+    auto fail = [&](int code) { std::string keep = g_last_error; adapt_destroy(g); g_last_error = keep; return code; };
+    for (int r = 0; r < n; r++) {
+        std::vector<int> pix = tile_partition_host(w, hh, r, n, tile, sx, ex, sy, ey);
+        if (pix.empty()) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: more devices than film tiles"));
+        adapt_scene_desc dr = *d;
+        dr.n_devices = 0; dr.device_ids = nullptr; dr.device_id = d->device_ids[r];
+        dr.pixel_list = pix.data(); dr.n_pixels = (int32_t)pix.size();
+        adapt_handle* m = nullptr;
+        int rc = adapt_create(&m, &dr);
+        if (rc) return fail(rc);
+        g->members.push_back(m);
+        g->member_npix.push_back((int)pix.size());
+        int* dp = nullptr;
+        if (r > 0) {
+            cudaSetDevice(g->device);
+            if (cudaMalloc((void**)&dp, pix.size() * sizeof(int)) != cudaSuccess ||
+                cudaMemcpy(dp, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+                g->d_member_pix.push_back(dp);
+                return fail(set_error(ADAPT_ERR_CUDA, "adapt_create: pixel list upload for the gather failed"));
+            }
+        }
+        g->d_member_pix.push_back(dp);
+    }
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    *out = g;
+    return 0;
+}
+// every member finished, then device_ids[0] pulls the other members' pixels into its film (stream-ordered on member 0's stream)
+static int group_gather(adapt_handle* g) {
+    for (adapt_handle* m : g->members) { int rc = adapt_sync(m); if (rc) return rc; }
+    adapt_handle* m0 = g->members[0];
+    CK(cudaSetDevice(m0->device));
+    for (size_t r = 1; r < g->members.size(); r++) {
+        const int n = g->member_npix[r];
+        k_gather_owned<<<(n + 255) / 256, 256, 0, m0->stream>>>(m0->d_accum, g->members[r]->d_accum, g->d_member_pix[r], n);
+        CK(cudaGetLastError());
+        m0->stats.kernel_launches += 1;
+    }
+    return 0;
+}
+#define GROUP_EACH(h, call) do { for (adapt_handle* m_ : (h)->members) { int rc_ = (call); if (rc_) return rc_; } return 0; } while (0)
 
 static int poisoned_error() { return set_error(ADAPT_ERR_STATE, "handle unusable: an earlier adapt_render / adapt_sync failed (see that call's error); destroy it"); }
 
@@ -725,6 +877,7 @@ static int wait_worker(adapt_handle* h) {
 
 int adapt_render(adapt_handle* h, int32_t n_spp) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_render: null handle");
+    if (!h->members.empty()) { if (n_spp > 0) h->cnt += n_spp; GROUP_EACH(h, adapt_render(m_, n_spp)); }      // asynchronous: every device starts at once
     if (h->poisoned) return poisoned_error();
     if (n_spp <= 0) return 0;
     // work ids are absolute and gap-free (pt_common.cuh: WorkStripe): a new batch just raises the limit.  The call returns at once; the
@@ -740,8 +893,15 @@ int adapt_render(adapt_handle* h, int32_t n_spp) {
     return 0;
 }
 
+int adapt_wait_enqueued(adapt_handle* h) {
+    if (!h) return set_error(ADAPT_ERR_STATE, "adapt_wait_enqueued: null handle");
+    if (!h->members.empty()) GROUP_EACH(h, adapt_wait_enqueued(m_));
+    return wait_worker(h);
+}
+
 int adapt_sync(adapt_handle* h) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_sync: null handle");
+    if (!h->members.empty()) GROUP_EACH(h, adapt_sync(m_));
     int rc = wait_worker(h);
     if (rc) return rc;
     if (h->poisoned) return poisoned_error();
@@ -755,6 +915,7 @@ int adapt_sync(adapt_handle* h) {
 
 int adapt_read_accum(adapt_handle* h, float* dst, int32_t* spp) {
     if (!h || !dst) return set_error(ADAPT_ERR_INVALID, "adapt_read_accum: null argument");
+    if (!h->members.empty()) { int rcg = group_gather(h); if (rcg) return rcg; return adapt_read_accum(h->members[0], dst, spp); }
     int rc = adapt_sync(h);
     if (rc) return rc;
     CK(cudaMemcpyAsync(dst, h->d_accum, (size_t)h->width * h->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -770,6 +931,7 @@ __global__ void k_resolve(const float* __restrict__ accum, float* __restrict__ m
 
 int adapt_read_pixels(adapt_handle* h, float* dst, int32_t* spp) {
     if (!h || !dst) return set_error(ADAPT_ERR_INVALID, "adapt_read_pixels: null argument");
+    if (!h->members.empty()) { int rcg = group_gather(h); if (rcg) return rcg; return adapt_read_pixels(h->members[0], dst, spp); }
     int rc = adapt_sync(h);
     if (rc) return rc;
     const size_t n = (size_t)h->width * h->height * 3;
@@ -793,6 +955,7 @@ void adapt_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int adapt_load_accum(adapt_handle* h, const float* src, int32_t spp) {
     if (!h || spp < 0) return set_error(ADAPT_ERR_INVALID, "adapt_load_accum: bad argument");
+    if (!h->members.empty()) { h->cnt = spp; GROUP_EACH(h, adapt_load_accum(m_, src, spp)); }      // every device gets the film; it only keeps adding to its own pixels
     int rc = adapt_sync(h);
     if (rc) return rc;
     const size_t bytes = (size_t)h->width * h->height * 3 * sizeof(float);
@@ -808,6 +971,7 @@ int adapt_load_accum(adapt_handle* h, const float* src, int32_t spp) {
 
 int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats) {
     if (!h || !dptr) return set_error(ADAPT_ERR_INVALID, "adapt_accum_device_ptr: null argument");
+    if (!h->members.empty()) { int rcg = group_gather(h); if (rcg) return rcg; return adapt_accum_device_ptr(h->members[0], dptr, n_floats); }
     *dptr = h->d_accum;
     if (n_floats) *n_floats = (uint64_t)h->width * h->height * 3;
     return 0;
@@ -815,6 +979,7 @@ int adapt_accum_device_ptr(adapt_handle* h, void** dptr, uint64_t* n_floats) {
 
 int adapt_set_stream(adapt_handle* h, void* cuda_stream) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_set_stream: null handle");
+    if (!h->members.empty()) return set_error(ADAPT_ERR_STATE, "adapt_set_stream: a multi-device handle runs on its own streams");
     CK(cudaSetDevice(h->device));
     int rc = wait_worker(h);
     if (rc) return rc;
@@ -829,6 +994,20 @@ int adapt_set_stream(adapt_handle* h, void* cuda_stream) {
 
 int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     if (!h || !out) return set_error(ADAPT_ERR_INVALID, "adapt_get_stats: null argument");
+    if (!h->members.empty()) {
+        // counters add up over the devices; stage times and iterations are those of the slowest device (they run side by side)
+        std::memset(out, 0, sizeof(*out));
+        for (adapt_handle* m : h->members) {
+            adapt_stats st; int rc = adapt_get_stats(m, &st); if (rc) return rc;
+            out->paths += st.paths; out->rays_closest += st.rays_closest; out->rays_shadow += st.rays_shadow;
+            out->kernel_launches += st.kernel_launches; out->nodes_visited += st.nodes_visited; out->prims_tested += st.prims_tested;
+            out->iterations = std::max(out->iterations, st.iterations);
+            out->ms_logic = std::max(out->ms_logic, st.ms_logic); out->ms_closest = std::max(out->ms_closest, st.ms_closest);
+            out->ms_shadow = std::max(out->ms_shadow, st.ms_shadow); out->ms_total = std::max(out->ms_total, st.ms_total);
+            out->reserved[0] += st.reserved[0]; out->reserved[1] = st.reserved[1]; out->reserved[2] += st.reserved[2]; out->reserved[3] = st.reserved[3];
+        }
+        return 0;
+    }
     CK(cudaSetDevice(h->device));
     int rc = wait_worker(h);
     if (rc) return rc;
@@ -856,6 +1035,7 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
 
 int adapt_reset_stats(adapt_handle* h) {
     if (!h) return set_error(ADAPT_ERR_STATE, "adapt_reset_stats: null handle");
+    if (!h->members.empty()) GROUP_EACH(h, adapt_reset_stats(m_));
     CK(cudaSetDevice(h->device));
     int rc = wait_worker(h);
     if (rc) return rc;
@@ -873,6 +1053,7 @@ int adapt_reset_stats(adapt_handle* h) {
 int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* rays_d, const float* tmax, int32_t n, int32_t any_hit,
                           int32_t* hit_obj, int32_t* hit_prim, float* hit_t, float* hit_u, float* hit_v) {
     if (!h || !rays_o || !rays_d || !hit_prim || n < 0) return set_error(ADAPT_ERR_INVALID, "adapt_intersect_batch: bad argument");
+    if (!h->members.empty()) return adapt_intersect_batch(h->members[0], rays_o, rays_d, tmax, n, any_hit, hit_obj, hit_prim, hit_t, hit_u, hit_v);
     if (!any_hit && (!hit_obj || !hit_t || !hit_u || !hit_v)) return set_error(ADAPT_ERR_INVALID, "adapt_intersect_batch: closest-hit needs all outputs");
     if (n == 0) return 0;
     CK(cudaSetDevice(h->device));
@@ -906,6 +1087,7 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
 
 int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s) {
     if (!h || !primitives || !n_g) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: null argument");
+    if (!h->members.empty()) GROUP_EACH(h, adapt_update_geometry(m_, primitives, n_g, n_s));
     if (h->has_ns && !n_s) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: the scene was created with vertex normals, n_s is required");
     CK(cudaSetDevice(h->device));
     int rc = adapt_sync(h);                                      // nothing may still be tracing through the old structure
@@ -949,6 +1131,7 @@ int adapt_update_geometry(adapt_handle* h, const float* primitives, const float*
 int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_t* depth, int32_t* builder, float* build_ms,
                      float* nodes_out, float* prims_out) {
     if (!h) return set_error(ADAPT_ERR_INVALID, "adapt_bvh_export: null handle");
+    if (!h->members.empty()) return adapt_bvh_export(h->members[0], n_nodes, n_prims, depth, builder, build_ms, nodes_out, prims_out);
     if (n_nodes) *n_nodes = h->bvh_nodes;
     if (n_prims) *n_prims = h->sv.n_prims;
     if (depth) *depth = h->bvh_depth;
@@ -964,6 +1147,7 @@ int adapt_bxdf_batch(adapt_handle* h, int32_t obj, int32_t n, const float* n_s, 
                      int32_t two_sides, uint64_t seed, float* eval3, float* pdf, float* s_dir3, float* s_spec3, float* s_pdf, int32_t* s_flag) {
     if (!h || !n_s || !n_g || !incid || !out || !eval3 || !pdf || !s_dir3 || !s_spec3 || !s_pdf || !s_flag || n < 0)
         return set_error(ADAPT_ERR_INVALID, "adapt_bxdf_batch: bad argument");
+    if (!h->members.empty()) return adapt_bxdf_batch(h->members[0], obj, n, n_s, n_g, incid, out, two_sides, seed, eval3, pdf, s_dir3, s_spec3, s_pdf, s_flag);
     if (obj < 0 || obj >= h->sv.n_objects) return set_error(ADAPT_ERR_INVALID, "adapt_bxdf_batch: object index out of range");
     if (n == 0) return 0;
     CK(cudaSetDevice(h->device));

@@ -63,15 +63,16 @@ class _Counter:
 class Renderer:
     def __init__(self, emitters: List, array_info: dict, objects: List, prop: dict, *, seed: int = 0,
                  device_id: int = 0, pixel_list: Optional[np.ndarray] = None, pool_size: int = 0,
-                 max_bounce: Optional[int] = None, bvh_builder=0, integrator: str = "pt"):
+                 max_bounce: Optional[int] = None, bvh_builder=0, integrator: str = "pt", device_ids=None):
         """bvh_builder: 0 / "sah" = host binned-SAH build (default), 1 / "lbvh" = linear BVH built on the device.
-        integrator: "pt" (renderer/vanilla_renderer.py); "vpt" (renderer/vpt.py, homogeneous media) is refused by the library unless
-        ADAPT_ENABLE_VPT=1 switches on its first, not yet GPU-validated version."""
+        integrator: "pt" (renderer/vanilla_renderer.py) or "vpt" (renderer/vpt.py over homogeneous media; see VolumeRenderer).
+        device_ids: several CUDA ordinals -> ONE renderer over all of them (single process): the library replicates the scene, splits the
+        film into interleaved tiles and gathers the film over NVLink peer loads when it is read (include/adapt_b200.h: n_devices)."""
         self.clock = TicToc()
         self._lib = load_library()
         self._packed = pack_scene(emitters, array_info, objects, prop, seed=seed, device_id=device_id,
                                   pixel_list=pixel_list, pool_size=pool_size, max_bounce=max_bounce,
-                                  bvh_builder=bvh_builder, integrator=integrator)
+                                  bvh_builder=bvh_builder, integrator=integrator, device_ids=device_ids)
         host = self._packed.host
         # attributes the reference driver / watermark / checkpoint code read
         for key in ("w", "h", "crop_x", "crop_y", "crop_rx", "crop_ry", "do_crop", "start_x", "end_x", "start_y",
@@ -106,8 +107,13 @@ class Renderer:
         self.render_batch(1)
 
     def render_batch(self, n_spp: int):
+        """Enqueue n_spp samples per pixel; returns at once (adapt_render is asynchronous), `synchronize` / any film read waits."""
         check(self._lib, self._lib.adapt_render(self._handle, int(n_spp)), "adapt_render")
         self._cnt += int(n_spp)
+
+    def wait(self):
+        """Block until every sample enqueued so far has been handed to a path slot (paths in flight keep going)."""
+        check(self._lib, self._lib.adapt_wait_enqueued(self._handle), "adapt_wait_enqueued")
 
     def synchronize(self):
         check(self._lib, self._lib.adapt_sync(self._handle), "adapt_sync")

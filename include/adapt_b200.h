@@ -113,11 +113,18 @@ typedef struct {
     const adapt_texture* textures;  /* [3][n_objects]: albedo, normal, bump descriptor per object, or NULL (no textures) */
     const float* tex_image[3];      /* packed atlas per map kind, [tex_size][tex_size][3] floats (row = v, column = u), or NULL */
     int32_t tex_size[3];            /* atlas edge length per map kind                                                      */
-    int32_t integrator;             /* 0 = `pt` (renderer/vanilla_renderer.py), 1 = `vpt` (renderer/vpt.py: homogeneous media; implemented by the
-                                       CPU oracle; libadapt_b200 returns ADAPT_ERR_INVALID for it unless ADAPT_ENABLE_VPT=1 switches on its
-                                       kernels, which are verified on the CPU but have not been validated on a GPU yet)           */
+    int32_t integrator;             /* 0 = `pt` (renderer/vanilla_renderer.py), 1 = `vpt` (renderer/vpt.py over homogeneous media: k_logic_vpt /
+                                       k_trace_vpt); anything else is refused                                                    */
     /* participating media: renderer/vpt.py:53, bxdf/bsdf.py:37, parsers/world.py:34. Optional (NULL = everything transparent). */
     const adapt_medium* media;      /* [n_objects + 1]: medium of each object's BSDF (ignored for BRDF objects), last entry = world medium */
+    /* several GPUs behind ONE handle (the reference is single-device: renderer/vanilla_renderer.py:35 is its only parallelism).
+     * n_devices > 1: the scene is replicated on every listed device, the film (or crop window) is split into interleaved 32x32 tiles
+     * (tile k -> device_ids[k % n_devices]; smaller tiles when the window has fewer tiles than devices), adapt_render enqueues on all of
+     * them, and adapt_read_accum / adapt_read_pixels gather every device's own pixels into device_ids[0]'s film with peer-to-peer
+     * loads over NVLink before the copy to the host.  Needs peer access between device_ids[0] and the others; device_id, pixel_list
+     * and n_pixels are ignored.  n_devices <= 1: one device, `device_id`. */
+    int32_t n_devices;
+    const int32_t* device_ids;      /* [n_devices] distinct CUDA ordinals                                                          */
 } adapt_scene_desc;
 
 /* Counters since create (or the last adapt_reset_stats). Ray counts are the calls the reference
@@ -142,9 +149,21 @@ typedef struct adapt_handle adapt_handle;
 int adapt_create(adapt_handle** out, const adapt_scene_desc* desc);
 void adapt_destroy(adapt_handle* h);
 
-/* Enqueue n_spp samples per owned pixel (Renderer.render called n_spp times). Asynchronous with
- * respect to the host where possible; adapt_sync / adapt_read_accum are the sync points. */
+/* The film partition of a multi-device handle (and of adapt_b200/dist.py for the one-process-per-GPU set-up): tile k -- row-major over
+ * tile x tile pixel tiles of `window` = (start_x, end_x, start_y, end_y), NULL = whole film -- belongs to rank k % world; inside a tile
+ * the pixels are listed in 4 x 8 patches.  Writes up to `capacity` film indices i * height + j into `out` (may be NULL) and returns how
+ * many pixels the rank owns (negative: error code). */
+int32_t adapt_tile_partition(int32_t width, int32_t height, int32_t rank, int32_t world, int32_t tile, const int32_t* window,
+                             int32_t* out, int32_t capacity);
+
+/* Enqueue n_spp samples per owned pixel (Renderer.render called n_spp times; renderer/vanilla_renderer.py:32-120 is one spp per call).
+ * Asynchronous: the call raises the handle's work limit, wakes its launch thread and returns (well under a millisecond); batches
+ * enqueued back to back run without a gap between them.  A launch failure is reported by the next synchronising call.
+ *   adapt_wait_enqueued  blocks until every sample enqueued so far has been handed to a path slot (paths still in flight keep going:
+ *                        the point up to which the reference's render() call would have blocked the host, minus the tail)
+ *   adapt_sync           blocks until every enqueued sample is finished and accumulated (adapt_read_* / adapt_load_accum imply it) */
 int adapt_render(adapt_handle* h, int32_t n_spp);
+int adapt_wait_enqueued(adapt_handle* h);
 int adapt_sync(adapt_handle* h);
 
 /* Framebuffer: `color` sum in the reference layout (w,h,3) indexed [i=x][j=y], and the sample

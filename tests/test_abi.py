@@ -30,7 +30,8 @@ def test_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.adapt_bxdf) == 64 and C.sizeof(_lib.adapt_emitter) == 64 and C.sizeof(_lib.adapt_medium) == 80
-    assert _lib.adapt_scene_desc.media.offset % 8 == 0 and _lib.adapt_scene_desc.media.offset + 8 == C.sizeof(_lib.adapt_scene_desc)
+    assert _lib.adapt_scene_desc.media.offset % 8 == 0 and _lib.adapt_scene_desc.device_ids.offset + 8 == C.sizeof(_lib.adapt_scene_desc)
+    assert _lib.adapt_scene_desc.n_devices.offset == _lib.adapt_scene_desc.media.offset + 8
     assert _lib.adapt_scene_desc.seed.offset % 8 == 0
     assert C.sizeof(_lib.adapt_stats) == 5 * 8 + 4 * 4 + 2 * 8 + 4 * 8
 
@@ -167,3 +168,37 @@ def test_bvh_build_rejects_bad_input(lib):
     rc = lib.adapt_bvh_build(prims.ctypes.data_as(fp), 2, oi.ctypes.data_as(ip), 1, w.ctypes.data_as(fp), w.ctypes.data_as(fp),
                              C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(nr), C.byref(nn))
     assert rc == -1 and b"obj_info" in lib.adapt_last_error()
+
+
+def test_tile_partition_of_the_library_equals_the_python_one(lib):
+    """A multi-device handle (adapt_scene_desc.n_devices > 1) splits the film with the same rule as adapt_b200/dist.py::tile_partition."""
+    from adapt_b200.dist import tile_partition
+    ip = C.POINTER(C.c_int32)
+    for (w, h, world, tile, window) in [(64, 48, 2, 32, None), (130, 37, 3, 16, None), (1920, 1080, 8, 32, None), (200, 120, 4, 32, (40, 150, 10, 90))]:
+        seen = []
+        for rank in range(world):
+            want = tile_partition(w, h, rank, world, tile=tile, window=window)
+            win = None if window is None else (C.c_int32 * 4)(*window)
+            n = lib.adapt_tile_partition(w, h, rank, world, tile, win, None, 0)
+            assert n == want.size
+            got = np.zeros(max(n, 1), np.int32)
+            assert lib.adapt_tile_partition(w, h, rank, world, tile, win, got.ctypes.data_as(ip), n) == n
+            np.testing.assert_array_equal(got[:n], want)
+            seen.append(got[:n])
+        allpix = np.sort(np.concatenate(seen))
+        assert np.unique(allpix).size == allpix.size                # disjoint ownership
+    assert lib.adapt_tile_partition(8, 8, 2, 2, 32, None, None, 0) < 0
+
+
+def test_multi_device_descriptor_needs_a_gpu_too(lib, scene_root):
+    """n_devices > 1 goes through the same loud failure without a device: no CPU fallback for the group handle either."""
+    from adapt_b200._lib import pack_scene
+    e, a, o, c = load_scene(scene_root, "cbox", "cbox.xml", 64, 64)
+    ps = pack_scene(e, a, o, c, device_ids=[0, 1])
+    assert ps.desc.n_devices == 2 and ps.desc.device_ids[1] == 1
+    with pytest.raises(ValueError):
+        pack_scene(e, a, o, c, device_ids=[0, 1], pixel_list=np.arange(16, dtype=np.int32))
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.adapt_create(C.byref(h), C.byref(ps.desc)) == -3 and not h           # ADAPT_ERR_NO_DEVICE

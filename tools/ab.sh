@@ -1,6 +1,8 @@
 #!/bin/bash
 # A/B bench lines: bash tools/ab.sh "<bench args>" VAR=VAL [VAR=VAL ...]   (first run = defaults)
 args=$1; shift
+# A/B tables are taken at 32 spp per step (the round-1 figures) unless the arguments say otherwise
+case "$args" in *--spp-per-step*) ;; *) args="$args --spp-per-step 32" ;; esac
 mkdir -p gpurun_out
 for v in "DEFAULT=1" "$@"; do
   echo -n "== $args | $v : "

@@ -64,8 +64,19 @@ for rep in sorted(os.listdir(src)):
         u = units[i].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "usecond": 1, "nsecond": 1e-3, "msecond": 1e3}.get(u, 1)
     per = [(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"), val(r, "gpu__time_duration.sum")) for r in rows[2:]]
-    summary[f"k_{kern}"] = {"dram_bytes_per_launch": sum(p[0] for p in per) / len(per), "duration_us": sum(p[1] for p in per) / len(per),
-                            "launches_captured": len(per), "session": tag}
+    entry = {"dram_bytes_per_launch": sum(p[0] for p in per) / len(per), "duration_us": sum(p[1] for p in per) / len(per),
+             "launches_captured": len(per), "session": tag}
+    # rays traced by exactly those launches (ADAPT_ITER_LOG of the same command; the capture skips the first NCU_SKIP launches of the kernel)
+    log = os.path.join(src, f"iter_log_{kern}.txt")
+    if os.path.exists(log):
+        skip = int(os.environ.get("NCU_SKIP", "6"))
+        it = [tuple(int(x) for x in ln.split()) for ln in open(log) if ln.strip() and not ln.startswith("#")]
+        sel = [r for r in it if skip <= r[0] < skip + len(per)]
+        if sel:
+            entry["rays_in_launch"] = sum(r[1] for r in sel) / len(sel)
+            entry["shadow_rays_in_launch"] = sum(r[2] for r in sel) / len(sel)
+            entry["dram_bytes_per_ray"] = entry["dram_bytes_per_launch"] / max(entry["rays_in_launch"] + entry["shadow_rays_in_launch"], 1.0)
+    summary[f"k_{kern}"] = entry
 json.dump(summary, open(summary_path, "w"), indent=1)
 print(json.dumps(summary, indent=1))
 if os.path.exists(os.path.join(src, "bench.json")):
