@@ -1085,22 +1085,34 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
     return 0;
 }
 
-int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s) {
-    if (!h || !primitives || !n_g) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: null argument");
-    if (!h->members.empty()) GROUP_EACH(h, adapt_update_geometry(m_, primitives, n_g, n_s));
-    if (h->has_ns && !n_s) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: the scene was created with vertex normals, n_s is required");
+// shared by adapt_update_geometry (rebuild) and adapt_refit_geometry (same tree, new boxes)
+static int new_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s, bool refit, const char* who) {
+    if (h->has_ns && !n_s) return set_error(ADAPT_ERR_INVALID, std::string(who) + ": the scene was created with vertex normals, n_s is required");
     CK(cudaSetDevice(h->device));
     int rc = adapt_sync(h);                                      // nothing may still be tracing through the old structure
     if (rc) return rc;
+    if (refit && h->trace_mode == 3)
+        return set_error(ADAPT_ERR_STATE, std::string(who) + ": the compressed 8-wide tree has no refit (create the handle with ADAPT_TRACE_MODE=1, or use adapt_update_geometry)");
     const int np = h->sv.n_prims;
     std::vector<float4> prim_geom, prim_shade;
     pack_geometry(primitives, n_g, h->has_ns ? n_s : nullptr, np, h->sph, h->prim_obj, prim_geom, prim_shade);
     CK(cudaMemcpyAsync(h->d_prim_geom, prim_geom.data(), prim_geom.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_prim_shade, prim_shade.data(), prim_shade.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    rc = build_accel(h, primitives);
-    if (rc) return rc;
-    if (h->trace_mode == 3 && !h->wide_ok) h->trace_mode = 1;
+    if (refit) {
+        float lo[3], hi[3], ms = 0.f; std::string what;
+        cudaError_t re = refit_bvh_device(const_cast<float4*>(h->sv.nodes), h->bvh_nodes, const_cast<float4*>(h->sv.leaf_prims), np, primitives,
+                                          h->stream, lo, hi, &ms, what);
+        if (re != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH refit: " + what + ": " + cudaGetErrorString(re));
+        h->bvh_build_ms = ms;
+        const float pad = 1e-3f;
+        h->sv.world_lo = mk3(lo[0] - pad, lo[1] - pad, lo[2] - pad);
+        h->sv.world_hi = mk3(hi[0] + pad, hi[1] + pad, hi[2] + pad);
+    } else {
+        rc = build_accel(h, primitives);
+        if (rc) return rc;
+        if (h->trace_mode == 3 && !h->wide_ok) h->trace_mode = 1;
+    }
     // area emitters on deforming meshes: inv_area = 1 / surface area of the attached object (parsers/obj_loader.py:82-93 as called from
     // parsers/xml_parser.py:103; a sphere counts 4 pi r^2), recomputed for the new vertices
     bool any_area = false;
@@ -1126,6 +1138,18 @@ int adapt_update_geometry(adapt_handle* h, const float* primitives, const float*
     // non-blocking: make sure everything is in place before the next adapt_render
     CK(cudaDeviceSynchronize());
     return 0;
+}
+
+int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s) {
+    if (!h || !primitives || !n_g) return set_error(ADAPT_ERR_INVALID, "adapt_update_geometry: null argument");
+    if (!h->members.empty()) GROUP_EACH(h, adapt_update_geometry(m_, primitives, n_g, n_s));
+    return new_geometry(h, primitives, n_g, n_s, false, "adapt_update_geometry");
+}
+
+int adapt_refit_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s) {
+    if (!h || !primitives || !n_g) return set_error(ADAPT_ERR_INVALID, "adapt_refit_geometry: null argument");
+    if (!h->members.empty()) GROUP_EACH(h, adapt_refit_geometry(m_, primitives, n_g, n_s));
+    return new_geometry(h, primitives, n_g, n_s, true, "adapt_refit_geometry");
 }
 
 int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_t* depth, int32_t* builder, float* build_ms,

@@ -20,6 +20,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "bvh_lbvh.h"
@@ -232,6 +233,136 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
     out.leaf_prims = reinterpret_cast<float4*>(d_prims);
     out.n_nodes = (int)h_cnt; out.depth = depth; out.build_ms = ms;
     for (int a = 0; a < 3; a++) { out.root_lo[a] = root[a]; out.root_hi[a] = root[3 + a]; }
+    return cudaSuccess;
+}
+
+
+// ================================================================================================
+// refit (adapt_refit_geometry): same topology, new boxes
+// ================================================================================================
+namespace {
+
+// leaf record k <- the new vertices of the primitive it names (record word t2.y = primitive id, sphere flag in bit 31 of t2.z)
+__global__ void k_refit_prims(float4* __restrict__ prims, const float* __restrict__ prim9, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 t2 = prims[(size_t)k * 3 + 2];
+    const int pid = __float_as_int(t2.y);
+    const bool sph = (__float_as_uint(t2.z) & 0x80000000u) != 0u;
+    const float* v = prim9 + (size_t)pid * 9;
+    if (sph) {
+        prims[(size_t)k * 3] = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        prims[(size_t)k * 3] = make_float4(v[0], v[1], v[2], v[3] - v[0]);
+        prims[(size_t)k * 3 + 1] = make_float4(v[4] - v[1], v[5] - v[2], v[6] - v[0], v[7] - v[1]);
+        prims[(size_t)k * 3 + 2] = make_float4(v[8] - v[2], t2.y, t2.z, t2.w);
+    }
+}
+// parent links (node * 2 + child slot) and arrival counters: a node is complete when its own thread has written its leaf children's
+// boxes and every inner child has delivered its box
+__global__ void k_refit_init(const float4* __restrict__ nodes, int n_nodes, int* __restrict__ parent, unsigned* __restrict__ pending) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4 n3 = nodes[(size_t)i * 4 + 3];
+    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    unsigned p = 1u;
+    if (c0 >= 0) { parent[c0] = i * 2; p++; }
+    if (c1 >= 0 && c1 != c0) { parent[c1] = i * 2 + 1; p++; }
+    pending[i] = p;
+    if (i == 0) parent[0] = -1;
+}
+__device__ __forceinline__ void leaf_box(const float4* __restrict__ prims, int code, float lo[3], float hi[3]) {
+    const int first = code >> 3, cnt = (code & 7) + 1;
+    for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; }
+    for (int k = first; k < first + cnt; k++) {
+        const float4 t0 = prims[(size_t)k * 3], t1 = prims[(size_t)k * 3 + 1], t2 = prims[(size_t)k * 3 + 2];
+        float plo[3], phi[3];
+        if (__float_as_uint(t2.z) & 0x80000000u) {
+            const float c[3] = {t0.x, t0.y, t0.z};
+            for (int a = 0; a < 3; a++) { plo[a] = c[a] - t0.w; phi[a] = c[a] + t0.w; }
+        } else {
+            const float v0[3] = {t0.x, t0.y, t0.z}, e1[3] = {t0.w, t1.x, t1.y}, e2[3] = {t1.z, t1.w, t2.x};
+            for (int a = 0; a < 3; a++) {
+                const float p1 = v0[a] + e1[a], p2 = v0[a] + e2[a];
+                plo[a] = fminf(v0[a], fminf(p1, p2)); phi[a] = fmaxf(v0[a], fmaxf(p1, p2));
+                // flat boxes get the reference's pad (bvh_helper.h:36-42); one ulp more than the builder's test because v0 + e only
+                // reproduces the vertex to rounding
+                if (phi[a] - plo[a] < 1.0001e-4f) { plo[a] -= 1e-4f; phi[a] += 1e-4f; }
+            }
+        }
+        for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], plo[a]); hi[a] = fmaxf(hi[a], phi[a]); }
+    }
+}
+// store a child box into slot `child` of node `i`, widened by an ulp like the builder does (bvh_build.cpp: put_box)
+__device__ __forceinline__ void put_child_box(float4* __restrict__ nodes, int i, int child, const float lo[3], const float hi[3]) {
+    float l[3], h[3];
+    for (int a = 0; a < 3; a++) { l[a] = nextafterf(lo[a], -3.0e38f); h[a] = nextafterf(hi[a], 3.0e38f); }
+    float* n = reinterpret_cast<float*>(nodes + (size_t)i * 4);
+    if (child == 0) { n[0] = l[0]; n[1] = h[0]; n[2] = l[1]; n[3] = h[1]; n[8] = l[2]; n[9] = h[2]; }
+    else { n[4] = l[0]; n[5] = h[0]; n[6] = l[1]; n[7] = h[1]; n[10] = l[2]; n[11] = h[2]; }
+}
+__global__ void k_refit_nodes(float4* nodes, int n_nodes, const float4* __restrict__ prims, const int* __restrict__ parent, unsigned* pending) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    {
+        const float4 n3 = nodes[(size_t)i * 4 + 3];
+        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        float lo[3], hi[3];
+        if (c0 < 0) { leaf_box(prims, ~c0, lo, hi); put_child_box(nodes, i, 0, lo, hi); }
+        if (c1 < 0 && c1 != c0) { leaf_box(prims, ~c1, lo, hi); put_child_box(nodes, i, 1, lo, hi); }
+    }
+    // whoever completes a node carries its box to the parent; the other arrivals leave
+    while (true) {
+        __threadfence();
+        if (atomicSub(&pending[i], 1u) != 1u) return;
+        __threadfence();
+        const int pc = parent[i];
+        if (pc < 0) return;                                           // the root is complete
+        const volatile float* n = reinterpret_cast<const volatile float*>(nodes + (size_t)i * 4);
+        const float4 n3 = nodes[(size_t)i * 4 + 3];
+        const bool one_child = __float_as_int(n3.x) == __float_as_int(n3.y);       // synthetic single-leaf root: second box is empty
+        float lo[3], hi[3];
+        lo[0] = one_child ? n[0] : fminf(n[0], n[4]); hi[0] = one_child ? n[1] : fmaxf(n[1], n[5]);
+        lo[1] = one_child ? n[2] : fminf(n[2], n[6]); hi[1] = one_child ? n[3] : fmaxf(n[3], n[7]);
+        lo[2] = one_child ? n[8] : fminf(n[8], n[10]); hi[2] = one_child ? n[9] : fmaxf(n[9], n[11]);
+        put_child_box(nodes, pc >> 1, pc & 1, lo, hi);
+        i = pc >> 1;
+    }
+}
+
+}  // namespace
+
+cudaError_t refit_bvh_device(float4* nodes, int32_t n_nodes, float4* leaf_prims, int32_t n_prims, const float* primitives,
+                             cudaStream_t st, float root_lo[3], float root_hi[3], float* refit_ms, std::string& what) {
+    float* d_prim9 = nullptr; int* d_parent = nullptr; unsigned* d_pending = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup_out = [&]() {
+        if (d_prim9) cudaFree(d_prim9); if (d_parent) cudaFree(d_parent); if (d_pending) cudaFree(d_pending);
+        if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+        d_prim9 = nullptr; d_parent = nullptr; d_pending = nullptr; e0 = e1 = nullptr;
+    };
+    if (!nodes || !leaf_prims || !primitives || n_nodes <= 0 || n_prims <= 0) { what = "refit_bvh_device: bad argument"; return cudaErrorInvalidValue; }
+    LBCK(cudaMalloc((void**)&d_prim9, (size_t)n_prims * 9 * sizeof(float)));
+    LBCK(cudaMalloc((void**)&d_parent, (size_t)n_nodes * sizeof(int)));
+    LBCK(cudaMalloc((void**)&d_pending, (size_t)n_nodes * sizeof(unsigned)));
+    LBCK(cudaEventCreate(&e0)); LBCK(cudaEventCreate(&e1));
+    LBCK(cudaMemcpyAsync(d_prim9, primitives, (size_t)n_prims * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    LBCK(cudaEventRecord(e0, st));
+    k_refit_prims<<<lb_grid(n_prims), LB_BLOCK, 0, st>>>(leaf_prims, d_prim9, n_prims);
+    k_refit_init<<<lb_grid(n_nodes), LB_BLOCK, 0, st>>>(nodes, n_nodes, d_parent, d_pending);
+    k_refit_nodes<<<lb_grid(n_nodes), LB_BLOCK, 0, st>>>(nodes, n_nodes, leaf_prims, d_parent, d_pending);
+    LBCK(cudaEventRecord(e1, st));
+    float root[16];
+    LBCK(cudaMemcpyAsync(root, nodes, sizeof(root), cudaMemcpyDeviceToHost, st));
+    LBCK(cudaStreamSynchronize(st));
+    LBCK(cudaGetLastError());
+    int c0, c1; memcpy(&c0, &root[12], 4); memcpy(&c1, &root[13], 4);
+    const bool one = c0 == c1;
+    root_lo[0] = one ? root[0] : std::min(root[0], root[4]); root_hi[0] = one ? root[1] : std::max(root[1], root[5]);
+    root_lo[1] = one ? root[2] : std::min(root[2], root[6]); root_hi[1] = one ? root[3] : std::max(root[3], root[7]);
+    root_lo[2] = one ? root[8] : std::min(root[8], root[10]); root_hi[2] = one ? root[9] : std::max(root[9], root[11]);
+    if (refit_ms) cudaEventElapsedTime(refit_ms, e0, e1);
+    cleanup_out();
     return cudaSuccess;
 }
 

@@ -23,3 +23,12 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
                              int32_t n, int32_t n_objects, int max_leaf, cudaStream_t stream, DeviceBvh& out, std::string& what);
 
 }  // namespace adapt
+
+namespace adapt {
+// Refit: new vertex positions for the SAME tree.  Rewrites the 48-byte leaf records from `primitives` (host, [n*9]) and recomputes every
+// child box of the 64-byte nodes bottom-up on the device (a leaf child's box from its records, an inner child's box as the union of that
+// node's two child boxes, ordered by one arrival counter per node); the topology -- and with it the quality of a SAH tree built for the
+// rest pose -- is kept.  Runs on `stream` and synchronises it; root_lo / root_hi receive the new bounds of the whole tree.
+cudaError_t refit_bvh_device(float4* nodes, int32_t n_nodes, float4* leaf_prims, int32_t n_prims, const float* primitives,
+                             cudaStream_t stream, float root_lo[3], float root_hi[3], float* refit_ms, std::string& what);
+}  // namespace adapt

@@ -33,6 +33,9 @@ using namespace adapt;
 #ifndef LOGIC_BULK_TILE
 #define LOGIC_BULK_TILE 0
 #endif
+// Measured and rejected for k_logic in session r02k (profiles/r02k_ab_logic_variants.txt, logic ms/step bunny90k / orb500k / balls-mono,
+// shipped 17.4 / 23.5 / 22.3): requesting a slot's whole state in one batch before the misc word is looked at (18.1 / 25.0 / 23.3 -- the
+// extra live registers cost more than the saved round trip), five resident blocks per SM instead of four (18.0 / 24.2 / 23.0), six (18.8).
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif

@@ -222,10 +222,11 @@ class Renderer:
             v.ctypes.data_as(fp)), "adapt_intersect_batch")
         return dict(obj=obj, prim=prim, t=t, u=u, v=v)
 
-    def update_geometry(self, primitives, n_g, n_s=None):
+    def update_geometry(self, primitives, n_g, n_s=None, refit: bool = False):
         """New vertex positions for the same topology (animated meshes): (N,3,3) primitives, (N,3) geometric normals and, when
         the scene has vertex normals, (N,3,3) shading normals -- the arrays of ``array_info``.  Rebuilds the acceleration
-        structure with this renderer's builder; the accumulation buffer is kept (``reset_accumulation()`` starts over)."""
+        structure with this renderer's builder, or with ``refit=True`` keeps the tree and only recomputes its boxes on the device
+        (adapt_refit_geometry); the accumulation buffer is kept (``reset_accumulation()`` starts over)."""
         fp = C.POINTER(C.c_float)
         n = self.num_prims
         pr = np.ascontiguousarray(primitives, np.float32).reshape(-1)
@@ -237,8 +238,8 @@ class Renderer:
             ns = np.ascontiguousarray(n_s, np.float32).reshape(-1)
             if ns.size != n * 9:
                 raise ValueError(f"update_geometry: expected {n} x 3 shading normals")
-        check(self._lib, self._lib.adapt_update_geometry(self._handle, pr.ctypes.data_as(fp), ng.ctypes.data_as(fp),
-                                                         None if ns is None else ns.ctypes.data_as(fp)), "adapt_update_geometry")
+        fn, name = (self._lib.adapt_refit_geometry, "adapt_refit_geometry") if refit else (self._lib.adapt_update_geometry, "adapt_update_geometry")
+        check(self._lib, fn(self._handle, pr.ctypes.data_as(fp), ng.ctypes.data_as(fp), None if ns is None else ns.ctypes.data_as(fp)), name)
 
     def reset_accumulation(self, spp: int = 0):
         """Empty film (cleared on the device); the next sample rendered is number ``spp + 1``."""

@@ -203,6 +203,11 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
  * object they are attached to; the accumulation buffer is left as it is -- reset it with adapt_load_accum(h, NULL, 0) when the image
  * should start over.  On failure the handle keeps its previous acceleration structure. */
 int adapt_update_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s);
+/* The same call without the rebuild: the tree keeps its topology and only the boxes are recomputed, bottom-up on the device (leaf records
+ * rewritten from the new vertices, one arrival counter per node).  For meshes that deform a little per frame this keeps the quality of the
+ * SAH tree built for the rest pose at a fraction of a millisecond per update; the more the mesh departs from that pose, the looser the
+ * boxes get (results stay exact -- only traversal time grows), and adapt_update_geometry is the reset.  Binary tree only. */
+int adapt_refit_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s);
 
 /* Stage-level hook for the acceleration structure that replaces LinearBVH / LinearNode (tracer/ti_bvh.py:10-53) on the device:
  * sizes, builder used (0 host SAH, 1 device linear BVH) and its build time; nodes_out [n_nodes*16] receives the 64-byte nodes

@@ -126,3 +126,38 @@ def test_update_geometry_rebuilds_and_renders_like_a_fresh_scene(Renderer, scene
     still.render_batch(spp)
     assert rel_l2(still.pixels.to_numpy(), ref_img) > 1e-2          # the move is visible: the update really changed the scene
     r.close(); fresh.close(); still.close()
+
+
+@pytest.mark.parametrize("builder", ["sah", "lbvh"])
+def test_refit_geometry_keeps_the_tree_and_renders_like_a_fresh_scene(Renderer, scene_root, builder, monkeypatch):
+    """adapt_refit_geometry: deform and move the 90k-triangle mesh, recompute only the boxes on the device (same node count, same child
+    codes), and get the image of a renderer created on the moved geometry; the refitted boxes enclose every primitive (validate)."""
+    monkeypatch.setenv("ADAPT_TRACE_MODE", "1")                     # the refit path is the binary tree's
+    size, spp = 64, 4
+    e, a, o, c = _load(scene_root, "cbox", "bunny90k.xml", size)
+    r = Renderer(e, a, o, c, seed=5, bvh_builder=builder)
+    r.render_batch(1)
+    first = r.bvh_export()
+    moved = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    big = max(range(len(o)), key=lambda k: o[k].tri_num)
+    p0 = sum(x.tri_num for x in o[:big]); p1 = p0 + o[big].tri_num
+    pr = moved["primitives"][p0:p1]
+    centre = pr.reshape(-1, 3).mean(axis=0)
+    pr[:] = (pr - centre) * np.float32([1.08, 0.94, 1.03]) + centre + np.float32([0.15, 0.1, -0.2])     # squash + move: not a rigid motion
+    e1, e2 = pr[:, 1] - pr[:, 0], pr[:, 2] - pr[:, 0]
+    ng = np.cross(e1, e2); ng /= np.maximum(np.linalg.norm(ng, axis=1, keepdims=True), 1e-20)
+    moved["n_g"][p0:p1] = ng.astype(np.float32)
+    r.update_geometry(moved["primitives"], moved["n_g"], moved["n_s"], refit=True)
+    r.reset_accumulation()
+    r.render_batch(spp)
+    img = r.pixels.to_numpy()
+    again = r.bvh_export()
+    print(f"[{builder}] build {first['build_ms']:.2f} ms, refit {again['build_ms']:.3f} ms, {again['n_nodes']} nodes")
+    assert again["n_nodes"] == first["n_nodes"]
+    np.testing.assert_array_equal(again["nodes"].view(np.uint32)[:, 12:14], first["nodes"].view(np.uint32)[:, 12:14])      # same topology
+    prims, sph = _tables(moved, o)
+    assert validate(again["nodes"], again["prims"], prims, sph)[0] == 0
+    fresh = Renderer(e, moved, o, c, seed=5, bvh_builder=builder)
+    fresh.render_batch(spp)
+    assert np.isfinite(img).all() and rel_l2(img, fresh.pixels.to_numpy()) < 1e-5
+    assert again["build_ms"] < 5.0
