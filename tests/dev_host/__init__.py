@@ -56,12 +56,12 @@ def wavefront_render(packed, n_spp: int, pool_slots: int = 256, trace_grid: int 
         _wf.wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     w, h = packed.desc.width, packed.desc.height
     acc = np.zeros((w, h, 3), np.float32)
-    st = np.zeros(5, np.uint64)
+    st = np.zeros(6, np.uint64)
     rc = _wf.wavefront_render(C.addressof(packed.desc), int(n_spp), int(pool_slots), int(trace_grid), int(cnt_start), acc.ctypes.data_as(C.POINTER(C.c_float)),
                               st.ctypes.data_as(C.POINTER(C.c_uint64)))
     if rc != 0:
         raise RuntimeError(f"emulated wavefront failed ({rc}): no progress" if rc == -1 else f"emulated wavefront failed ({rc})")
-    return acc, dict(paths=int(st[0]), rays_closest=int(st[1]), rays_shadow=int(st[2]), iterations=int(st[3]), launches=int(st[4]))
+    return acc, dict(paths=int(st[0]), rays_closest=int(st[1]), rays_shadow=int(st[2]), iterations=int(st[3]), launches=int(st[4]), rays_culled=int(st[5]))
 
 
 def load():

@@ -82,7 +82,7 @@ void launch_iteration(Wavefront& w) {
 extern "C" {
 
 // Renders n_spp samples of every pixel of the scene with the emulated kernels; film sums are ADDED to accum (w,h,3).
-// stats: [paths done, closest rays, shadow rays / transmittance segments, iterations, kernel launches].  Returns 0, or -1 when the
+// stats: [paths done, closest rays, shadow rays / transmittance segments, iterations, kernel launches, camera rays culled].  Returns 0, or -1 when the
 // wavefront stops making progress.
 int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int trace_grid, int cnt_start, float* accum, uint64_t* stats) {
     Wavefront w;
@@ -124,6 +124,11 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
         w.scene->sv.nodes = reinterpret_cast<const float4*>(w.scene->bvh.nodes.data());
         w.scene->sv.leaf_prims = reinterpret_cast<const float4*>(w.scene->bvh.prims.data());
         w.scene->sv.nodes8 = w.trace_mode == 3 ? reinterpret_cast<const uint4*>(w.scene->bvh.nodes8.data()) : nullptr;
+        // camera rays that miss the padded scene box end in k_logic (adapt_abi.cu: build_accel / adapt_create)
+        const Aabb& rb = br.nodes[0].box;
+        w.scene->sv.world_lo = mk3(rb.lo[0] - 1e-3f, rb.lo[1] - 1e-3f, rb.lo[2] - 1e-3f);
+        w.scene->sv.world_hi = mk3(rb.hi[0] + 1e-3f, rb.hi[1] + 1e-3f, rb.hi[2] + 1e-3f);
+        w.scene->sv.cull_primary = getenv("ADAPT_CULL_PRIMARY") ? atoi(getenv("ADAPT_CULL_PRIMARY")) : 1;
     }
     // pixels owned by this handle: the tile partition's list, or the film / crop window in 4x8 patches (adapt_create)
     if (d->pixel_list && d->n_pixels > 0) w.pixels.assign(d->pixel_list, d->pixel_list + d->n_pixels);
@@ -178,7 +183,8 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     for (size_t k = 0; k < w.accum.size(); k++) accum[k] += w.accum[k];
     if (stats) {
         unsigned long long done = 0; for (const WorkStripe& s : w.work) done += s.done;
-        stats[0] = done; stats[1] = w.ctr.rays_closest; stats[2] = w.ctr.rays_shadow; stats[3] = w.iterations; stats[4] = w.launches;
+        stats[0] = done; stats[1] = w.ctr.rays_closest + w.ctr.rays_culled; stats[2] = w.ctr.rays_shadow; stats[3] = w.iterations; stats[4] = w.launches;
+        stats[5] = w.ctr.rays_culled;       // camera rays answered by the scene-box test in k_logic (counted in stats[1] like adapt_get_stats does)
     }
     delete w.scene;
     return 0;

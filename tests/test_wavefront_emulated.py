@@ -189,3 +189,17 @@ def test_8_wide_tree_volumetric_streams(scene_root, oracle_lib, monkeypatch):
     img, st, ref, cn = _run(scene_root, "test", "media.xml", 12, 12, 2, 256, integrator="vpt")
     match, flipped = _flip(img, ref)
     assert st["paths"] == cn["paths"] and flipped <= 0.02 and rel_l2(img[match], ref[match]) < 2e-5
+
+
+def test_camera_rays_culled_against_the_scene_box(scene_root, oracle_lib, monkeypatch):
+    """A film much wider than the scene: most camera rays miss the scene's bounding box and end in k_logic where they are generated
+    (adapt_create: cull_primary).  Same film, same path and ray counts with the cull on and off."""
+    kw = dict(fov=100.0)
+    on, st_on, ref, cn = _run(scene_root, "cbox", "cbox.xml", 24, 12, 2, 256, **kw)
+    monkeypatch.setenv("ADAPT_CULL_PRIMARY", "0")
+    off, st_off, _, _ = _run(scene_root, "cbox", "cbox.xml", 24, 12, 2, 256, **kw)
+    assert rel_l2(on, off) < 1e-6 and rel_l2(on, ref) < 2e-5
+    assert st_on["paths"] == st_off["paths"] == cn["paths"]
+    assert st_on["rays_closest"] == st_off["rays_closest"] == cn["rays_closest_useful"]     # culled rays are ray_intersect calls too
+    assert st_off["rays_culled"] == 0 and st_on["rays_culled"] > 0.3 * 24 * 12 * 2          # ... that never reach the trace kernel
+    assert st_on["iterations"] <= st_off["iterations"]

@@ -43,7 +43,7 @@ for refill, leaf_t, steps in [(16, 12, 1), (16, 12, 2), (16, 12, 4), (16, 8, 4),
     os.environ.update(ADAPT_REFILL=str(refill), ADAPT_LEAF_T=str(leaf_t), ADAPT_NODE_STEPS=str(steps), ADAPT_TRACE_MODE="3" if WIDE8 else "1")
     L = C.CDLL(lib_path)
     L.wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
-    acc = np.zeros((size, size, 3), np.float32); st = np.zeros(5, np.uint64); ts = np.zeros(8, np.uint64)
+    acc = np.zeros((size, size, 3), np.float32); st = np.zeros(6, np.uint64); ts = np.zeros(8, np.uint64)
     L.wavefront_trace_stats(ts.ctypes.data_as(C.POINTER(C.c_uint64)))
     rc = L.wavefront_render(C.addressof(ps.desc), spp, 2048, 2, 0, acc.ctypes.data_as(C.POINTER(C.c_float)), st.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert rc == 0
