@@ -242,91 +242,25 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
 // ================================================================================================
 namespace {
 
-// leaf record k <- the new vertices of the primitive it names (record word t2.y = primitive id, sphere flag in bit 31 of t2.z)
-__global__ void k_refit_prims(float4* __restrict__ prims, const float* __restrict__ prim9, int n) {
+__global__ void k_refit_prims(float* __restrict__ prims, const float* __restrict__ prim9, int n) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const float4 t2 = prims[(size_t)k * 3 + 2];
-    const int pid = __float_as_int(t2.y);
-    const bool sph = (__float_as_uint(t2.z) & 0x80000000u) != 0u;
-    const float* v = prim9 + (size_t)pid * 9;
-    if (sph) {
-        prims[(size_t)k * 3] = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-        prims[(size_t)k * 3] = make_float4(v[0], v[1], v[2], v[3] - v[0]);
-        prims[(size_t)k * 3 + 1] = make_float4(v[4] - v[1], v[5] - v[2], v[6] - v[0], v[7] - v[1]);
-        prims[(size_t)k * 3 + 2] = make_float4(v[8] - v[2], t2.y, t2.z, t2.w);
-    }
+    if (k < n) lbvh::refit_prim(k, prim9, prims);
 }
-// parent links (node * 2 + child slot) and arrival counters: a node is complete when its own thread has written its leaf children's
-// boxes and every inner child has delivered its box
-__global__ void k_refit_init(const float4* __restrict__ nodes, int n_nodes, int* __restrict__ parent, unsigned* __restrict__ pending) {
+__global__ void k_refit_links(const float* __restrict__ nodes, int n_nodes, int* __restrict__ parent, unsigned* __restrict__ pending) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    const float4 n3 = nodes[(size_t)i * 4 + 3];
-    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-    unsigned p = 1u;
-    if (c0 >= 0) { parent[c0] = i * 2; p++; }
-    if (c1 >= 0 && c1 != c0) { parent[c1] = i * 2 + 1; p++; }
-    pending[i] = p;
-    if (i == 0) parent[0] = -1;
+    if (i < n_nodes) lbvh::refit_links(i, nodes, parent, pending);
 }
-__device__ __forceinline__ void leaf_box(const float4* __restrict__ prims, int code, float lo[3], float hi[3]) {
-    const int first = code >> 3, cnt = (code & 7) + 1;
-    for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; }
-    for (int k = first; k < first + cnt; k++) {
-        const float4 t0 = prims[(size_t)k * 3], t1 = prims[(size_t)k * 3 + 1], t2 = prims[(size_t)k * 3 + 2];
-        float plo[3], phi[3];
-        if (__float_as_uint(t2.z) & 0x80000000u) {
-            const float c[3] = {t0.x, t0.y, t0.z};
-            for (int a = 0; a < 3; a++) { plo[a] = c[a] - t0.w; phi[a] = c[a] + t0.w; }
-        } else {
-            const float v0[3] = {t0.x, t0.y, t0.z}, e1[3] = {t0.w, t1.x, t1.y}, e2[3] = {t1.z, t1.w, t2.x};
-            for (int a = 0; a < 3; a++) {
-                const float p1 = v0[a] + e1[a], p2 = v0[a] + e2[a];
-                plo[a] = fminf(v0[a], fminf(p1, p2)); phi[a] = fmaxf(v0[a], fmaxf(p1, p2));
-                // flat boxes get the reference's pad (bvh_helper.h:36-42); one ulp more than the builder's test because v0 + e only
-                // reproduces the vertex to rounding
-                if (phi[a] - plo[a] < 1.0001e-4f) { plo[a] -= 1e-4f; phi[a] += 1e-4f; }
-            }
-        }
-        for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], plo[a]); hi[a] = fmaxf(hi[a], phi[a]); }
-    }
-}
-// store a child box into slot `child` of node `i`, widened by an ulp like the builder does (bvh_build.cpp: put_box)
-__device__ __forceinline__ void put_child_box(float4* __restrict__ nodes, int i, int child, const float lo[3], const float hi[3]) {
-    float l[3], h[3];
-    for (int a = 0; a < 3; a++) { l[a] = nextafterf(lo[a], -3.0e38f); h[a] = nextafterf(hi[a], 3.0e38f); }
-    float* n = reinterpret_cast<float*>(nodes + (size_t)i * 4);
-    if (child == 0) { n[0] = l[0]; n[1] = h[0]; n[2] = l[1]; n[3] = h[1]; n[8] = l[2]; n[9] = h[2]; }
-    else { n[4] = l[0]; n[5] = h[0]; n[6] = l[1]; n[7] = h[1]; n[10] = l[2]; n[11] = h[2]; }
-}
-__global__ void k_refit_nodes(float4* nodes, int n_nodes, const float4* __restrict__ prims, const int* __restrict__ parent, unsigned* pending) {
+__global__ void k_refit_nodes(float* nodes, int n_nodes, const float* __restrict__ prims, const float* __restrict__ prim9,
+                              const int* __restrict__ parent, unsigned* pending) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
-    {
-        const float4 n3 = nodes[(size_t)i * 4 + 3];
-        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-        float lo[3], hi[3];
-        if (c0 < 0) { leaf_box(prims, ~c0, lo, hi); put_child_box(nodes, i, 0, lo, hi); }
-        if (c1 < 0 && c1 != c0) { leaf_box(prims, ~c1, lo, hi); put_child_box(nodes, i, 1, lo, hi); }
-    }
+    lbvh::refit_leaf_children(i, nodes, prims, prim9);
     // whoever completes a node carries its box to the parent; the other arrivals leave
-    while (true) {
+    while (i >= 0) {
         __threadfence();
         if (atomicSub(&pending[i], 1u) != 1u) return;
         __threadfence();
-        const int pc = parent[i];
-        if (pc < 0) return;                                           // the root is complete
-        const volatile float* n = reinterpret_cast<const volatile float*>(nodes + (size_t)i * 4);
-        const float4 n3 = nodes[(size_t)i * 4 + 3];
-        const bool one_child = __float_as_int(n3.x) == __float_as_int(n3.y);       // synthetic single-leaf root: second box is empty
-        float lo[3], hi[3];
-        lo[0] = one_child ? n[0] : fminf(n[0], n[4]); hi[0] = one_child ? n[1] : fmaxf(n[1], n[5]);
-        lo[1] = one_child ? n[2] : fminf(n[2], n[6]); hi[1] = one_child ? n[3] : fmaxf(n[3], n[7]);
-        lo[2] = one_child ? n[8] : fminf(n[8], n[10]); hi[2] = one_child ? n[9] : fmaxf(n[9], n[11]);
-        put_child_box(nodes, pc >> 1, pc & 1, lo, hi);
-        i = pc >> 1;
+        i = lbvh::refit_carry(i, nodes, parent);
     }
 }
 
@@ -348,9 +282,10 @@ cudaError_t refit_bvh_device(float4* nodes, int32_t n_nodes, float4* leaf_prims,
     LBCK(cudaEventCreate(&e0)); LBCK(cudaEventCreate(&e1));
     LBCK(cudaMemcpyAsync(d_prim9, primitives, (size_t)n_prims * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
     LBCK(cudaEventRecord(e0, st));
-    k_refit_prims<<<lb_grid(n_prims), LB_BLOCK, 0, st>>>(leaf_prims, d_prim9, n_prims);
-    k_refit_init<<<lb_grid(n_nodes), LB_BLOCK, 0, st>>>(nodes, n_nodes, d_parent, d_pending);
-    k_refit_nodes<<<lb_grid(n_nodes), LB_BLOCK, 0, st>>>(nodes, n_nodes, leaf_prims, d_parent, d_pending);
+    float* fnodes = reinterpret_cast<float*>(nodes); float* fprims = reinterpret_cast<float*>(leaf_prims);
+    k_refit_prims<<<lb_grid(n_prims), LB_BLOCK, 0, st>>>(fprims, d_prim9, n_prims);
+    k_refit_links<<<lb_grid(n_nodes), LB_BLOCK, 0, st>>>(fnodes, n_nodes, d_parent, d_pending);
+    k_refit_nodes<<<lb_grid(n_nodes), LB_BLOCK, 0, st>>>(fnodes, n_nodes, fprims, d_prim9, d_parent, d_pending);
     LBCK(cudaEventRecord(e1, st));
     float root[16];
     LBCK(cudaMemcpyAsync(root, nodes, sizeof(root), cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,7 @@
 // serial loops so that the tree logic is covered by `-m "not gpu"` tests.  The harness is test infrastructure only; the
 // library has no CPU build path behind this builder.
 #pragma once
+#include <string.h>
 #include <cstdint>
 #include <cmath>
 
@@ -227,6 +228,88 @@ LB_HD void emit_prim(int k, const uint32_t* __restrict__ order, const float* __r
     g[9] = bits2f(p);
     g[10] = bits2f((uint32_t)obj | (s ? 0x80000000u : 0u));
     g[11] = bits2f(obj_class ? (uint32_t)obj_class[obj] : 0u);
+}
+
+// ---- refit: the same tree over new vertices (adapt_refit_geometry) -------------------------------------------------------------
+// The launch sequence of refit_bvh_device (bvh_device.cu) and of tests/lbvh_host:  refit_prim for every record, refit_links for every
+// node, then for every node refit_leaf_children followed by the climb -- a node is complete once its own thread has written its leaf
+// children's boxes and every inner child has delivered its box (pending[i] arrivals); whoever completes it carries its box into the
+// parent's child slot (refit_carry) and goes on with the parent.
+LB_HD uint32_t f2bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+// leaf record k <- the new vertices of the primitive it names (record word 9 = primitive id, sphere flag in bit 31 of word 10)
+LB_HD void refit_prim(int k, const float* __restrict__ prim9, float* __restrict__ prims) {
+    float* g = prims + (size_t)k * 12;
+    const uint32_t p = f2bits(g[9]);
+    const float* v = prim9 + (size_t)p * 9;
+    if (f2bits(g[10]) & 0x80000000u) {
+        g[0] = v[0]; g[1] = v[1]; g[2] = v[2]; g[3] = v[3];
+    } else {
+        g[0] = v[0]; g[1] = v[1]; g[2] = v[2];
+        g[3] = v[3] - v[0]; g[4] = v[4] - v[1]; g[5] = v[5] - v[2];
+        g[6] = v[6] - v[0]; g[7] = v[7] - v[1]; g[8] = v[8] - v[2];
+    }
+}
+// parent link of node i's inner children (parent * 2 + child slot) and the arrivals node i waits for
+LB_HD void refit_links(int i, const float* __restrict__ nodes, int* __restrict__ parent, uint32_t* __restrict__ pending) {
+    const int32_t* gc = reinterpret_cast<const int32_t*>(nodes + (size_t)i * 16 + 12);
+    const int c0 = gc[0], c1 = gc[1];
+    uint32_t p = 1u;
+    if (c0 >= 0) { parent[c0] = i * 2; p++; }
+    if (c1 >= 0 && c1 != c0) { parent[c1] = i * 2 + 1; p++; }
+    pending[i] = p;
+    if (i == 0) parent[0] = -1;
+}
+// box of a leaf from the NEW vertices of the primitives its records name (the builder's own prim_box rule, flat pad included)
+LB_HD void refit_leaf_box(int code, const float* __restrict__ prims, const float* __restrict__ prim9, float* __restrict__ b) {
+    const int first = code >> 3, cnt = (code & 7) + 1;
+    for (int a = 0; a < 3; a++) { b[a] = 3.0e38f; b[3 + a] = -3.0e38f; }
+    for (int k = first; k < first + cnt; k++) {
+        const float* g = prims + (size_t)k * 12;
+        const uint32_t p = f2bits(g[9]);
+        const float* v = prim9 + (size_t)p * 9;
+        float lo[3], hi[3];
+        if (f2bits(g[10]) & 0x80000000u) {
+            for (int a = 0; a < 3; a++) { lo[a] = v[a] - v[3 + a]; hi[a] = v[a] + v[3 + a]; }
+        } else {
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fminf(v[a], fminf(v[3 + a], v[6 + a]));
+                hi[a] = fmaxf(v[a], fmaxf(v[3 + a], v[6 + a]));
+                if (hi[a] - lo[a] < 1e-4f) { lo[a] -= 1e-4f; hi[a] += 1e-4f; }
+            }
+        }
+        for (int a = 0; a < 3; a++) { b[a] = fminf(b[a], lo[a]); b[3 + a] = fmaxf(b[3 + a], hi[a]); }
+    }
+}
+LB_HD void refit_leaf_children(int i, float* __restrict__ nodes, const float* __restrict__ prims, const float* __restrict__ prim9) {
+    float* g = nodes + (size_t)i * 16;
+    const int32_t* gc = reinterpret_cast<const int32_t*>(g + 12);
+    const int c0 = gc[0], c1 = gc[1];
+    float b[6];
+    if (c0 < 0) { refit_leaf_box(~c0, prims, prim9, b); put_child_box(g, 0, b); }
+    if (c1 < 0 && c1 != c0) { refit_leaf_box(~c1, prims, prim9, b); put_child_box(g, 1, b); }
+}
+// node i is complete: its box (union of its two child boxes; a synthetic single-leaf root has one) goes into its parent's slot.
+// Returns the parent, or -1 at the root.  Reads past L1 on the device (the child boxes were written by other threads of this launch).
+LB_HD int refit_carry(int i, float* nodes, const int* __restrict__ parent) {
+    const int pc = parent[i];
+    if (pc < 0) return -1;
+    const float* g = nodes + (size_t)i * 16;
+    const int32_t* gc = reinterpret_cast<const int32_t*>(g + 12);
+    const bool one = gc[0] == gc[1];
+    float n[12];
+    for (int a = 0; a < 12; a++) n[a] = LB_LD(g + a);
+    float b[6];
+    b[0] = one ? n[0] : fminf(n[0], n[4]); b[3] = one ? n[1] : fmaxf(n[1], n[5]);
+    b[1] = one ? n[2] : fminf(n[2], n[6]); b[4] = one ? n[3] : fmaxf(n[3], n[7]);
+    b[2] = one ? n[8] : fminf(n[8], n[10]); b[5] = one ? n[9] : fmaxf(n[9], n[11]);
+    put_child_box(nodes + (size_t)(pc >> 1) * 16, pc & 1, b);
+    return pc >> 1;
 }
 
 }  // namespace lbvh

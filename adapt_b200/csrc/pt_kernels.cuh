@@ -706,6 +706,11 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
 //   MODE 3: the same scheduler over the compressed 8-wide BVH collapsed from it (pt_trace.cuh: trace_stream_cw8)
 //   (MODE 2 was an uncompressed 4-wide tree: measured equal on orb500k and 6 % slower on bunny90k in round 1, removed)
 // ================================================================================================
+// Measured and rejected in session r02n (profiles/r02n_ab_ray_bins.txt): visiting the slots in an order binned by (direction octant,
+// 16^3 origin cell) instead of slot order -- a counting sort of the live slots before every trace launch.  Coherent warps cut the trace
+// time by 6 % (bunny90k), 7-10 % (orb500k), 8 % (balls-mono), 9 % (car290k); the sort itself (a histogram whose bins are as contended as
+// the camera rays are coherent, a scan, a scatter) cost four times that, and even a sort at the speed of two streaming passes over the
+// pool would only break even.
 struct ClosestSource {
     PathPool pool;
     PT_D unsigned size() const { return (unsigned)pool.n_slots; }

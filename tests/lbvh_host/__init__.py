@@ -81,3 +81,13 @@ def trace_check(nodes, recs, rays_o, rays_d):
     op = np.zeros(nr, np.int32); ot = np.zeros(nr, np.float32); bp = np.zeros(nr, np.int32); bt = np.zeros(nr, np.float32)
     v = L.lbvh_trace_check(_p(nodes), _p(recs), recs.shape[0], _p(ro), _p(rd), nr, _p(op), _p(ot), _p(bp), _p(bt))
     return op, ot, bp, bt, v / 1000.0
+
+
+def refit_tree(tree, prims, order_seed=0):
+    """Refit `tree` (dict from build_tree) IN PLACE over the new vertices `prims` (n,3,3) with the device refit's per-element steps."""
+    L = load()
+    prims = np.ascontiguousarray(prims, np.float32).reshape(-1, 9)
+    rc = L.lbvh_host_refit(_p(tree["nodes"]), tree["nodes"].shape[0], _p(tree["prims"]), prims.shape[0], _p(prims), C.c_uint(order_seed))
+    if rc != 0:
+        raise RuntimeError(f"host refit failed: {rc}")
+    return tree

@@ -213,6 +213,33 @@ int lbvh_trace_check(const float* nodes, const float* prims, int n, const float*
     return n_rays ? (int)(visited * 1000 / n_rays) : 0;
 }
 
+
+// Refit of a tree in the traversal layout over new vertices: the launch sequence of refit_bvh_device (bvh_device.cu) as serial loops --
+// records rewritten, parent links + arrival counters, then per node its leaf children's boxes and the climb (whoever brings a node's
+// counter to zero carries its box into the parent).  `order_seed` permutes the order in which the "threads" run, so the counter logic is
+// exercised with inner children finishing before and after their parents' own threads.  Returns 0, or -1 if a counter ends up non-zero.
+int lbvh_host_refit(float* nodes, int n_nodes, float* prims, int n, const float* prim9, unsigned order_seed) {
+    for (int k = 0; k < n; k++) refit_prim(k, prim9, prims);
+    std::vector<int> parent((size_t)n_nodes, -2);
+    std::vector<uint32_t> pending((size_t)n_nodes, 0);
+    for (int i = 0; i < n_nodes; i++) refit_links(i, nodes, parent.data(), pending.data());
+    std::vector<int> order((size_t)n_nodes);
+    std::iota(order.begin(), order.end(), 0);
+    if (order_seed) {
+        uint64_t s = order_seed * 0x9E3779B97F4A7C15ull + 1;
+        for (int i = n_nodes - 1; i > 0; i--) { s = s * 6364136223846793005ull + 1442695040888963407ull; std::swap(order[i], order[(int)((s >> 33) % (uint64_t)(i + 1))]); }
+    }
+    for (int t : order) {
+        int i = t;
+        refit_leaf_children(i, nodes, prims, prim9);
+        while (i >= 0) {
+            if (--pending[i] != 0u) break;
+            i = refit_carry(i, nodes, parent.data());
+        }
+    }
+    for (int i = 0; i < n_nodes; i++) if (pending[i] != 0u) return -1;
+    return 0;
+}
 }  // extern "C"
 
 // The host SAH builder of the library (bvh_build.cpp) in the same traversal layout, for tree-quality comparisons.

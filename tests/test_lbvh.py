@@ -116,3 +116,43 @@ def test_records_carry_object_and_class():
     assert sorted(pid.tolist()) == list(range(n))
     assert np.array_equal(ob, prim_obj[pid].astype(np.uint32))
     assert np.array_equal(cl, cls[prim_obj[pid]].astype(np.uint32))
+
+
+@pytest.mark.parametrize("builder,seed", [("lbvh", 0), ("lbvh", 7), ("sah", 0), ("sah", 3)])
+def test_refit_keeps_the_topology_and_encloses_the_deformed_mesh(builder, seed):
+    """adapt_refit_geometry's per-element steps (bvh_lbvh.h: refit_*) as serial loops: after a non-rigid deformation the tree has the same
+    child codes, every box encloses what is below it (validate), and closest hits equal brute force bit for bit -- whatever order the
+    nodes' "threads" run in (the arrival counters decide who carries a node's box upwards)."""
+    from lbvh_host import refit_tree
+    prims = _mesh(40, 32)
+    t = build_tree(prims, max_leaf=4, builder=builder)
+    codes = t["nodes"].view(np.uint32)[:, 12:14].copy()
+    v = prims.reshape(-1, 3, 3).copy()
+    c = v.reshape(-1, 3).mean(0)
+    v = ((v - c) * np.float32([1.15, 0.85, 1.05]) + c + np.float32([0.3, -0.2, 0.1]) + 0.03 * np.sin(9 * v[..., [1, 2, 0]])).astype(np.float32)
+    moved = v.reshape(-1, 9)
+    refit_tree(t, moved, order_seed=seed)
+    np.testing.assert_array_equal(t["nodes"].view(np.uint32)[:, 12:14], codes)
+    rc, _ = validate(t["nodes"], t["prims"], moved)
+    assert rc == 0, f"validator code {rc}"
+    ro, rd = _rays(t["prims"], 1200, 5)
+    p, tt, bp, bt, _ = trace_check(t["nodes"], t["prims"], ro, rd)
+    assert np.array_equal(tt, bt) and ((p >= 0) == (bp >= 0)).all() and (p >= 0).sum() > 300
+    # refitting back to the rest pose gives the records of a fresh build bit for bit, and its boxes up to the ulps the refit adds per
+    # level (a node's box is the union of child boxes that were already widened by one ulp when they were stored): never smaller
+    refit_tree(t, prims, order_seed=seed + 1)
+    fresh = build_tree(prims, max_leaf=4, builder=builder)
+    np.testing.assert_array_equal(t["prims"].view(np.uint32), fresh["prims"].view(np.uint32))
+    if builder == "lbvh":
+        lo_cols, hi_cols = [0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9, 11]
+        assert (t["nodes"][:, lo_cols] <= fresh["nodes"][:, lo_cols]).all() and (t["nodes"][:, hi_cols] >= fresh["nodes"][:, hi_cols]).all()
+        np.testing.assert_allclose(t["nodes"][:, :12], fresh["nodes"][:, :12], rtol=1e-5, atol=1e-6)
+
+
+def test_refit_of_a_single_leaf_scene():
+    from lbvh_host import refit_tree
+    prims = _mesh(40, 32)[:3]
+    t = build_tree(prims, max_leaf=4)
+    moved = (prims.reshape(-1, 3, 3) + np.float32([1.0, 2.0, -1.0])).reshape(-1, 9)
+    refit_tree(t, moved)
+    assert validate(t["nodes"], t["prims"], moved)[0] == 0
