@@ -717,12 +717,16 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         Lane& L = h->lanes[l];
         if (l > 0) { CKC(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking)); L.stream = L.own_stream; }
         L.pool.n_slots = P;
-        CKH(dev_alloc(h, &L.pool.ray_o, (size_t)P)); CKH(dev_alloc(h, &L.pool.ray_d, (size_t)P));
-        CKH(dev_alloc(h, &L.pool.hit, (size_t)P)); CKH(dev_alloc(h, &L.pool.thr, (size_t)P));
-        CKH(dev_alloc(h, &L.pool.col, (size_t)P)); CKH(dev_alloc(h, &L.pool.misc, (size_t)P));
-        CKH(dev_alloc(h, &L.pool.rng, (size_t)P));
-        CKC(cudaMemset(L.pool.misc, 0, (size_t)P * sizeof(uint4)));
-        CKC(cudaMemset(L.pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
+        {
+            // one allocation of 6 x P words (pt_common.cuh: PathPool)
+            float4* base = nullptr;
+            CKH(dev_alloc(h, &base, (size_t)P * 6));
+            L.pool.ray_o = base; L.pool.ray_d = base + (size_t)P; L.pool.hit = base + 2 * (size_t)P;
+            L.pool.thr = base + 3 * (size_t)P; L.pool.col = base + 4 * (size_t)P;
+            L.pool.misc = reinterpret_cast<uint4*>(base + 5 * (size_t)P);
+            CKC(cudaMemset(base, 0, (size_t)P * 6 * sizeof(float4)));
+            CKC(cudaMemset(L.pool.ray_o, 0xff, (size_t)P * sizeof(float4)));      // NaN tmax: "o4.w > 0" is false -> nothing traced
+        }
         L.sq.seg_cap = (int)seg_cap;
         L.sq.capacity = (int)Q;
         CKH(dev_alloc(h, &L.sq.o, Q)); CKH(dev_alloc(h, &L.sq.d, Q)); CKH(dev_alloc(h, &L.sq.c, Q));

@@ -129,16 +129,20 @@ struct SceneView {
     int tex_size[3];
 };
 
-// Path pool (SoA, one entry per slot) and queues. All float4 / uint4 so every access is one 128-bit
-// load or store, coalesced across a warp.
+// Path pool (structure of arrays, one entry per slot) and queues.  All float4 / uint4 so every access is one 128-bit load or store,
+// coalesced across a warp (thread t owns slot t: a warp's access is one contiguous 512 bytes).  The 64-bit PCG state rides in the two
+// spare words of ray_d and misc, so a slot is six words and there is no seventh array.
+// Measured and rejected in session r02o (profiles/r02o_ab_pool_layout.txt): the same six words as one 96-byte record per slot, so that the
+// gathered accesses of the class-list launches fetch whole sectors -- slower on every workload (bunny90k 52.95 -> 55.26 ms/step, orb500k
+// 67.86 -> 68.98, car290k 32.17 -> 34.16): the trace kernel's refill loads and every thread-owns-slot access lose their coalescing, which
+// costs more than the half-used sectors of the gathers.
 struct PathPool {
     float4* ray_o;     // (o.xyz, tmax)   tmax < 0: nothing to trace for this slot in this iteration
-    float4* ray_d;     // (d.xyz, -)
-    float4* hit;       // (t, u, v, prim_id bits)   prim_id < 0: miss
-    float4* thr;       // (contribution.rgb, ray_pdf)
-    float4* col;       // (color.rgb, -)   shadow kernel adds NEE payloads here
-    uint4* misc;       // (pixel, sample cnt, bounce | flags << 16, -)
-    uint2* rng;        // PCG32 state
+    float4* ray_d;     // (d.xyz, rng state high word)
+    float4* hit;       // (t, u, v, prim_id | class bits)   prim_id < 0: miss
+    float4* thr;       // (contribution.rgb, ray_pdf)   [vpt: emission weight in .w]
+    float4* col;       // (color.rgb, -)   stays in HBM: emission and the shadow kernel's payloads arrive as REDs
+    uint4* misc;       // (pixel, sample cnt, bounce | flags << 16, rng state low word)
     int n_slots;
 };
 enum : uint32_t { SLOT_ALIVE = 1u << 16, SLOT_SPECULAR = 1u << 17, SLOT_FINISH = 1u << 18 };

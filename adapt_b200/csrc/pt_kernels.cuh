@@ -26,13 +26,10 @@ using namespace adapt;
 #ifndef LOGIC_MIN_BLOCKS_SIMPLE
 #define LOGIC_MIN_BLOCKS_SIMPLE 4
 #endif
-// 1: the non-listed k_logic stages its slot tile in shared memory with bulk copies (TMA path, see k_logic).  Measured and left off
-// (sessions r02d / r02e, bunny90k): k_logic 17.3 -> 18.5 ms/step -- the 23 KB of shared memory per block come out of L1, every warp waits
-// for the whole tile instead of its own 128-byte lines, and the loads were never short of bytes in flight (the kernel issues all six
-// per-slot loads back to back already).
-#ifndef LOGIC_BULK_TILE
-#define LOGIC_BULK_TILE 0
-#endif
+// Measured and rejected for k_logic in sessions r02d / r02e (bunny90k, code removed): the block's 256-slot tile staged in shared memory
+// with six TMA bulk copies (cp.async.bulk + mbarrier, the BulkLoad helper below) issued by one thread at block start: 17.3 -> 18.5
+// ms/step -- the 23 KB per block come out of L1, every warp waits for the whole tile instead of its own 128-byte lines, and the kernel
+// was never short of bytes in flight.
 // Measured and rejected for k_logic in session r02k (profiles/r02k_ab_logic_variants.txt, logic ms/step bunny90k / orb500k / balls-mono,
 // shipped 17.4 / 23.5 / 22.3): requesting a slot's whole state in one batch before the misc word is looked at (18.1 / 25.0 / 23.3 -- the
 // extra live registers cost more than the saved round trip), five resident blocks per SM instead of four (18.0 / 24.2 / 23.0), six (18.8).
@@ -240,30 +237,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         if (!__any_sync(0xffffffffu, slot >= 0)) return;              // past the end of the lists
     }
     const bool listed_idle = LISTED && slot < 0;                      // only in the last warp of a listed launch
-#if LOGIC_BULK_TILE
-    // Thread t owns slot t (not listed): the block's 256-slot tile of the pool -- six contiguous pieces, 22 KB -- comes in with six bulk
-    // copies (TMA path) issued by one thread the moment the block starts, so the whole tile is in flight at once and costs no registers
-    // while it travels; before, every thread read its misc word, waited, and only then issued the other five loads (two dependent HBM
-    // round trips per slot).
-    alignas(128) __shared__ uint4 s_misc[LISTED ? 1 : LOGIC_BLOCK];
-    alignas(128) __shared__ float4 s_hit[LISTED ? 1 : LOGIC_BLOCK], s_ro[LISTED ? 1 : LOGIC_BLOCK], s_rd[LISTED ? 1 : LOGIC_BLOCK], s_thr[LISTED ? 1 : LOGIC_BLOCK];
-    alignas(128) __shared__ uint2 s_rng[LISTED ? 1 : LOGIC_BLOCK];
-    alignas(8) __shared__ unsigned long long s_bar;
-    if (!LISTED) {
-        BulkLoad bl; bl.init(&s_bar);
-        if (threadIdx.x == 0) {
-            const size_t b0 = (size_t)blockIdx.x * LOGIC_BLOCK;
-            bl.expect(LOGIC_BLOCK * (16u * 5u + 8u));
-            bl.copy(s_misc, pool.misc + b0, LOGIC_BLOCK * 16u); bl.copy(s_hit, pool.hit + b0, LOGIC_BLOCK * 16u);
-            bl.copy(s_ro, pool.ray_o + b0, LOGIC_BLOCK * 16u); bl.copy(s_rd, pool.ray_d + b0, LOGIC_BLOCK * 16u);
-            bl.copy(s_thr, pool.thr + b0, LOGIC_BLOCK * 16u); bl.copy(s_rng, pool.rng + b0, LOGIC_BLOCK * 8u);
-        }
-        bl.wait();
-    }
-    uint4 misc = listed_idle ? make_uint4(0u, 0u, 0u, 0u) : (LISTED ? pool.misc[slot] : s_misc[threadIdx.x]);
-#else
     uint4 misc = listed_idle ? make_uint4(0u, 0u, 0u, 0u) : pool.misc[slot];
-#endif
     bool alive = (misc.z & SLOT_ALIVE) != 0;
     // drain phase: a warp with no live path whose stripe (and its next three neighbours) has no work left has nothing to do
     if (!__any_sync(0xffffffffu, alive)) {
@@ -289,16 +263,8 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 
     if (alive) {
         // all per-slot state in one batch of independent 128-bit loads (one memory round trip)
-#if LOGIC_BULK_TILE
-        const float4 h4 = LISTED ? pool.hit[slot] : s_hit[threadIdx.x];
-        const float4 o4 = LISTED ? pool.ray_o[slot] : s_ro[threadIdx.x], d4 = LISTED ? pool.ray_d[slot] : s_rd[threadIdx.x];
-        const float4 t4 = LISTED ? pool.thr[slot] : s_thr[threadIdx.x];
-        const uint2 r2 = LISTED ? pool.rng[slot] : s_rng[threadIdx.x];
-#else
         const float4 h4 = pool.hit[slot];
         const float4 o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
-        const uint2 r2 = pool.rng[slot];
-#endif
         bounce = (int)(misc.z & 0xffffu);
         const int hit_word = __float_as_int(h4.w);
         const int prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
@@ -307,7 +273,7 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         } else {
             ray_o = mk3(o4.x, o4.y, o4.z); ray_d = mk3(d4.x, d4.y, d4.z);
             contribution = mk3(t4.x, t4.y, t4.z); ray_pdf = t4.w;
-            rng.state = ((uint64_t)r2.y << 32) | r2.x;
+            rng.state = ((uint64_t)__float_as_uint(d4.w) << 32) | misc.w;
             bool sphere;
             load_surface(sv, prim, ray_o, ray_d, h4.x, h4.y, h4.z, sf, obj, sphere);
             const int4 oi = __ldg(sv.obj_info + obj);
@@ -462,10 +428,10 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         float tmax = PT_T_INF;
         if (bounce >= sv.max_bounce) { flags |= SLOT_FINISH; tmax = -1.f; }   // the reference's last trace is never used
         pool.ray_o[slot] = make_float4(hit_point.x, hit_point.y, hit_point.z, tmax);
-        pool.ray_d[slot] = make_float4(new_dir.x, new_dir.y, new_dir.z, 0.f);
+        pool.ray_d[slot] = make_float4(new_dir.x, new_dir.y, new_dir.z, __uint_as_float((uint32_t)(rng.state >> 32)));
         pool.thr[slot] = make_float4(contribution.x, contribution.y, contribution.z, new_pdf);
-        pool.rng[slot] = make_uint2((uint32_t)rng.state, (uint32_t)(rng.state >> 32));
         misc.z = (uint32_t)bounce | flags;
+        misc.w = (uint32_t)rng.state;
         pool.misc[slot] = misc;
     }
 
@@ -535,11 +501,10 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
                     // max_bounce <= 0: the reference still traces the primary ray but never enters the loop
                     const bool no_loop = sv.max_bounce <= 0;
                     pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, no_loop ? -1.f : PT_T_INF);
-                    pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+                    pool.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float((uint32_t)(g.state >> 32)));
                     pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
                     pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), 0u);
+                    pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE | (no_loop ? SLOT_FINISH : 0u), (uint32_t)g.state);
                     need = false;
                 }
             } else if (!live || attempt == 3) {
@@ -595,11 +560,10 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
         VolOutcome out = VOL_SPLAT_NOW;
         if (!(misc.z & SLOT_FINISH)) {
             const float4 h4 = pool.hit[slot], o4 = pool.ray_o[slot], d4 = pool.ray_d[slot], t4 = pool.thr[slot];
-            const uint2 r2 = pool.rng[slot];
             p.ray_o = mk3(o4.x, o4.y, o4.z); p.ray_d = mk3(d4.x, d4.y, d4.z);
             p.throughput = mk3(t4.x, t4.y, t4.z); p.emission_weight = t4.w;
             p.bounce = (int)(misc.z & 0xffffu);
-            p.rng.state = ((uint64_t)r2.y << 32) | r2.x;
+            p.rng.state = ((uint64_t)__float_as_uint(d4.w) << 32) | misc.w;
             HitRec h; h.t = h4.x; h.u = h4.y; h.v = h4.z; h.obj = 0; h.cls = 0;
             const int hit_word = __float_as_int(h4.w);
             h.prim = hit_word < 0 ? -1 : (hit_word & PT_HIT_PRIM_MASK);
@@ -617,11 +581,11 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
         } else {
             const bool last = out == VOL_FINISH;                 // over, but this step's transmittance samples still have to land
             pool.ray_o[slot] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, last ? -1.f : PT_T_INF);
-            pool.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, 0.f);
+            pool.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, __uint_as_float((uint32_t)(p.rng.state >> 32)));
             pool.thr[slot] = make_float4(p.throughput.x, p.throughput.y, p.throughput.z, p.emission_weight);
             pool.col[slot] = make_float4(p.color.x, p.color.y, p.color.z, 0.f);
-            pool.rng[slot] = make_uint2((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32));
             misc.z = (uint32_t)p.bounce | SLOT_ALIVE | (last ? SLOT_FINISH : 0u);
+            misc.w = (uint32_t)p.rng.state;
             pool.misc[slot] = misc;
         }
     }
@@ -681,11 +645,10 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
                 const int i = pixel / sv.height, jj = pixel - i * sv.height;
                 const float3 d = camera_ray(sv, g, i, jj, cnt);
                 pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, PT_T_INF);
-                pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+                pool.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float((uint32_t)(g.state >> 32)));
                 pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                     // throughput, emission weight
                 pool.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-                pool.rng[slot] = make_uint2((uint32_t)g.state, (uint32_t)(g.state >> 32));
-                pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE, 0u);
+                pool.misc[slot] = make_uint4((uint32_t)pixel, (uint32_t)cnt, SLOT_ALIVE, (uint32_t)g.state);
                 need = false;
             } else if (!live || attempt == 3) {
                 if (misc.z & SLOT_ALIVE) {

@@ -340,10 +340,11 @@ def run_b200(args):
         logical = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         queue_gbs = queue_bytes_per_launch / (avg_ms * 1e-3) / 1e9
         kern = "k_trace" if fused else "k_closest"
-        # k_logic: 88 B state read + 72 B state write per live slot (the colour word stays in HBM), 48 B per shadow ray written
+        # k_logic: 80 B state read + 64 B state write per live slot (the colour word stays in HBM, the RNG state rides in two spare words),
+        # 48 B per shadow ray written
         pool_slots = int(st.get("pool_slots") or args.pool or int(os.environ.get("ADAPT_POOL", 0)) or 0)
         lanes = int(st.get("lanes") or 1)          # a handle runs `lanes` pools side by side; a launch covers one of them
-        logic_bytes = pool_slots / lanes * 160.0 + shadow_per_launch * 48.0
+        logic_bytes = pool_slots / lanes * 144.0 + shadow_per_launch * 48.0
         # ncu captures (tools/profile_summary.py): DRAM bytes, duration and ray counts of the SAME launches
         cap = cap_logic = None
         if args.workload == "bunny90k" and not args.width and args.integrator == "pt":
@@ -387,6 +388,11 @@ def run_b200(args):
                          "note": "k_trace is latency / issue bound, not HBM bound: the BVH is served by L1/L2, only the ray and hit queues stream through HBM. "
                                  "frac = DRAM side (ncu bytes over the capture's own duration); frac_logical = bytes the reference's unordered traversal would touch "
                                  "(SURVEY 8(d)), not an HBM figure; frac_queue_only = compulsory queue bytes over the live launch duration",
+                         # the whole step: compulsory HBM bytes of both kernels (pool state + queues) over the device-timed step
+                         # (`iters` counts the launches of all ranks; achieved / frac are per GPU)
+                         "step": {"compulsory_bytes_per_step": (logic_bytes + queue_bytes_per_launch) * iters / args.steps,
+                                  "achieved": (logic_bytes + queue_bytes_per_launch) * iters / world / (ms * 1e-3) / 1e9,
+                                  "frac": (logic_bytes + queue_bytes_per_launch) * iters / world / (ms * 1e-3) / 1e9 / peak_gbs},
                          # second kernel of the iteration: streams the whole path pool (HBM-bound by construction)
                          "k_logic": {"achieved": logic_bytes / max(logic_ms * 1e-3, 1e-9) / 1e9,
                                      "frac": logic_bytes / max(logic_ms * 1e-3, 1e-9) / 1e9 / peak_gbs,

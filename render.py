@@ -60,8 +60,8 @@ def write_metrics(path: str, opts, rdr, stats: dict, seconds: float, spp: int, w
         "paths": stats["paths"], "rays_closest": stats["rays_closest"], "rays_shadow": stats["rays_shadow"],
         "iterations": stats["iterations"], "kernel_launches": stats["kernel_launches"],
         "stage_ms": {"logic": logic_ms, "trace": trace_ms},
-        # k_logic streams the pool: 88 B read + 72 B written per slot and launch
-        "k_logic_hbm_gbs": (stats["iterations"] * pool * 160.0 / (logic_ms * 1e-3) / 1e9) if logic_ms > 0 else None,
+        # k_logic streams the pool: 80 B read + 64 B written per slot and launch
+        "k_logic_hbm_gbs": (stats["iterations"] * pool * 144.0 / (logic_ms * 1e-3) / 1e9) if logic_ms > 0 else None,
         "bvh": {k: v for k, v in rdr.bvh_export(arrays=False).items() if k in ("builder", "n_nodes", "depth", "build_ms")},
     }
     with open(path, "w") as f:

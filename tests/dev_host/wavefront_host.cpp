@@ -17,8 +17,7 @@ template <typename T> T* zeros(std::vector<T>& v, size_t n) { v.assign(n, T()); 
 struct Wavefront {
     DevHost* scene = nullptr;
     PathPool pool{}; ShadowQueue sq{};
-    std::vector<float4> ray_o, ray_d, hit, thr, col, sq_o, sq_d, sq_c;
-    std::vector<uint4> misc; std::vector<uint2> rng;
+    std::vector<float4> pool_words, sq_o, sq_d, sq_c;
     std::vector<CursorStripe> seg_count, cls_count;
     std::vector<unsigned> cls_items;
     std::vector<WorkStripe> work;
@@ -144,9 +143,13 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
     int P = std::max(pool_slots, LOGIC_BLOCK);
     P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
     w.pool.n_slots = P;
-    w.pool.ray_o = zeros(w.ray_o, P); w.pool.ray_d = zeros(w.ray_d, P); w.pool.hit = zeros(w.hit, P); w.pool.thr = zeros(w.thr, P);
-    w.pool.col = zeros(w.col, P); w.pool.misc = zeros(w.misc, P); w.pool.rng = zeros(w.rng, P);
-    memset(w.ray_o.data(), 0xff, (size_t)P * sizeof(float4));                  // NaN tmax: nothing to trace
+    {
+        // adapt_create: one allocation of six words per slot
+        float4* base = zeros(w.pool_words, (size_t)P * 6);
+        w.pool.ray_o = base; w.pool.ray_d = base + (size_t)P; w.pool.hit = base + 2 * (size_t)P; w.pool.thr = base + 3 * (size_t)P;
+        w.pool.col = base + 4 * (size_t)P; w.pool.misc = reinterpret_cast<uint4*>(base + 5 * (size_t)P);
+        memset(w.pool.ray_o, 0xff, (size_t)P * sizeof(float4));                    // NaN tmax: nothing to trace
+    }
     const size_t extra_warps = getenv("WF_OLD_SEGCAP") ? 0 : (w.logic_lists ? 8 : 0);       // adapt_create: slack for the per-group launches
     const size_t seg_cap = (((size_t)P / 32 + PT_NCURSOR - 1) / PT_NCURSOR + extra_warps) * 32 * (size_t)std::max(1, d->num_shadow_ray);
     const size_t Q = seg_cap * PT_NCURSOR;
