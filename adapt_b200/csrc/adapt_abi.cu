@@ -119,7 +119,7 @@ struct adapt_handle {
     bool want_wide = false;
     int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt / k_trace_vpt)
     VolumeView vv{};
-    int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH (bvh_device.cu)
+    int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH, 2 device binned SAH (bvh_device.cu)
     int bvh_nodes = 0, bvh_depth = 0;
     float bvh_build_ms = 0.f;
     BuildParams bvh_params;
@@ -416,11 +416,11 @@ static int build_accel(adapt_handle* h, const float* primitives) {
     auto drop_new = [&]() { dev_release(h, new_nodes); dev_release(h, new_nodes8); dev_release(h, new_prims); };
     bool wide_ok = true; int n_nodes = 0, depth = 0; float build_ms = 0.f;
     float root_lo[3], root_hi[3];
-    if (h->bvh_builder == 1) {
-        // device build: linear BVH straight into the traversal layout; no 8-wide tree
+    if (h->bvh_builder >= 1) {
+        // device build: linear BVH or binned SAH straight into the traversal layout; no 8-wide tree
         DeviceBvh db; std::string what;
         cudaError_t be = build_bvh_device(primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), np, no, h->bvh_params.max_leaf,
-                                          h->stream, db, what);
+                                          h->stream, db, what, h->bvh_builder, h->bvh_params.traverse_cost);
         if (be != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH build: " + what + ": " + cudaGetErrorString(be));
         h->allocs.push_back(db.nodes); h->allocs.push_back(db.leaf_prims);
         new_nodes = db.nodes; new_prims = db.leaf_prims;
@@ -586,7 +586,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     }
     if (np >= (1 << PT_HIT_PRIM_BITS)) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: more than 2^27 primitives"));
     h->bvh_builder = d->bvh_builder ? d->bvh_builder : env_int("ADAPT_BVH_BUILDER", 0);
-    if (h->bvh_builder != 0 && h->bvh_builder != 1) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (host SAH) or 1 (device LBVH)"));
+    if (h->bvh_builder < 0 || h->bvh_builder > 2) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (host SAH), 1 (device LBVH) or 2 (device SAH)"));
     SceneView& sv = h->sv;
     sv.n_objects = no; sv.n_prims = np;
     // traversal: 1 = binary BVH, 3 = compressed 8-wide BVH collapsed from it (host builder only), 0 = baseline without lane refill.

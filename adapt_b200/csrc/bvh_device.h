@@ -20,7 +20,10 @@ struct DeviceBvh {
 // of each object [n_objects].  Runs on `stream` and synchronises it.  Returns cudaSuccess or the failing call's error;
 // `what` then names the call.
 cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj, const uint8_t* obj_class,
-                             int32_t n, int32_t n_objects, int max_leaf, cudaStream_t stream, DeviceBvh& out, std::string& what);
+                             int32_t n, int32_t n_objects, int max_leaf, cudaStream_t stream, DeviceBvh& out, std::string& what,
+                             int builder = 1, float traverse_cost = 1.0f);
+// builder: 1 = linear BVH (Morton order, one sort; fastest build), 2 = top-down binned SAH (level-synchronous; the host builder's
+// tree quality at a fraction of its build time).  Both go through the same bottom-up fit and emission.
 
 }  // namespace adapt
 

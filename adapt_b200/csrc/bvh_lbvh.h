@@ -33,6 +33,24 @@
 #define LB_CLZ32(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
 #endif
 
+// atomics of the device builders (plain read-modify-writes in the serial CPU harness) and arithmetic that is never contracted into
+// FMAs, so that g++ and nvcc round alike wherever a decision hangs on the result
+#if defined(__CUDA_ARCH__)
+#define LB_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define LB_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define LB_ATOMIC_INC(p) atomicAdd((p), 1u)
+#define LB_FMUL(a, b) __fmul_rn((a), (b))        // never contracted: sah_bin and sah_flag must put a primitive into the same bin
+#define LB_FSUB(a, b) __fsub_rn((a), (b))
+#define LB_FADD(a, b) __fadd_rn((a), (b))
+#else
+#define LB_ATOMIC_MIN(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
+#define LB_ATOMIC_MAX(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
+#define LB_ATOMIC_INC(p) (++*(p))
+#define LB_FMUL(a, b) ((a) * (b))
+#define LB_FSUB(a, b) ((a) - (b))
+#define LB_FADD(a, b) ((a) + (b))
+#endif
+
 namespace adapt {
 namespace lbvh {
 
@@ -65,9 +83,19 @@ LB_HD float next_down(float x) { return nextafterf(x, -3.0e38f); }
 LB_HD float next_up(float x) { return nextafterf(x, 3.0e38f); }
 
 // ---- step 1: primitive box (lo.xyz, hi.xyz) -----------------------------------------------------------------------
-LB_HD void prim_box(const float* __restrict__ prim9, const uint8_t* __restrict__ sph, int i, float* __restrict__ pbox) {
+// pcen (optional): the point that stands for the primitive when ranges are split.  vertex_mean: the mean of a triangle's vertices (a
+// sphere's centre), as bvh_build.cpp::prim_bounds -- what the SAH builder needs: the two triangles of a quad share their box, and no
+// plane separates equal box centres (90k-triangle mesh, SAH cost of the inner nodes: 16.7 with box centres, 14.3 with vertex means,
+// the host builder's figure).  Otherwise the box centre -- what the linear BVH wants: equal keys keep such pairs together in its
+// always-full leaves (leaf cost 5.9 against 11.0 with vertex means).
+LB_HD void prim_box(const float* __restrict__ prim9, const uint8_t* __restrict__ sph, int i, float* __restrict__ pbox,
+                    float* __restrict__ pcen = nullptr, bool vertex_mean = false) {
     const float* p = prim9 + (size_t)i * 9;
     float lo[3], hi[3];
+    if (pcen && vertex_mean) {
+        const bool s = sph && sph[i];
+        for (int a = 0; a < 3; a++) pcen[(size_t)i * 3 + a] = s ? p[a] : LB_FMUL(LB_FADD(LB_FADD(p[a], p[3 + a]), p[6 + a]), 1.0f / 3.0f);
+    }
     if (sph && sph[i]) {
         for (int a = 0; a < 3; a++) { lo[a] = p[a] - p[3 + a]; hi[a] = p[a] + p[3 + a]; }
     } else {
@@ -79,9 +107,10 @@ LB_HD void prim_box(const float* __restrict__ prim9, const uint8_t* __restrict__
     }
     float* b = pbox + (size_t)i * 6;
     for (int a = 0; a < 3; a++) { b[a] = lo[a]; b[3 + a] = hi[a]; }
+    if (pcen && !vertex_mean) for (int a = 0; a < 3; a++) pcen[(size_t)i * 3 + a] = LB_FMUL(0.5f, LB_FADD(lo[a], hi[a]));
 }
 
-// ---- step 2: 63-bit Morton key of the box centre inside the bounds of all centres ---------------------------------
+// ---- step 2: 63-bit Morton key of the primitive's centre inside the bounds of all centres ---------------------------------
 LB_HD uint64_t spread21(uint32_t v) {          // 21 bits -> every third bit of 63
     uint64_t x = v & 0x1fffffu;
     x = (x | (x << 32)) & 0x1f00000000ffffull;
@@ -91,11 +120,10 @@ LB_HD uint64_t spread21(uint32_t v) {          // 21 bits -> every third bit of 
     x = (x | (x << 2)) & 0x1249249249249249ull;
     return x;
 }
-LB_HD uint64_t morton_key(const float* __restrict__ pbox, int i, const float* __restrict__ cen_lo, const float* __restrict__ cen_inv) {
-    const float* b = pbox + (size_t)i * 6;
+LB_HD uint64_t morton_key(const float* __restrict__ pcen, int i, const float* __restrict__ cen_lo, const float* __restrict__ cen_inv) {
     uint32_t q[3];
     for (int a = 0; a < 3; a++) {
-        float c = 0.5f * (b[a] + b[3 + a]);
+        float c = pcen[(size_t)i * 3 + a];
         float t = (c - cen_lo[a]) * cen_inv[a];                  // 0..1
         t = fminf(fmaxf(t, 0.f), 1.f) * 2097151.f;
         q[a] = (uint32_t)t;
@@ -152,9 +180,11 @@ LB_HD void child_box(int c, const float* __restrict__ pbox, const uint32_t* __re
         for (int a = 0; a < 6; a++) b[a] = LB_LD(s + a);
     }
 }
+// keep[i] != 0: inner node i is emitted; otherwise the sub-tree below it is one leaf.  The linear BVH keeps every node over more than
+// max_leaf primitives (keep_by_size); the SAH builder decides node by node.
 LB_HD void fit_node(int cur, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rng_first,
                     const int* __restrict__ rng_last, const float* __restrict__ pbox, const uint32_t* __restrict__ order,
-                    float* __restrict__ ibox, int* __restrict__ height, int max_leaf) {
+                    float* __restrict__ ibox, int* __restrict__ height, const uint32_t* __restrict__ keep) {
     float a[6], b[6];
     const int cl = left[cur], cr = right[cur];
     child_box(cl, pbox, order, ibox, a);
@@ -162,19 +192,17 @@ LB_HD void fit_node(int cur, const int* __restrict__ left, const int* __restrict
     float* o = ibox + (size_t)cur * 6;
     for (int k = 0; k < 3; k++) { o[k] = fminf(a[k], b[k]); o[3 + k] = fmaxf(a[3 + k], b[3 + k]); }
     int hl = cl < 0 ? 0 : LB_LD(height + cl), hr = cr < 0 ? 0 : LB_LD(height + cr);
-    const int size = rng_last[cur] - rng_first[cur] + 1;
-    height[cur] = size > max_leaf ? 1 + (hl > hr ? hl : hr) : 0;
+    height[cur] = keep[cur] ? 1 + (hl > hr ? hl : hr) : 0;
 }
 
 // ---- step 5: emission into the traversal layout --------------------------------------------------------------------
-LB_HD bool is_emitted(const int* __restrict__ rng_first, const int* __restrict__ rng_last, int i, int max_leaf) {
+LB_HD bool keep_by_size(const int* __restrict__ rng_first, const int* __restrict__ rng_last, int i, int max_leaf) {
     return rng_last[i] - rng_first[i] + 1 > max_leaf;
 }
 LB_HD int child_code(int c, const int* __restrict__ rng_first, const int* __restrict__ rng_last, const uint32_t* __restrict__ dense,
-                     int max_leaf) {
+                     const uint32_t* __restrict__ keep) {
     if (c < 0) return ~(((~c) << 3) | 0);
-    const int size = rng_last[c] - rng_first[c] + 1;
-    if (size <= max_leaf) return ~((rng_first[c] << 3) | (size - 1));
+    if (!keep[c]) return ~((rng_first[c] << 3) | (rng_last[c] - rng_first[c]));
     return (int)dense[c];
 }
 // node16: 16 floats of one 64-byte node (bvh_build.h: GpuNode)
@@ -186,8 +214,9 @@ LB_HD void put_child_box(float* __restrict__ node16, int child, const float* __r
 }
 LB_HD void emit_node(int i, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rng_first,
                      const int* __restrict__ rng_last, const float* __restrict__ pbox, const uint32_t* __restrict__ order,
-                     const float* __restrict__ ibox, const uint32_t* __restrict__ dense, int max_leaf, float* __restrict__ nodes) {
-    if (!is_emitted(rng_first, rng_last, i, max_leaf)) return;
+                     const float* __restrict__ ibox, const uint32_t* __restrict__ dense, const uint32_t* __restrict__ keep,
+                     float* __restrict__ nodes) {
+    if (!keep[i]) return;
     float* g = nodes + (size_t)dense[i] * 16;
     float a[6], b[6];
     child_box(left[i], pbox, order, ibox, a);
@@ -195,8 +224,8 @@ LB_HD void emit_node(int i, const int* __restrict__ left, const int* __restrict_
     put_child_box(g, 0, a);
     put_child_box(g, 1, b);
     int32_t* gc = reinterpret_cast<int32_t*>(g + 12);
-    gc[0] = child_code(left[i], rng_first, rng_last, dense, max_leaf);
-    gc[1] = child_code(right[i], rng_first, rng_last, dense, max_leaf);
+    gc[0] = child_code(left[i], rng_first, rng_last, dense, keep);
+    gc[1] = child_code(right[i], rng_first, rng_last, dense, keep);
     gc[2] = 0; gc[3] = 0;
 }
 // root of a scene with at most max_leaf primitives: one leaf, second child an empty box (to_gpu_layout's single-leaf case)
@@ -228,6 +257,300 @@ LB_HD void emit_prim(int k, const uint32_t* __restrict__ order, const float* __r
     g[9] = bits2f(p);
     g[10] = bits2f((uint32_t)obj | (s ? 0x80000000u : 0u));
     g[11] = bits2f(obj_class ? (uint32_t)obj_class[obj] : 0u);
+}
+
+// ---- top-down binned SAH on the device (builder 2): the same intermediate representation, a better tree ----------------------------
+// The radix tree splits a range where the Morton keys' highest differing bit says; this builder splits it where the surface-area
+// heuristic says (16 bins on each of the three axes over the range's centre bounds, like the host builder bvh_build.cpp:44-83) and
+// hands the rest of the pipeline -- fit_node, the dense numbering, emit_node, emit_prim -- the same arrays the radix tree would:
+// a permutation `order` of the primitives and, for each of the n - 1 inner nodes, children / range / parent.  An inner node that
+// splits positions [first, last] between g and g + 1 gets the id g (every adjacent pair of positions is separated by exactly one node,
+// so ids are unique in [0, n - 2]); the root swaps ids with whoever would be 0, because the emitted tree starts at node 0.
+//
+// Level-synchronous: all ranges ("segments") of more than max_leaf primitives that exist at one depth are processed by the same
+// launches.  Per level:  sah_clear_bins (per bin)  ->  sah_bin (per position: 7 atomics per axis into its segment's bins)  ->
+// sah_split (per segment: best plane; node record; sub-trees of <= max_leaf primitives finished on the spot, they collapse into one leaf at
+// emission)  ->  sah_flag (per position: goes left? | new-segment count at segment heads)  ->  exclusive scan (CUB on the device)  ->
+// sah_spawn (per segment: the next level's segments)  ->  sah_scatter (per position: stable partition through the scan; centre bounds
+// of the child segment by atomics).  The partition is stable and the numbering comes from scans, so the tree does not depend on the
+// order in which threads run: the device-built tree equals the one tests/lbvh_host builds with serial loops, bit for bit.
+#define LB_SAH_BINS 16
+
+// one level's segments: [first, last] positions, parent = (inner node id) * 2 + child slot (-1: the root), centre bounds as f2ord keys
+struct SahSegs {
+    int* first; int* last; int* parent; uint32_t* cb;      // cb: [s * 6] = lo.xyz, hi.xyz
+};
+// split of each segment of the current level, and where its children go
+struct SahSplit {
+    int* axis;      // -1: no plane separates the centres -> split by position, no reordering
+    int* bin;       // primitives whose bin on `axis` is <= bin go left
+    int* nl;        // primitives going left
+    int* child;     // [s * 2] segment index of the left / right child in the next level, -1 when it has <= max_leaf primitives
+};
+struct SahTree {    // the intermediate representation of `hierarchy` above
+    int* left; int* right; int* rng_first; int* rng_last; int* parent_inner; int* parent_leaf;
+    uint32_t* keep;                                         // node is emitted (see fit_node)
+    int* root_gamma;                                        // split position of the root (written by level 0)
+    int* small_last; int* small_parent;                     // [position]: a range of 2..max_leaf primitives starts here (last position, parent * 2 + slot)
+    float traverse_cost;                                    // cost of an inner node against one primitive test (bvh_build.h: BuildParams)
+};
+
+LB_HD void sah_frame(const uint32_t* __restrict__ cb6, int a, float& lo, float& scale) {
+    lo = ord2f(cb6[a]);
+    const float ext = LB_FSUB(ord2f(cb6[3 + a]), lo);
+    scale = ext > 1e-12f ? (float)LB_SAH_BINS / ext : 0.f;          // 0: every centre in one plane, no split on this axis
+}
+LB_HD int sah_bin_of(float c, float lo, float scale) {
+    const int b = (int)LB_FMUL(LB_FSUB(c, lo), scale);
+    return b < 0 ? 0 : (b > LB_SAH_BINS - 1 ? LB_SAH_BINS - 1 : b);
+}
+LB_HD int sah_node_id(int gamma, int root_gamma) { return gamma == root_gamma ? 0 : (gamma == 0 ? root_gamma : gamma); }
+
+// bins: cnt[(s * 3 + axis) * BINS + b], box[((s * 3 + axis) * BINS + b) * 6 + (lo.xyz, hi.xyz)] as f2ord keys
+LB_HD void sah_clear_bin(int j, uint32_t* __restrict__ cnt, uint32_t* __restrict__ box) {
+    cnt[j] = 0u;
+    uint32_t* b = box + (size_t)j * 6;
+    b[0] = b[1] = b[2] = 0xffffffffu; b[3] = b[4] = b[5] = 0u;
+}
+// seg_base: the segment whose bins start at cnt[0] / box[0] (0 for the global arrays; a block whose positions all belong to one segment
+// bins into a private copy in shared memory first, bvh_device.cu)
+LB_HD void sah_bin(int k, const int* __restrict__ pseg, const uint32_t* __restrict__ order, const float* __restrict__ pbox,
+                   const float* __restrict__ pcen, const uint32_t* __restrict__ seg_cb, uint32_t* cnt, uint32_t* box, int seg_base = 0) {
+    const int s = pseg[k];
+    if (s < 0) return;
+    const float* b6 = pbox + (size_t)order[k] * 6;
+    const float* c3 = pcen + (size_t)order[k] * 3;
+    uint32_t key[6];
+    for (int j = 0; j < 6; j++) key[j] = f2ord(b6[j]);
+    for (int a = 0; a < 3; a++) {
+        float lo, scale;
+        sah_frame(seg_cb + (size_t)s * 6, a, lo, scale);
+        if (scale == 0.f) continue;
+        const size_t j = ((size_t)(s - seg_base) * 3 + a) * LB_SAH_BINS + sah_bin_of(c3[a], lo, scale);
+        LB_ATOMIC_INC(cnt + j);
+        uint32_t* b = box + j * 6;
+        LB_ATOMIC_MIN(b + 0, key[0]); LB_ATOMIC_MIN(b + 1, key[1]); LB_ATOMIC_MIN(b + 2, key[2]);
+        LB_ATOMIC_MAX(b + 3, key[3]); LB_ATOMIC_MAX(b + 4, key[4]); LB_ATOMIC_MAX(b + 5, key[5]);
+    }
+}
+
+struct SahBox { float lo[3], hi[3]; };
+LB_HD void sah_box_reset(SahBox& b) { for (int a = 0; a < 3; a++) { b.lo[a] = 3.0e38f; b.hi[a] = -3.0e38f; } }
+LB_HD void sah_box_grow(SahBox& b, const uint32_t* k6) {
+    for (int a = 0; a < 3; a++) { b.lo[a] = fminf(b.lo[a], ord2f(k6[a])); b.hi[a] = fmaxf(b.hi[a], ord2f(k6[3 + a])); }
+}
+LB_HD float sah_half_area(const SahBox& b) {              // never contracted: the CPU harness and the B200 must rank the planes alike
+    const float dx = LB_FSUB(b.hi[0], b.lo[0]), dy = LB_FSUB(b.hi[1], b.lo[1]), dz = LB_FSUB(b.hi[2], b.lo[2]);
+    return LB_FADD(LB_FADD(LB_FMUL(dx, dy), LB_FMUL(dy, dz)), LB_FMUL(dz, dx));
+}
+LB_HD float sah_cost(float area_l, int nl, float area_r, int nr) { return LB_FADD(LB_FMUL(area_l, (float)nl), LB_FMUL(area_r, (float)nr)); }
+
+// A range of at most max_leaf (<= 8) primitives below inner node `pid`: split by position down to single primitives, so that the
+// representation stays a full binary tree; none of these nodes is emitted (is_emitted), fit_node still walks through them.
+LB_HD void sah_small_subtree(int first, int last, int pid, int side, int root_gamma, const SahTree& T) {
+    int st_f[8], st_l[8], st_p[8], st_s[8], sp = 0;
+    st_f[0] = first; st_l[0] = last; st_p[0] = pid; st_s[0] = side; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int f = st_f[sp], l = st_l[sp], p = st_p[sp], sd = st_s[sp];
+        if (f == l) {
+            if (sd) T.right[p] = ~f; else T.left[p] = ~f;
+            T.parent_leaf[f] = p;
+            continue;
+        }
+        const int g = f + (l - f + 1) / 2 - 1;
+        const int id = sah_node_id(g, root_gamma);
+        T.rng_first[id] = f; T.rng_last[id] = l; T.parent_inner[id] = p; T.keep[id] = 0u;
+        if (sd) T.right[p] = id; else T.left[p] = id;
+        st_f[sp] = f; st_l[sp] = g; st_p[sp] = id; st_s[sp] = 0; sp++;
+        st_f[sp] = g + 1; st_l[sp] = l; st_p[sp] = id; st_s[sp] = 1; sp++;
+    }
+}
+
+// best plane of segment s (surface-area heuristic over the bins), its node record, and its small children
+LB_HD void sah_split(int s, int level, const SahSegs& S, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ box, int max_leaf,
+                     const SahSplit& X, const SahTree& T) {
+    const int first = S.first[s], last = S.last[s], count = last - first + 1;
+    float best = 3.0e38f; int best_axis = -1, best_bin = -1, best_nl = 0;
+    for (int a = 0; a < 3; a++) {
+        float lo, scale;
+        sah_frame(S.cb + (size_t)s * 6, a, lo, scale);
+        if (scale == 0.f) continue;
+        const size_t j0 = ((size_t)s * 3 + a) * LB_SAH_BINS;
+        // all 7 x 16 words of this axis requested before the first one is used (one round trip to L2 instead of one per bin)
+        uint32_t c16[LB_SAH_BINS], k16[LB_SAH_BINS][6];
+        #pragma unroll
+        for (int b = 0; b < LB_SAH_BINS; b++) c16[b] = LB_LD(cnt + j0 + b);
+        #pragma unroll
+        for (int b = 0; b < LB_SAH_BINS; b++)
+            #pragma unroll
+            for (int q = 0; q < 6; q++) k16[b][q] = LB_LD(box + (j0 + b) * 6 + q);
+        float right_area[LB_SAH_BINS];
+        SahBox acc; sah_box_reset(acc);
+        #pragma unroll
+        for (int b = LB_SAH_BINS - 1; b > 0; b--) {
+            if (c16[b]) sah_box_grow(acc, k16[b]);
+            right_area[b] = sah_half_area(acc);
+        }
+        sah_box_reset(acc);
+        int nl = 0;
+        #pragma unroll
+        for (int b = 0; b < LB_SAH_BINS - 1; b++) {
+            const int c = (int)c16[b];
+            if (c) sah_box_grow(acc, k16[b]);
+            nl += c;
+            const int nr = count - nl;
+            if (nl == 0 || nr == 0) continue;
+            const float cost = sah_cost(sah_half_area(acc), nl, right_area[b + 1], nr);
+            if (cost < best) { best = cost; best_axis = a; best_bin = b; best_nl = nl; }
+        }
+    }
+    if (best_axis < 0) best_nl = count / 2;                             // coincident centres: split by position
+    X.axis[s] = best_axis; X.bin[s] = best_bin; X.nl[s] = best_nl;
+    const int gamma = first + best_nl - 1;
+    if (level == 0) *T.root_gamma = gamma;
+    const int rg = level == 0 ? gamma : LB_LD(T.root_gamma);
+    const int id = sah_node_id(gamma, rg);
+    T.rng_first[id] = first; T.rng_last[id] = last; T.keep[id] = 1u;     // more than max_leaf primitives: always an inner node
+    const int par = S.parent[s];
+    if (par < 0) T.parent_inner[id] = -1;
+    else {
+        T.parent_inner[id] = par >> 1;
+        if (par & 1) T.right[par >> 1] = id; else T.left[par >> 1] = id;
+    }
+    // children of one primitive are leaves; ranges of 2..max_leaf primitives are finished by sah_small once the scatter has filled them
+    for (int side = 0; side < 2; side++) {
+        const int cf = side ? gamma + 1 : first, cl = side ? last : gamma, m = cl - cf + 1;
+        if (m == 1) { if (side) T.right[id] = ~cf; else T.left[id] = ~cf; T.parent_leaf[cf] = id; }
+        else if (m <= max_leaf) { T.small_last[cf] = cl; T.small_parent[cf] = id * 2 + side; }
+    }
+}
+
+// A range of 2..max_leaf (<= 8) primitives, one thread: the surface-area heuristic decides between a leaf and a split like the host
+// builder does (bvh_build.cpp: `best_cost < count`), here with an exact sweep over the sorted centres instead of bins.  Kept nodes
+// reorder their positions in `order` (which must be the buffer the level's scatter wrote).
+LB_HD void sah_small(int k, uint32_t* order, const float* __restrict__ pbox, const float* __restrict__ pcen, const SahTree& T) {
+    const int last0 = T.small_last[k];
+    if (last0 < 0) return;
+    T.small_last[k] = -1;
+    const int rg = LB_LD(T.root_gamma);
+    int st_f[8], st_l[8], st_p[8], st_s[8], sp = 0;
+    st_f[0] = k; st_l[0] = last0; st_p[0] = T.small_parent[k] >> 1; st_s[0] = T.small_parent[k] & 1; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int f = st_f[sp], l = st_l[sp], pid = st_p[sp], sd = st_s[sp], m = l - f + 1;
+        if (m == 1) {
+            if (sd) T.right[pid] = ~f; else T.left[pid] = ~f;
+            T.parent_leaf[f] = pid;
+            continue;
+        }
+        uint32_t pr[8]; SahBox bx[8]; float cn[8][3]; SahBox all; sah_box_reset(all);
+        for (int i = 0; i < m; i++) {
+            pr[i] = order[f + i];
+            const float* b6 = pbox + (size_t)pr[i] * 6;
+            for (int a = 0; a < 3; a++) cn[i][a] = pcen[(size_t)pr[i] * 3 + a];
+            for (int a = 0; a < 3; a++) { bx[i].lo[a] = b6[a]; bx[i].hi[a] = b6[3 + a]; all.lo[a] = fminf(all.lo[a], b6[a]); all.hi[a] = fmaxf(all.hi[a], b6[3 + a]); }
+        }
+        float best = 3.0e38f; int best_axis = -1, best_nl = 0; int best_perm[8];
+        for (int a = 0; a < 3; a++) {
+            int perm[8];
+            for (int i = 0; i < m; i++) {                                   // stable insertion sort by centre
+                const float c = cn[i][a];
+                int j = i;
+                while (j > 0 && cn[perm[j - 1]][a] > c) { perm[j] = perm[j - 1]; j--; }
+                perm[j] = i;
+            }
+            float right_area[8];
+            SahBox acc; sah_box_reset(acc);
+            for (int i = m - 1; i > 0; i--) {
+                for (int q = 0; q < 3; q++) { acc.lo[q] = fminf(acc.lo[q], bx[perm[i]].lo[q]); acc.hi[q] = fmaxf(acc.hi[q], bx[perm[i]].hi[q]); }
+                right_area[i] = sah_half_area(acc);
+            }
+            sah_box_reset(acc);
+            for (int i = 0; i < m - 1; i++) {
+                for (int q = 0; q < 3; q++) { acc.lo[q] = fminf(acc.lo[q], bx[perm[i]].lo[q]); acc.hi[q] = fmaxf(acc.hi[q], bx[perm[i]].hi[q]); }
+                const float cost = sah_cost(sah_half_area(acc), i + 1, right_area[i + 1], m - 1 - i);
+                if (cost < best) { best = cost; best_axis = a; best_nl = i + 1; for (int q = 0; q < m; q++) best_perm[q] = perm[q]; }
+            }
+        }
+        // split when  traverse_cost + best / area(range) < m   (one primitive test = 1)
+        const float budget = LB_FMUL(LB_FSUB((float)m, T.traverse_cost), sah_half_area(all));
+        if (best_axis < 0 || !(best < budget)) { sah_small_subtree(f, l, pid, sd, rg, T); continue; }
+        for (int i = 0; i < m; i++) order[f + i] = pr[best_perm[i]];
+        const int g = f + best_nl - 1;
+        const int id = sah_node_id(g, rg);
+        T.rng_first[id] = f; T.rng_last[id] = l; T.parent_inner[id] = pid; T.keep[id] = 1u;
+        if (sd) T.right[pid] = id; else T.left[pid] = id;
+        st_f[sp] = f; st_l[sp] = g; st_p[sp] = id; st_s[sp] = 0; sp++;
+        st_f[sp] = g + 1; st_l[sp] = l; st_p[sp] = id; st_s[sp] = 1; sp++;
+    }
+}
+
+// position k: bit 0 = goes left; at a segment's first position the high word counts the children that live on (0..2)
+LB_HD uint64_t sah_flag(int k, const int* __restrict__ pseg, const uint32_t* __restrict__ order, const float* __restrict__ pcen,
+                        const SahSegs& S, const SahSplit& X, int max_leaf) {
+    const int s = pseg[k];
+    if (s < 0) return 0ull;
+    const int first = S.first[s], nl = X.nl[s], axis = X.axis[s];
+    bool left;
+    if (axis < 0) left = k - first < nl;
+    else {
+        float lo, scale;
+        sah_frame(S.cb + (size_t)s * 6, axis, lo, scale);
+        left = sah_bin_of(pcen[(size_t)order[k] * 3 + axis], lo, scale) <= X.bin[s];
+    }
+    uint64_t f = left ? 1ull : 0ull;
+    if (k == first) {
+        const int nr = S.last[s] - first + 1 - nl;
+        f |= (uint64_t)((nl > max_leaf ? 1 : 0) + (nr > max_leaf ? 1 : 0)) << 32;
+    }
+    return f;
+}
+
+// segment s of this level -> its (up to two) segments of the next level; scan = exclusive sum of sah_flag over the positions
+LB_HD void sah_spawn(int s, const SahSegs& S, const SahSplit& X, const uint64_t* __restrict__ scan, int max_leaf, const SahSegs& N,
+                     const SahTree& T) {
+    const int first = S.first[s], last = S.last[s], nl = X.nl[s], nr = last - first + 1 - nl;
+    const int gamma = first + nl - 1;
+    const int id = sah_node_id(gamma, LB_LD(T.root_gamma));
+    int base = (int)(scan[first] >> 32);
+    for (int side = 0; side < 2; side++) {
+        const bool lives = (side ? nr : nl) > max_leaf;
+        X.child[s * 2 + side] = lives ? base : -1;
+        if (!lives) continue;
+        N.first[base] = side ? gamma + 1 : first;
+        N.last[base] = side ? last : gamma;
+        N.parent[base] = id * 2 + side;
+        uint32_t* cb = N.cb + (size_t)base * 6;
+        cb[0] = cb[1] = cb[2] = 0xffffffffu; cb[3] = cb[4] = cb[5] = 0u;
+        base++;
+    }
+}
+
+// centre bounds cb6 (f2ord keys) grow by primitive p
+LB_HD void sah_grow_cb(uint32_t* cb6, const float* __restrict__ pcen, uint32_t p) {
+    for (int a = 0; a < 3; a++) {
+        const uint32_t key = f2ord(pcen[(size_t)p * 3 + a]);
+        LB_ATOMIC_MIN(cb6 + a, key); LB_ATOMIC_MAX(cb6 + 3 + a, key);
+    }
+}
+// stable partition of position k into its child's range.  Returns the child segment the primitive went to (-1: none lives on), whose
+// centre bounds the caller grows by it (sah_grow_cb); side_out = 0 left / 1 right.
+LB_HD int sah_scatter(int k, const int* __restrict__ pseg, const uint32_t* __restrict__ order,
+                      const SahSegs& S, const SahSplit& X, const uint64_t* __restrict__ flag, const uint64_t* __restrict__ scan,
+                      uint32_t* __restrict__ order_out, int* __restrict__ pseg_out, uint32_t& p_out, int& side_out) {
+    const int s = pseg[k];
+    p_out = order[k]; side_out = 0;
+    if (s < 0) { order_out[k] = order[k]; pseg_out[k] = -1; return -1; }
+    const int first = S.first[s], nl = X.nl[s];
+    const int rank_l = (int)(uint32_t)(scan[k] - scan[first]);         // low words: primitives of this segment before k that go left
+    const bool left = (flag[k] & 1ull) != 0ull;
+    const int dest = left ? first + rank_l : first + nl + (k - first - rank_l);
+    const uint32_t p = order[k];
+    const int child = X.child[s * 2 + (left ? 0 : 1)];
+    order_out[dest] = p; pseg_out[dest] = child;
+    side_out = left ? 0 : 1;
+    return child;
 }
 
 // ---- refit: the same tree over new vertices (adapt_refit_geometry) -------------------------------------------------------------

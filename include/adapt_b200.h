@@ -107,7 +107,8 @@ typedef struct {
     int32_t pool_size;          /* path slots kept in flight, 0 = auto                                       */
     int32_t accelerator;        /* the reference's <string name="accelerator"> switch: 1 = "bvh". This library always uses its
                                    BVH; the CPU oracle follows the reference (brute force unless 1)                           */
-    int32_t bvh_builder;        /* 0 = default (host binned-SAH build, or env ADAPT_BVH_BUILDER), 1 = linear BVH built on the device */
+    int32_t bvh_builder;        /* 0 = default (host binned-SAH build, or env ADAPT_BVH_BUILDER), 1 = linear BVH built on the device,
+                                   2 = binned-SAH tree built on the device (level-synchronous; the host tree's quality)               */
     int32_t reserved[5];
     /* textures: tracer/path_tracer.py:83-123 (albedo_map / normal_map / bump_map + their packed images). All optional. */
     const adapt_texture* textures;  /* [3][n_objects]: albedo, normal, bump descriptor per object, or NULL (no textures) */
@@ -198,7 +199,7 @@ int adapt_intersect_batch(adapt_handle* h, const float* rays_o, const float* ray
 /* New vertex positions for the SAME scene topology (animated / edited meshes): primitives [n_prims*9], n_g [n_prims*3] and
  * n_s [n_prims*9] (required iff the scene was created with vertex normals) as in adapt_scene_desc.  Waits for enqueued work,
  * replaces the per-primitive tables of load_primitives (tracer/tracer_base.py:117-134) and rebuilds the acceleration structure
- * with the handle's builder (bvh_process, tracer/path_tracer.py:143-179; with bvh_builder = 1 entirely on the device).  The
+ * with the handle's builder (bvh_process, tracer/path_tracer.py:143-179; with bvh_builder = 1 or 2 entirely on the device).  The
  * reference has no counterpart: it re-creates the renderer.  inv_area of area emitters is recomputed from the new vertices of the
  * object they are attached to; the accumulation buffer is left as it is -- reset it with adapt_load_accum(h, NULL, 0) when the image
  * should start over.  On failure the handle keeps its previous acceleration structure. */

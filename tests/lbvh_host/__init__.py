@@ -44,16 +44,20 @@ def _norm(prims, sph, prim_obj, obj_class):
     return prims, n, sph, prim_obj, obj_class
 
 
-def build_tree(prims, sph=None, prim_obj=None, obj_class=None, max_leaf=4, builder="lbvh"):
-    """-> dict(nodes (n_nodes,16), prims (n,12), depth, root_box) from the emulated device builder ("lbvh") or the library's
-    host SAH builder ("sah")."""
+def build_tree(prims, sph=None, prim_obj=None, obj_class=None, max_leaf=4, builder="lbvh", order_seed=0, traverse_cost=1.0):
+    """-> dict(nodes (n_nodes,16), prims (n,12), depth, root_box) from the emulated device builders ("lbvh": linear BVH, "sah_device":
+    level-synchronous binned SAH, its per-position steps run in an order permuted by order_seed) or the library's host SAH builder ("sah")."""
     L = load()
     prims, n, sph, prim_obj, obj_class = _norm(prims, sph, prim_obj, obj_class)
     nodes = np.zeros((max(1, n - 1), 16), np.float32)
     recs = np.zeros((n, 12), np.float32)
     nn, dp = C.c_int(), C.c_int()
     root = np.zeros(6, np.float32)
-    if builder == "lbvh":
+    if builder == "sah_device":
+        lv = C.c_int()
+        rc = L.lbvh_host_build_sah(_p(prims), _p(sph), _p(prim_obj), _p(obj_class), n, max_leaf, _p(nodes), _p(recs), C.byref(nn), C.byref(dp), _p(root),
+                                   C.c_uint(order_seed), C.byref(lv), C.c_float(traverse_cost))
+    elif builder == "lbvh":
         rc = L.lbvh_host_build(_p(prims), _p(sph), _p(prim_obj), _p(obj_class), n, max_leaf, _p(nodes), _p(recs), C.byref(nn), C.byref(dp), _p(root))
     else:
         rc = L.sah_host_build(_p(prims), _p(sph), _p(prim_obj), _p(obj_class), n, max_leaf, _p(nodes), _p(recs), C.byref(nn), C.byref(dp))
@@ -81,6 +85,13 @@ def trace_check(nodes, recs, rays_o, rays_d):
     op = np.zeros(nr, np.int32); ot = np.zeros(nr, np.float32); bp = np.zeros(nr, np.int32); bt = np.zeros(nr, np.float32)
     v = L.lbvh_trace_check(_p(nodes), _p(recs), recs.shape[0], _p(ro), _p(rd), nr, _p(op), _p(ot), _p(bp), _p(bt))
     return op, ot, bp, bt, v / 1000.0
+
+
+def last_prims_tested():
+    """Leaf primitives tested by the most recent trace_check call (all rays): the second tree-quality figure next to nodes per ray."""
+    L = load()
+    L.lbvh_last_prims_tested.restype = C.c_longlong
+    return int(L.lbvh_last_prims_tested())
 
 
 def refit_tree(tree, prims, order_seed=0):

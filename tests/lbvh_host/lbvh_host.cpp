@@ -18,8 +18,8 @@ extern "C" {
 int lbvh_host_build(const float* prim9, const uint8_t* sph, const int32_t* prim_obj, const uint8_t* obj_class, int n, int max_leaf,
                     float* nodes_out, float* prims_out, int* n_nodes, int* depth, float* root_box) {
     if (n <= 0 || max_leaf < 1 || max_leaf > 8) return -1;
-    std::vector<float> pbox((size_t)n * 6);
-    for (int i = 0; i < n; i++) prim_box(prim9, sph, i, pbox.data());
+    std::vector<float> pbox((size_t)n * 6), pcen((size_t)n * 3);
+    for (int i = 0; i < n; i++) prim_box(prim9, sph, i, pbox.data(), pcen.data());
     std::vector<uint32_t> order((size_t)n);
     std::iota(order.begin(), order.end(), 0u);
     if (n <= max_leaf) {
@@ -33,7 +33,7 @@ int lbvh_host_build(const float* prim9, const uint8_t* sph, const int32_t* prim_
     uint32_t cb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     for (int i = 0; i < n; i++)
         for (int a = 0; a < 3; a++) {
-            uint32_t k = f2ord(0.5f * (pbox[(size_t)i * 6 + a] + pbox[(size_t)i * 6 + 3 + a]));
+            uint32_t k = f2ord(pcen[(size_t)i * 3 + a]);
             cb[a] = std::min(cb[a], k); cb[3 + a] = std::max(cb[3 + a], k);
         }
     float cen_lo[3], cen_inv[3];
@@ -43,12 +43,14 @@ int lbvh_host_build(const float* prim9, const uint8_t* sph, const int32_t* prim_
         cen_inv[a] = ext > 0.f ? 1.f / ext : 0.f;
     }
     std::vector<uint64_t> keys((size_t)n), skeys((size_t)n);
-    for (int i = 0; i < n; i++) keys[i] = morton_key(pbox.data(), i, cen_lo, cen_inv);
+    for (int i = 0; i < n; i++) keys[i] = morton_key(pcen.data(), i, cen_lo, cen_inv);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });   // device: cub radix sort (stable)
     for (int i = 0; i < n; i++) skeys[i] = keys[order[i]];
     const int ni = n - 1;
     std::vector<int> left(ni), right(ni), first(ni), last(ni), par_i(ni, -2), par_l(n, -2), height(ni, 0);
     for (int i = 0; i < ni; i++) hierarchy(skeys.data(), n, i, left.data(), right.data(), first.data(), last.data(), par_i.data(), par_l.data());
+    std::vector<uint32_t> keep(ni);
+    for (int i = 0; i < ni; i++) keep[i] = keep_by_size(first.data(), last.data(), i, max_leaf) ? 1u : 0u;
     // bottom-up fit: the second thread to arrive at a node processes it
     std::vector<uint32_t> arrive(ni, 0);
     std::vector<float> ibox((size_t)ni * 6);
@@ -56,17 +58,112 @@ int lbvh_host_build(const float* prim9, const uint8_t* sph, const int32_t* prim_
         int cur = par_l[k];
         while (cur >= 0) {
             if (arrive[cur]++ == 0) break;
-            fit_node(cur, left.data(), right.data(), first.data(), last.data(), pbox.data(), order.data(), ibox.data(), height.data(), max_leaf);
+            fit_node(cur, left.data(), right.data(), first.data(), last.data(), pbox.data(), order.data(), ibox.data(), height.data(), keep.data());
             cur = par_i[cur];
         }
     }
     for (int i = 0; i < ni; i++) if (arrive[i] != 2) return -2;
     std::vector<uint32_t> dense(ni);
     uint32_t cnt = 0;
-    for (int i = 0; i < ni; i++) { dense[i] = cnt; cnt += is_emitted(first.data(), last.data(), i, max_leaf) ? 1u : 0u; }   // device: cub exclusive scan
+    for (int i = 0; i < ni; i++) { dense[i] = cnt; cnt += keep[i]; }   // device: cub exclusive scan
     for (int i = 0; i < ni; i++)
-        emit_node(i, left.data(), right.data(), first.data(), last.data(), pbox.data(), order.data(), ibox.data(), dense.data(), max_leaf, nodes_out);
+        emit_node(i, left.data(), right.data(), first.data(), last.data(), pbox.data(), order.data(), ibox.data(), dense.data(), keep.data(), nodes_out);
     for (int k = 0; k < n; k++) emit_prim(k, order.data(), prim9, sph, prim_obj, obj_class, prims_out);
+    *n_nodes = (int)cnt; *depth = height[0];
+    for (int a = 0; a < 6; a++) root_box[a] = ibox[a];
+    return 0;
+}
+
+// The device SAH builder (builder 2 of build_bvh_device): the same level loop with every kernel as a serial loop.  `order_seed`
+// permutes the order in which the "threads" of the per-position kernels run -- the result must not depend on it (stable partition
+// through the scan, atomics only for min / max / count).
+int lbvh_host_build_sah(const float* prim9, const uint8_t* sph, const int32_t* prim_obj, const uint8_t* obj_class, int n, int max_leaf,
+                        float* nodes_out, float* prims_out, int* n_nodes, int* depth, float* root_box, unsigned order_seed, int* levels_out,
+                        float traverse_cost) {
+    if (n <= 0 || max_leaf < 1 || max_leaf > 8) return -1;
+    if (n <= max_leaf) return lbvh_host_build(prim9, sph, prim_obj, obj_class, n, max_leaf, nodes_out, prims_out, n_nodes, depth, root_box);
+    std::vector<float> pbox((size_t)n * 6), pcen((size_t)n * 3);
+    for (int i = 0; i < n; i++) prim_box(prim9, sph, i, pbox.data(), pcen.data(), true);
+    uint32_t cb0[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    for (int i = 0; i < n; i++)
+        for (int a = 0; a < 3; a++) {
+            uint32_t k = f2ord(pcen[(size_t)i * 3 + a]);
+            cb0[a] = std::min(cb0[a], k); cb0[3 + a] = std::max(cb0[3 + a], k);
+        }
+    std::vector<int> run((size_t)n);                        // order in which the per-position "threads" run
+    std::iota(run.begin(), run.end(), 0);
+    if (order_seed) {
+        uint64_t s = order_seed * 0x9E3779B97F4A7C15ull + 1;
+        for (int i = n - 1; i > 0; i--) { s = s * 6364136223846793005ull + 1442695040888963407ull; std::swap(run[i], run[(int)((s >> 33) % (uint64_t)(i + 1))]); }
+    }
+    const int ni = n - 1;
+    const size_t MS = (size_t)n / (size_t)(max_leaf + 1) + 2;
+    std::vector<uint32_t> order[2] = {std::vector<uint32_t>((size_t)n), std::vector<uint32_t>((size_t)n)};
+    std::vector<int> pseg[2] = {std::vector<int>((size_t)n, 0), std::vector<int>((size_t)n, 0)};
+    std::iota(order[0].begin(), order[0].end(), 0u);
+    std::vector<int> sf[2], sl[2], sp[2]; std::vector<uint32_t> scb[2];
+    SahSegs segs[2];
+    for (int q = 0; q < 2; q++) {
+        sf[q].assign(MS, 0); sl[q].assign(MS, 0); sp[q].assign(MS, 0); scb[q].assign(MS * 6, 0u);
+        segs[q] = SahSegs{sf[q].data(), sl[q].data(), sp[q].data(), scb[q].data()};
+    }
+    std::vector<int> xa(MS), xb(MS), xn(MS), xc(MS * 2);
+    SahSplit split{xa.data(), xb.data(), xn.data(), xc.data()};
+    const int UNSET = INT32_MIN;
+    std::vector<int> left(ni, UNSET), right(ni, UNSET), first(ni, UNSET), last(ni, UNSET), par_i(ni, UNSET), par_l(n, UNSET), height(ni, 0);
+    int root_gamma = -1;
+    std::vector<uint32_t> keep(ni, 0xdeadu);
+    std::vector<int> small_last((size_t)n, -1), small_parent((size_t)n, 0);
+    SahTree tree{left.data(), right.data(), first.data(), last.data(), par_i.data(), par_l.data(), keep.data(), &root_gamma,
+                 small_last.data(), small_parent.data(), traverse_cost};
+    std::vector<uint32_t> bcnt(MS * 3 * LB_SAH_BINS), bbox(MS * 3 * LB_SAH_BINS * 6);
+    std::vector<uint64_t> flag((size_t)n + 1), scan((size_t)n + 1);
+    segs[0].first[0] = 0; segs[0].last[0] = n - 1; segs[0].parent[0] = -1;
+    for (int a = 0; a < 6; a++) segs[0].cb[a] = cb0[a];
+    int cur = 0, n_seg = 1, level = 0;
+    while (n_seg > 0) {
+        if (level >= 96 || (size_t)n_seg > MS) return -3;
+        const int nb = n_seg * 3 * LB_SAH_BINS;
+        for (int j = 0; j < nb; j++) sah_clear_bin(j, bcnt.data(), bbox.data());
+        for (int k : run) sah_bin(k, pseg[cur].data(), order[cur].data(), pbox.data(), pcen.data(), segs[cur].cb, bcnt.data(), bbox.data());
+        for (int s = n_seg - 1; s >= 0; s--) sah_split(s, level, segs[cur], bcnt.data(), bbox.data(), max_leaf, split, tree);
+        for (int k : run) flag[k] = sah_flag(k, pseg[cur].data(), order[cur].data(), pcen.data(), segs[cur], split, max_leaf);
+        flag[n] = 0;
+        uint64_t acc = 0;
+        for (int k = 0; k <= n; k++) { scan[k] = acc; acc += flag[k]; }                        // device: cub exclusive sum
+        for (int s = 0; s < n_seg; s++) sah_spawn(s, segs[cur], split, scan.data(), max_leaf, segs[cur ^ 1], tree);
+        for (int k : run) {
+            uint32_t p; int side;
+            const int child = sah_scatter(k, pseg[cur].data(), order[cur].data(), segs[cur], split, flag.data(), scan.data(),
+                                          order[cur ^ 1].data(), pseg[cur ^ 1].data(), p, side);
+            if (child >= 0) sah_grow_cb(segs[cur ^ 1].cb + (size_t)child * 6, pcen.data(), p);
+        }
+        for (int k : run) sah_small(k, order[cur ^ 1].data(), pbox.data(), pcen.data(), tree);
+        n_seg = (int)(scan[n] >> 32);
+        cur ^= 1; level++;
+    }
+    if (levels_out) *levels_out = level;
+    const std::vector<uint32_t>& ord = order[cur];
+    for (int i = 0; i < ni; i++) if (left[i] == UNSET || right[i] == UNSET || first[i] == UNSET || par_i[i] == UNSET) return -4;
+    for (int k = 0; k < n; k++) if (par_l[k] == UNSET) return -5;
+    for (int i = 0; i < ni; i++) if (keep[i] > 1u) return -6;
+    std::vector<uint32_t> arrive(ni, 0);
+    std::vector<float> ibox((size_t)ni * 6);
+    for (int k = 0; k < n; k++) {
+        int c = par_l[k];
+        while (c >= 0) {
+            if (arrive[c]++ == 0) break;
+            fit_node(c, left.data(), right.data(), first.data(), last.data(), pbox.data(), ord.data(), ibox.data(), height.data(), keep.data());
+            c = par_i[c];
+        }
+    }
+    for (int i = 0; i < ni; i++) if (arrive[i] != 2) return -2;
+    std::vector<uint32_t> dense(ni);
+    uint32_t cnt = 0;
+    for (int i = 0; i < ni; i++) { dense[i] = cnt; cnt += keep[i]; }
+    for (int i = 0; i < ni; i++)
+        emit_node(i, left.data(), right.data(), first.data(), last.data(), pbox.data(), ord.data(), ibox.data(), dense.data(), keep.data(), nodes_out);
+    for (int k = 0; k < n; k++) emit_prim(k, ord.data(), prim9, sph, prim_obj, obj_class, prims_out);
     *n_nodes = (int)cnt; *depth = height[0];
     for (int a = 0; a < 6; a++) root_box[a] = ibox[a];
     return 0;
@@ -138,6 +235,8 @@ int lbvh_validate(const float* nodes, int n_nodes, const float* prims, int n, co
 // Closest hit of a ray batch through a tree in the traversal layout (triangles and spheres, acceptance as pt_trace.cuh), plus
 // the same by brute force over the records; out_prim / out_t per ray, brute-force results in bf_prim / bf_t.  Returns the mean
 // number of nodes visited per ray * 1000 (tree-quality figure).
+static long long g_prims_tested = 0;      // leaf primitives tested by the last lbvh_trace_check (second tree-quality figure)
+long long lbvh_last_prims_tested() { return g_prims_tested; }
 int lbvh_trace_check(const float* nodes, const float* prims, int n, const float* ro, const float* rd, int n_rays,
                      int32_t* out_prim, float* out_t, int32_t* bf_prim, float* bf_t) {
     auto prim_hit = [&](const float* g, const float* o, const float* d, float tmax, float& t_out) {
@@ -164,6 +263,7 @@ int lbvh_trace_check(const float* nodes, const float* prims, int n, const float*
         return false;
     };
     long long visited = 0;
+    g_prims_tested = 0;
     for (int r = 0; r < n_rays; r++) {
         const float* o = ro + (size_t)r * 3; const float* d = rd + (size_t)r * 3;
         float best = 1e7f; int bp = -1;
@@ -204,6 +304,7 @@ int lbvh_trace_check(const float* nodes, const float* prims, int n, const float*
                 const int code = ~node, first = code >> 3, cnt = (code & 7) + 1;
                 for (int k = first; k < first + cnt; k++) {
                     float t;
+                    g_prims_tested++;
                     if (prim_hit(prims + (size_t)k * 12, o, d, hit_t, t)) { hit_t = t; std::memcpy(&hp, prims + (size_t)k * 12 + 9, 4); }
                 }
             }

@@ -1,5 +1,5 @@
-"""Device BVH builder -- GPU half: the tree built by bvh_device.cu (through adapt_create with bvh_builder = 1 and read back with
-adapt_bvh_export) is held to the CPU emulation of the same per-element steps bit for bit, traced against the host-SAH handle,
+"""Device BVH builders -- GPU half: the tree built by bvh_device.cu (through adapt_create with bvh_builder = 1, the linear BVH, or 2, the
+level-synchronous binned SAH, and read back with adapt_bvh_export) is held to the CPU emulation of the same per-element steps bit for bit, traced against the host-SAH handle,
 and rendered: tree shape must not change a result (closest hit is unique)."""
 import numpy as np
 import pytest
@@ -51,16 +51,17 @@ def _load(scene_root, scene, name, size):
     return load_scene(scene_root, scene, name, size, size)
 
 
+@pytest.mark.parametrize("builder", ["lbvh", "sah_device"])
 @pytest.mark.parametrize("scene,name", SCENES)
-def test_device_tree_equals_emulated_tree(Renderer, scene_root, scene, name):
+def test_device_tree_equals_emulated_tree(Renderer, scene_root, scene, name, builder):
     e, a, o, c = _load(scene_root, scene, name, 32)
-    r = Renderer(e, a, o, c, bvh_builder="lbvh")
+    r = Renderer(e, a, o, c, bvh_builder=builder)
     ex = r.bvh_export()
-    assert ex["builder"] == 1 and ex["n_prims"] == a["primitives"].shape[0]
+    assert ex["builder"] == {"lbvh": 1, "sah_device": 2}[builder] and ex["n_prims"] == a["primitives"].shape[0]
     prims, sph = _tables(a, o)
     rc, depth = validate(ex["nodes"], ex["prims"], prims, sph)
     assert rc == 0 and depth == ex["depth"]
-    ref = build_tree(prims, sph, max_leaf=4)
+    ref = build_tree(prims, sph, max_leaf=4, builder=builder, order_seed=3)   # the emulated threads run in a shuffled order
     assert ex["n_nodes"] == ref["nodes"].shape[0] and ex["depth"] == ref["depth"]
     # geometry words of the records and the whole node array, bit for bit (object / class words depend on the scene tables)
     assert np.array_equal(ex["prims"][:, :10].view(np.uint32), ref["prims"][:, :10].view(np.uint32))
@@ -68,11 +69,12 @@ def test_device_tree_equals_emulated_tree(Renderer, scene_root, scene, name):
     r.close()
 
 
+@pytest.mark.parametrize("builder", ["lbvh", "sah_device"])
 @pytest.mark.parametrize("scene,name", SCENES)
-def test_same_hits_and_same_image_as_host_sah_tree(Renderer, scene_root, scene, name):
+def test_same_hits_and_same_image_as_host_sah_tree(Renderer, scene_root, scene, name, builder):
     size, spp = 64, 4
     e, a, o, c = _load(scene_root, scene, name, size)
-    r_l = Renderer(e, a, o, c, seed=2, bvh_builder="lbvh")
+    r_l = Renderer(e, a, o, c, seed=2, bvh_builder=builder)
     r_s = Renderer(e, a, o, c, seed=2, bvh_builder="sah")
     assert r_s.bvh_export(arrays=False)["builder"] == 0
     prims, _ = _tables(a, o)
@@ -93,10 +95,10 @@ def test_same_hits_and_same_image_as_host_sah_tree(Renderer, scene_root, scene, 
     r_l.close(); r_s.close()
 
 
-@pytest.mark.parametrize("builder", ["lbvh", "sah"])
+@pytest.mark.parametrize("builder", ["lbvh", "sah", "sah_device"])
 def test_update_geometry_rebuilds_and_renders_like_a_fresh_scene(Renderer, scene_root, builder):
-    """adapt_update_geometry: move one mesh, rebuild (on the device for "lbvh"), and get the image a renderer created on the
-    moved geometry gives."""
+    """adapt_update_geometry: move one mesh, rebuild (on the device for "lbvh" and "sah_device"), and get the image a renderer
+    created on the moved geometry gives."""
     size, spp = 64, 4
     e, a, o, c = _load(scene_root, "cbox", "bunny90k.xml", size)
     r = Renderer(e, a, o, c, seed=5, bvh_builder=builder)
@@ -114,8 +116,8 @@ def test_update_geometry_rebuilds_and_renders_like_a_fresh_scene(Renderer, scene
     print(f"[{builder}] first build {first['build_ms']:.2f} ms, rebuild {again['build_ms']:.2f} ms, {again['n_nodes']} nodes")
     prims, sph = _tables(moved, o)
     assert validate(again["nodes"], again["prims"], prims, sph)[0] == 0
-    if builder == "lbvh":
-        ref = build_tree(prims, sph, max_leaf=4)
+    if builder != "sah":
+        ref = build_tree(prims, sph, max_leaf=4, builder=builder)
         assert np.array_equal(again["nodes"].view(np.uint32), ref["nodes"].view(np.uint32))
     fresh = Renderer(e, moved, o, c, seed=5, bvh_builder=builder)
     fresh.render_batch(spp)

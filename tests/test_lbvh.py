@@ -67,6 +67,79 @@ def test_tree_quality_close_to_sah():
     assert n_l < 1.6 * n_s
 
 
+# ---- the level-synchronous binned-SAH builder (builder 2) through the same harness ------------------------------------------------
+@pytest.mark.parametrize("max_leaf", [1, 2, 4, 8])
+def test_sah_device_tree_is_sound_and_traces_like_brute_force(max_leaf):
+    prims = _mesh()
+    t, _ = _check(prims, max_leaf=max_leaf, builder="sah_device")
+    n = prims.shape[0]
+    if max_leaf == 1:
+        assert t["nodes"].shape[0] == n - 1
+    v = prims.reshape(-1, 3, 3)
+    assert np.allclose(t["root_box"][:3], v.min((0, 1)), atol=2e-4) and np.allclose(t["root_box"][3:], v.max((0, 1)), atol=2e-4)
+
+
+def test_sah_device_tree_does_not_depend_on_thread_order():
+    """Stable partition through the scan, atomics only for counts and min / max: whatever order the per-position steps run in, the
+    same tree comes out (what makes the B200-built tree comparable bit for bit, tests/test_gpu_lbvh.py)."""
+    prims = _mesh(64, 50)
+    t0 = build_tree(prims, max_leaf=4, builder="sah_device")
+    for seed in (1, 9):
+        t1 = build_tree(prims, max_leaf=4, builder="sah_device", order_seed=seed)
+        assert np.array_equal(t0["nodes"].view(np.uint32), t1["nodes"].view(np.uint32))
+        assert np.array_equal(t0["prims"].view(np.uint32), t1["prims"].view(np.uint32))
+
+
+def test_sah_device_tree_quality_matches_the_host_sah_tree():
+    """Node visits + primitive tests per ray of the device-SAH tree against the linear BVH and the host builder's tree on the same mesh
+    and rays: clearly below the linear BVH and level with the host tree (same heuristic, same bins, same centres)."""
+    from lbvh_host import last_prims_tested
+    prims = _mesh(96, 80)
+    res = {}
+    for b in ("lbvh", "sah_device", "sah"):
+        t = build_tree(prims, max_leaf=4, builder=b)
+        ro, rd = _rays(t["prims"], 1500, 1)
+        *_, nodes_per_ray = trace_check(t["nodes"], t["prims"], ro, rd)
+        res[b] = nodes_per_ray + last_prims_tested() / 1500
+    assert res["sah_device"] < 0.9 * res["lbvh"]
+    assert res["sah_device"] < 1.03 * res["sah"]
+
+
+@pytest.mark.parametrize("n", [5, 6, 9, 17])
+def test_sah_device_small_scenes(n):
+    rng = np.random.default_rng(n)
+    prims = (rng.random((n, 3, 3)) * 0.3 + rng.random((n, 1, 3)) * 2).astype(np.float32).reshape(-1, 9)
+    for ml in (1, 2, 4):
+        _check(prims, max_leaf=ml, n_rays=300, seed=n, builder="sah_device")
+
+
+def test_sah_device_coincident_centres_split_on_position():
+    """Thousands of primitives with the same box centre: no plane separates them, the ranges are halved by position and the tree
+    stays balanced (depth ~ log2 n) and sound."""
+    rng = np.random.default_rng(3)
+    n = 3000
+    d = rng.normal(0, 1, (n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    e = np.cross(d, rng.normal(0, 1, (n, 3))); e /= np.linalg.norm(e, axis=1, keepdims=True)
+    c = np.float64([1.0, 2.0, 3.0])
+    # triangles whose bounding boxes are all centred on c: vertex pairs symmetric about c would be degenerate, so use spheres
+    prims = np.zeros((n, 9), np.float32)
+    prims[:, :3] = c
+    prims[:, 3:6] = (0.1 + rng.random((n, 1))) * np.ones((1, 3))
+    sph = np.ones(n, np.uint8)
+    t = build_tree(prims, sph, max_leaf=4, builder="sah_device")
+    rc, depth = validate(t["nodes"], t["prims"], prims, sph)
+    assert rc == 0 and depth <= 14
+
+
+def test_sah_device_spheres_and_triangles_mixed(scene_root):
+    e, a, o, c = load_scene(scene_root, "test", "allbxdf.xml", 16, 16)
+    prims = a["primitives"].reshape(-1, 9)
+    sph = np.zeros(prims.shape[0], np.uint8)
+    if a["indices"] is not None:
+        sph[np.asarray(a["indices"], np.int64)] = 1
+    _check(prims, sph, max_leaf=4, builder="sah_device")
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9])
 def test_tiny_scenes(n):
     rng = np.random.default_rng(n)

@@ -19,7 +19,7 @@ for name in (sys.argv[1:] or ["bunny90k", "orb500k"]):
     ensure_big_meshes(DEFAULT_ROOT, (name,))
     e, a, o, c = scene_parsing(os.path.join(DEFAULT_ROOT, "cbox"), name + ".xml")
     c["film"]["width"] = c["film"]["height"] = 16
-    for builder in ("sah", "lbvh"):
+    for builder in (os.environ.get("BUILDERS", "sah,lbvh,sah_device").split(",")):
         r = Renderer(e, a, o, c, bvh_builder=builder)
         first = r.bvh_export(arrays=False)
         re_ms, call_ms = [], []
