@@ -198,7 +198,17 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
             k_logic_vpt<M_ALL | M_TEXTURED><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
                 h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
                 parity, (unsigned)L.iterations);
-        else
+        else if ((h->mats & (M_GLOSSY | M_COAT_GGX)) == 0 && env_int("ADAPT_VPT_SPECIALISE", 1)) {
+            // scenes of Lambertian / Phong / mirror surfaces (+ the BSDF containers of media): the small instantiations
+            if (h->mats & M_BSDF)
+                k_logic_vpt<M_SIMPLE | M_BSDF><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                    h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
+                    parity, (unsigned)L.iterations);
+            else
+                k_logic_vpt<M_SIMPLE><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                    h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
+                    parity, (unsigned)L.iterations);
+        } else
             k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
                 h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
                 parity, (unsigned)L.iterations);

@@ -531,10 +531,16 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 // closest-hit segments, the lane re-arming itself) and RED-adds payload * transmittance to the path colour.  A path that ends
 // after queueing samples is flagged SLOT_FINISH and splatted by the next launch, like a `pt` path at its last bounce.  Slot layout
 // as for `pt`, except that thr.w carries the emission weight.
-// NOT YET RUN ON A GPU: adapt_create only accepts integrator = 1 with ADAPT_ENABLE_VPT=1.  The functions it calls are verified on
-// the CPU (tests/test_vpt_device_code.py) and the kernel itself runs under the SIMT emulator (tests/test_wavefront_emulated.py).
+// Instantiated per material set of the scene (adapt_abi.cu: launch_iteration), like k_logic.  The functions it calls are also verified
+// on the CPU (tests/test_vpt_device_code.py) and the kernel itself runs under the SIMT emulator (tests/test_wavefront_emulated.py).
+// Resident blocks per SM (session r02x, profiles/r02x_ab_vpt_logic.txt, logic ms/step cbox fog / media scene): 2 blocks (112 registers,
+// no spills) 19.5 / 31.7, 3 blocks (80 registers, ~220 bytes of spills) 18.0 / 29.7, 4 blocks 18.0 / 30.5; the per-material-set
+// instantiations are worth another 4 % (20.3 / 32.7 with the all-material kernel at 2 blocks).
+#ifndef VPT_MIN_BLOCKS
+#define VPT_MIN_BLOCKS 3
+#endif
 template <int MATS>
-__global__ void __launch_bounds__(LOGIC_BLOCK, 2)
+__global__ void __launch_bounds__(LOGIC_BLOCK, VPT_MIN_BLOCKS)
 k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
             WorkStripe* __restrict__ work, Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list,
             const int n_pixels, const unsigned long long work_hi, const long long cnt_origin, const int parity, const unsigned rot) {
