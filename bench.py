@@ -437,8 +437,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="bunny90k", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=128,
-                    help="samples per pixel one step enqueues (a step ends with adapt_sync, i.e. drains the path pool: ~4 ms of ragged tail, 7 %% of a 32-spp step on bunny90k, 2 %% of a 128-spp one)")
+    ap.add_argument("--spp-per-step", type=int, default=256,
+                    help="samples per pixel one step enqueues (a step ends with adapt_sync, i.e. drains the path pool: ~4 ms of ragged tail, 7 %% of a 32-spp step on bunny90k, 2 %% of a 128-spp one, 1 %% of a 256-spp one)")
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--max-bounce", type=int, default=None)
@@ -449,7 +449,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = spp_per_step x N samples per step (per-GPU work fixed), strong = spp_per_step samples per step whatever N")
     ap.add_argument("--also", default="orb500k", help="second workload timed in the same process at N = 1 ('' = none)")
-    ap.add_argument("--also-spp", type=int, default=64)
+    ap.add_argument("--also-spp", type=int, default=256)
     ap.add_argument("--integrator", default="pt", choices=["pt", "vpt"],
                     help="vpt: the volumetric integrator over homogeneous media (use with --workload cbox or media)")
     args = ap.parse_args()
