@@ -488,12 +488,14 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
         if (need) {
             if (live && v < limit) {
                 const unsigned long long id = stripe_item_id(v, c);
-                const unsigned long long s = id / (unsigned long long)n_pixels;
-                const int k = (int)(id - s * (unsigned long long)n_pixels);
+                unsigned long long s; unsigned ku;
+                divmod_u64(id, (unsigned)n_pixels, 1.0 / (double)n_pixels, s, ku);
+                const int k = (int)ku;
                 const int pixel = __ldg(pixel_list + k);
                 const int cnt = (int)(cnt_origin + (long long)s + 1);
                 Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
-                const int i = pixel / sv.height, jj = pixel - i * sv.height;
+                int i, jj;
+                divmod_small_q(pixel, sv.height, sv.inv_height, i, jj);
                 float3 d = camera_ray(sv, g, i, jj, cnt);
                 if (may_cull && attempt < 3 && !ray_hits_box(sv.cam_t, d, sv.world_lo, sv.world_hi)) {
                     culled++;                       // path over: ray_intersect would return a miss
@@ -643,12 +645,14 @@ k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
         if (need) {
             if (live && v < limit) {
                 const unsigned long long id = stripe_item_id(v, c);
-                const unsigned long long s = id / (unsigned long long)n_pixels;
-                const int k = (int)(id - s * (unsigned long long)n_pixels);
+                unsigned long long s; unsigned ku;
+                divmod_u64(id, (unsigned)n_pixels, 1.0 / (double)n_pixels, s, ku);
+                const int k = (int)ku;
                 const int pixel = __ldg(pixel_list + k);
                 const int cnt = (int)(cnt_origin + (long long)s + 1);
                 Rng g; g.init(sv.seed, (uint32_t)pixel, (uint32_t)cnt);
-                const int i = pixel / sv.height, jj = pixel - i * sv.height;
+                int i, jj;
+                divmod_small_q(pixel, sv.height, sv.inv_height, i, jj);
                 const float3 d = camera_ray(sv, g, i, jj, cnt);
                 pool.ray_o[slot] = make_float4(sv.cam_t.x, sv.cam_t.y, sv.cam_t.z, PT_T_INF);
                 pool.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float((uint32_t)(g.state >> 32)));

@@ -78,6 +78,7 @@ def load():
         lib.dev_host_phase_eval.argtypes = [C.c_void_p, fp, fp, C.c_int, fp]
         lib.dev_host_phase_sample.argtypes = [C.c_void_p, fp, C.c_uint64, C.c_int, fp, fp]
         lib.dev_host_medium_sample_mfp.argtypes = [C.c_void_p, C.c_float, C.c_uint64, C.c_int, ip, fp, fp]
+        lib.dev_host_index_arith_check.argtypes = [C.c_uint64, C.c_int]
         _lib = lib
     return _lib
 

@@ -117,4 +117,48 @@ void dev_host_medium_sample_mfp(const adapt_medium* m, float max_depth, uint64_t
     }
 }
 
+// pt_common.cuh's division-free index arithmetic against the plain operators: work id -> (sample, pixel slot), pixel -> (column, row),
+// floor modulo.  Returns the number of mismatches over a sweep of edge values and `n` pseudo-random cases.
+int dev_host_index_arith_check(uint64_t seed, int n) {
+    int bad = 0;
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 12345ull;
+    auto next = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return s ^ (s >> 29); };
+    auto check64 = [&](unsigned long long id, unsigned np) {
+        unsigned long long q; unsigned r;
+        divmod_u64(id, np, 1.0 / (double)np, q, r);
+        if (q != id / np || r != (unsigned)(id % np)) bad++;
+    };
+    auto check32 = [&](int p, int h) {
+        int q, r;
+        divmod_small_q(p, h, 1.f / (float)h, q, r);
+        if (q != p / h || r != p % h) bad++;
+    };
+    const unsigned nps[] = {1u, 2u, 3u, 1023u, 1024u, 262144u, 2073600u, 8294400u, 33177600u, 0x7fffffffu};
+    for (unsigned np : nps)
+        for (unsigned long long k = 0; k < 70; k++)
+            for (long long d = -2; d <= 2; d++) {
+                const unsigned long long base = k * (unsigned long long)np * (k < 40 ? 1ull : 1000003ull);
+                if ((long long)base + d >= 0) check64(base + (unsigned long long)d, np);
+            }
+    const int hs[] = {1, 2, 3, 16, 31, 32, 720, 1080, 2160, 4320, 16384};
+    for (int h : hs)
+        for (int col = 0; col < 1 << 20; col = col * 2 + 1)
+            for (int d = -2; d <= 2; d++) {
+                const long long p = (long long)col * h + d;
+                if (p >= 0 && p <= 0x7fffffffll && p / h < (1 << 20)) check32((int)p, h);
+            }
+    for (int k = 0; k < n; k++) {
+        const unsigned np = (unsigned)(next() % 40000000ull) + 1u;
+        check64(next() >> (14 + (int)(next() % 40ull)), np);
+        const int h = (int)(next() % 8192ull) + 1;
+        const int col = (int)(next() % (1ull << 20));
+        const long long p = (long long)col * h + (long long)(next() % (unsigned long long)h);
+        if (p <= 0x7fffffffll) check32((int)p, h);
+        const int a = (int)(uint32_t)next(), m = (int)(next() % 67ull) + 1;
+        int ref = a % m; if (ref < 0) ref += m;
+        if (floor_mod(a, m) != ref) bad++;
+    }
+    return bad;
+}
+
 }  // extern "C"

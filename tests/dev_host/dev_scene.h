@@ -52,7 +52,7 @@ inline DevHost* make_dev_scene(const adapt_scene_desc* d) {
     sv.cam_r.r1 = mk3(d->cam_r[3], d->cam_r[4], d->cam_r[5]);
     sv.cam_r.r2 = mk3(d->cam_r[6], d->cam_r[7], d->cam_r[8]);
     sv.cam_t = mk3(d->cam_t[0], d->cam_t[1], d->cam_t[2]);
-    sv.inv_focal = d->inv_focal; sv.half_w = d->half_w; sv.half_h = d->half_h; sv.width = d->width; sv.height = d->height;
+    sv.inv_focal = d->inv_focal; sv.half_w = d->half_w; sv.half_h = d->half_h; sv.width = d->width; sv.height = d->height; sv.inv_height = 1.f / (float)d->height;
     sv.max_bounce = d->max_bounce; sv.num_shadow_ray = d->num_shadow_ray; sv.use_rr = d->use_rr; sv.rr_bounce_th = d->rr_bounce_th;
     sv.use_mis = d->use_mis; sv.anti_alias = d->anti_alias; sv.stratified = d->stratified_sampling; sv.two_sides = d->brdf_two_sides;
     sv.has_v_normal = d->has_v_normal; sv.rr_threshold = d->rr_threshold; sv.world_ior = d->world_ior;

@@ -76,3 +76,12 @@ def test_device_traversal_matches_oracle_intersections(scene_root, oracle_lib, s
     np.testing.assert_array_equal(g["obj"][hit], ref["obj"][hit])
     ga, ra = dev.intersect_batch(ro, rd, tm, any_hit=True), osc.intersect_batch(ro, rd, tm, any_hit=True)
     assert (ga["prim"] == ra["prim"]).mean() > 0.9995
+
+
+def test_division_free_index_arithmetic_is_exact():
+    """k_logic turns a 64-bit work id into (sample, pixel slot) and a pixel index into (column, row) with a floating-point estimate and one
+    correction step instead of integer divisions, and takes floor-modulo of powers of two with an AND (pt_common.cuh): equal to the plain
+    operators on edge values (multiples of the divisor +- 2, ids up to 2^50, the BASELINE film sizes) and on 2 million random cases."""
+    import dev_host
+    lib = dev_host.load()
+    assert lib.dev_host_index_arith_check(7, 2_000_000) == 0
