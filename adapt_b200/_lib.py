@@ -118,7 +118,7 @@ ABI_SYMBOLS = [
     "adapt_create", "adapt_destroy", "adapt_render", "adapt_wait_enqueued", "adapt_sync", "adapt_read_accum", "adapt_load_accum",
     "adapt_read_pixels", "adapt_host_alloc", "adapt_host_free",
     "adapt_accum_device_ptr", "adapt_set_stream", "adapt_get_stats", "adapt_reset_stats", "adapt_intersect_batch", "adapt_bxdf_batch",
-    "adapt_bvh_export", "adapt_update_geometry", "adapt_refit_geometry",
+    "adapt_bvh_export", "adapt_bvh_export_wide", "adapt_update_geometry", "adapt_refit_geometry",
     "adapt_bvh_build", "adapt_free", "adapt_last_error", "adapt_version", "adapt_tile_partition",
 ]
 
@@ -173,6 +173,8 @@ def load_library(path: Optional[str] = None):
     lib.adapt_bxdf_batch.restype = C.c_int
     lib.adapt_bvh_export.argtypes = [H, _ip, _ip, _ip, _ip, _fp, _fp, _fp]
     lib.adapt_bvh_export.restype = C.c_int
+    lib.adapt_bvh_export_wide.argtypes = [H, _ip, _ip, C.POINTER(C.c_uint32)]
+    lib.adapt_bvh_export_wide.restype = C.c_int
     lib.adapt_update_geometry.argtypes = [H, _fp, _fp, _fp]
     lib.adapt_update_geometry.restype = C.c_int
     lib.adapt_refit_geometry.argtypes = [H, _fp, _fp, _fp]

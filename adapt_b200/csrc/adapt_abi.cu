@@ -120,7 +120,7 @@ struct adapt_handle {
     int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt / k_trace_vpt)
     VolumeView vv{};
     int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH, 2 device binned SAH (bvh_device.cu)
-    int bvh_nodes = 0, bvh_depth = 0;
+    int bvh_nodes = 0, bvh_depth = 0, bvh_nodes8 = 0, bvh_depth8 = 0;
     float bvh_build_ms = 0.f;
     BuildParams bvh_params;
     // host tables kept for adapt_update_geometry (the scene's topology: which object / class each primitive belongs to)
@@ -424,18 +424,23 @@ static int build_accel(adapt_handle* h, const float* primitives) {
     // still holds its previous, valid structure
     const float4 *new_nodes = nullptr, *new_prims = nullptr; const uint4* new_nodes8 = nullptr;
     auto drop_new = [&]() { dev_release(h, new_nodes); dev_release(h, new_nodes8); dev_release(h, new_prims); };
-    bool wide_ok = true; int n_nodes = 0, depth = 0; float build_ms = 0.f;
+    bool wide_ok = true; int n_nodes = 0, depth = 0, n_nodes8 = 0, depth8 = 0; float build_ms = 0.f;
     float root_lo[3], root_hi[3];
     if (h->bvh_builder >= 1) {
         // device build: linear BVH or binned SAH straight into the traversal layout; no 8-wide tree
         DeviceBvh db; std::string what;
-        cudaError_t be = build_bvh_device(primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), np, no, h->bvh_params.max_leaf,
-                                          h->stream, db, what, h->bvh_builder, h->bvh_params.traverse_cost);
+        // the SAH builder also collapses its tree into the compressed 8-wide layout when the handle traces through that (leaves <= 3)
+        const bool eight = h->want_wide && h->bvh_builder == 2;
+        cudaError_t be = build_bvh_device(primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), np, no,
+                                          eight ? std::min(h->bvh_params.max_leaf, 3) : h->bvh_params.max_leaf,
+                                          h->stream, db, what, h->bvh_builder, h->bvh_params.traverse_cost, eight);
         if (be != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH build: " + what + ": " + cudaGetErrorString(be));
         h->allocs.push_back(db.nodes); h->allocs.push_back(db.leaf_prims);
-        new_nodes = db.nodes; new_prims = db.leaf_prims;
+        if (db.nodes8) h->allocs.push_back(db.nodes8);
+        new_nodes = db.nodes; new_prims = db.leaf_prims; new_nodes8 = db.nodes8;
         if (db.depth > PT_STACK_SIZE) { drop_new(); return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack (use the host builder for this scene)"); }
-        wide_ok = false;
+        wide_ok = db.nodes8 != nullptr && db.depth8 + 1 <= PT_STACK8;
+        n_nodes8 = db.n_nodes8; depth8 = db.depth8;
         n_nodes = db.n_nodes; depth = db.depth; build_ms = db.build_ms;
         for (int a = 0; a < 3; a++) { root_lo[a] = db.root_lo[a]; root_hi[a] = db.root_hi[a]; }
     } else {
@@ -457,6 +462,7 @@ static int build_accel(adapt_handle* h, const float* primitives) {
             uint4* tmp8 = nullptr;
             if ((rc = dev_upload(h, &tmp8, reinterpret_cast<const uint4*>(gb.nodes8.data()), gb.nodes8.size() * 5))) { drop_new(); return rc; }
             new_nodes8 = tmp8;
+            n_nodes8 = (int)gb.nodes8.size(); depth8 = gb.depth8;
         }
         if ((rc = dev_upload(h, &tmp4, reinterpret_cast<const float4*>(gb.prims.data()), gb.prims.size() * 3))) { drop_new(); return rc; }
         new_prims = tmp4;
@@ -467,6 +473,7 @@ static int build_accel(adapt_handle* h, const float* primitives) {
     dev_release(h, sv.nodes); dev_release(h, sv.nodes8); dev_release(h, sv.leaf_prims);
     sv.nodes = new_nodes; sv.nodes8 = new_nodes8; sv.leaf_prims = new_prims;
     h->wide_ok = wide_ok; h->bvh_nodes = n_nodes; h->bvh_depth = depth; h->bvh_build_ms = build_ms;
+    h->bvh_nodes8 = new_nodes8 ? n_nodes8 : 0; h->bvh_depth8 = new_nodes8 ? depth8 : 0;
     // scene bounds (root of the BVH), padded: used to finish camera rays that cannot hit anything
     const float pad = 1e-3f;
     sv.world_lo = mk3(root_lo[0] - pad, root_lo[1] - pad, root_lo[2] - pad);
@@ -608,7 +615,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     const bool auto_mode = h->trace_mode < 0;
     if (auto_mode) h->trace_mode = (np <= 64 || np >= 400000) ? 3 : 1;
     if (h->trace_mode != 0 && h->trace_mode != 3) h->trace_mode = 1;
-    h->want_wide = h->trace_mode == 3 && h->bvh_builder == 0;
+    h->want_wide = h->trace_mode == 3 && h->bvh_builder != 1;          // the linear BVH is traced through the binary layout only
     CKH(build_accel(h, d->primitives));
     float4* tmp4 = nullptr;
     CKH(dev_upload(h, &tmp4, prim_geom.data(), prim_geom.size())); sv.prim_geom = tmp4; h->d_prim_geom = tmp4;
@@ -1179,6 +1186,17 @@ int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_
     CK(cudaSetDevice(h->device));
     if (nodes_out) CK(cudaMemcpy(nodes_out, h->sv.nodes, (size_t)h->bvh_nodes * 16 * sizeof(float), cudaMemcpyDeviceToHost));
     if (prims_out) CK(cudaMemcpy(prims_out, h->sv.leaf_prims, (size_t)h->sv.n_prims * 12 * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int adapt_bvh_export_wide(adapt_handle* h, int32_t* n_nodes8, int32_t* depth8, uint32_t* nodes8_out) {
+    if (!h) return set_error(ADAPT_ERR_INVALID, "adapt_bvh_export_wide: null handle");
+    if (!h->members.empty()) return adapt_bvh_export_wide(h->members[0], n_nodes8, depth8, nodes8_out);
+    const bool used = h->trace_mode == 3 && h->sv.nodes8 != nullptr;
+    if (n_nodes8) *n_nodes8 = used ? h->bvh_nodes8 : 0;
+    if (depth8) *depth8 = used ? h->bvh_depth8 : 0;
+    CK(cudaSetDevice(h->device));
+    if (nodes8_out && used) CK(cudaMemcpy(nodes8_out, h->sv.nodes8, (size_t)h->bvh_nodes8 * 20 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 

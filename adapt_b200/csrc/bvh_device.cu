@@ -99,15 +99,16 @@ __global__ void k_flag(const int* __restrict__ rng_first, const int* __restrict_
 __global__ void k_emit_nodes(int n_inner, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rng_first,
                              const int* __restrict__ rng_last, const float* __restrict__ pbox, const uint32_t* __restrict__ order,
                              const float* __restrict__ ibox, const uint32_t* __restrict__ dense, const uint32_t* __restrict__ keep,
-                             float* __restrict__ nodes) {
+                             float* __restrict__ nodes, const int* __restrict__ newpos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_inner) lbvh::emit_node(i, left, right, rng_first, rng_last, pbox, order, ibox, dense, keep, nodes);
+    if (i < n_inner) lbvh::emit_node(i, left, right, rng_first, rng_last, pbox, order, ibox, dense, keep, nodes, newpos);
 }
 
 __global__ void k_emit_prims(int n, const uint32_t* __restrict__ order, const float* __restrict__ prim9, const uint8_t* __restrict__ sph,
-                             const int32_t* __restrict__ prim_obj, const uint8_t* __restrict__ obj_class, float* __restrict__ prims) {
+                             const int32_t* __restrict__ prim_obj, const uint8_t* __restrict__ obj_class, float* __restrict__ prims,
+                             const int* __restrict__ newpos) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) lbvh::emit_prim(k, order, prim9, sph, prim_obj, obj_class, prims);
+    if (k < n) lbvh::emit_prim(k, order, prim9, sph, prim_obj, obj_class, prims, newpos);
 }
 
 __global__ void k_single_leaf(const float* __restrict__ pbox, int n, float* __restrict__ nodes, uint32_t* __restrict__ order) {
@@ -209,6 +210,19 @@ __global__ void k_sah_scatter(int n, const int* __restrict__ pseg, const uint32_
     }
 }
 
+// ---- compressed 8-wide tree collapsed from the fitted hierarchy, level by level (bvh_lbvh.h: cw8_*) ---------------------------------
+__global__ void k_cw8_collapse(int lvl_begin, int m, const int* __restrict__ wroot, lbvh::Cw8In I, int* __restrict__ items,
+                               uint64_t* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) counts[i] = lbvh::cw8_collapse(lvl_begin + i, wroot, I, items);
+    else if (i == m) counts[i] = 0ull;                               // the scan's extra element: totals
+}
+__global__ void k_cw8_emit(int lvl_begin, int m, int* wroot, lbvh::Cw8In I, const int* __restrict__ items, const uint64_t* __restrict__ scan,
+                           int child_base0, int prim_base0, int* __restrict__ newpos, uint32_t* __restrict__ nodes8) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) lbvh::cw8_emit(lvl_begin + i, wroot, I, items, scan[i], child_base0, prim_base0, wroot, newpos, nodes8);
+}
+
 // One cudaMalloc for every temporary of a build; sub-buffers are 256-byte aligned.
 struct Arena {
     uint8_t* base = nullptr;
@@ -232,21 +246,23 @@ struct Arena {
     } while (0)
 
 cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, const int32_t* prim_obj, const uint8_t* obj_class,
-                             int32_t n, int32_t n_objects, int max_leaf, cudaStream_t st, DeviceBvh& out, std::string& what, int builder, float traverse_cost) {
+                             int32_t n, int32_t n_objects, int max_leaf, cudaStream_t st, DeviceBvh& out, std::string& what, int builder, float traverse_cost, bool eight) {
     Arena A;
-    float* d_nodes = nullptr; float* d_prims = nullptr;
+    float* d_nodes = nullptr; float* d_prims = nullptr; uint32_t* d_nodes8 = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup_out = [&]() {
         if (d_nodes) cudaFree(d_nodes);
         if (d_prims) cudaFree(d_prims);
+        if (d_nodes8) cudaFree(d_nodes8);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
-        d_nodes = d_prims = nullptr; e0 = e1 = nullptr;
+        d_nodes = d_prims = nullptr; d_nodes8 = nullptr; e0 = e1 = nullptr;
     };
     if (n <= 0 || n_objects <= 0 || max_leaf < 1 || max_leaf > 8) { what = "build_bvh_device: bad argument"; return cudaErrorInvalidValue; }
     const bool tiny = n <= max_leaf;
     const size_t N = (size_t)n, NI = (size_t)(n > 1 ? n - 1 : 1);
     const int n_inner = n - 1;
+    int n_nodes8 = 0, depth8 = 0;
     // ---- temporaries: one allocation (about 220 bytes per primitive, ~110 MB for 500k triangles), sized before anything runs
     size_t sort_bytes = 0, scan_bytes = 0;
     if (!tiny) {
@@ -256,16 +272,18 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
     }
     // builder 2 (binned SAH): segments of one level (more than max_leaf primitives each), their bins, the per-position scan
     const bool sah = builder == 2 && !tiny;
+    const bool wide = eight && !tiny && max_leaf <= 3;               // a leaf child of an 8-wide node holds at most 3 primitives
     const size_t MS = sah ? N / (size_t)(max_leaf + 1) + 2 : 0;
     const size_t NBIN = MS * 3 * LB_SAH_BINS;
     size_t scan64_bytes = 0;
-    if (sah) LBCK(cub::DeviceScan::ExclusiveSum(nullptr, scan64_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, n + 1, st));
+    if (sah || wide) LBCK(cub::DeviceScan::ExclusiveSum(nullptr, scan64_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, n + 1, st));
     const size_t tmp_bytes = std::max(std::max(sort_bytes, scan_bytes), scan64_bytes);
     A.cap = Arena::pad(N * 36) + Arena::pad(N) + Arena::pad(N * 4) + Arena::pad((size_t)n_objects) + Arena::pad(N * 24) + Arena::pad(N * 12) + Arena::pad(24) +
             2 * Arena::pad(N * 8) + 2 * Arena::pad(N * 4) + 7 * Arena::pad(NI * 4) + Arena::pad(N * 4) + Arena::pad(NI * 24) +
             2 * Arena::pad((NI + 1) * 4) + Arena::pad(NI * 64) + Arena::pad(tmp_bytes ? tmp_bytes : 1) + 4096;
     if (sah) A.cap += 2 * Arena::pad(N * 4) + Arena::pad(N * 4) + 2 * (3 * Arena::pad(MS * 4) + Arena::pad(MS * 24)) + 3 * Arena::pad(MS * 4) +
                       Arena::pad(MS * 8) + Arena::pad(NBIN * 4) + Arena::pad(NBIN * 24) + 2 * Arena::pad((N + 1) * 8) + 2 * Arena::pad(N * 4) + 256;
+    if (wide) A.cap += Arena::pad(NI * 4) + Arena::pad(NI * 32) + Arena::pad(N * 4) + 2 * Arena::pad((NI + 1) * 8) + Arena::pad(NI * 80) + 256;
     LBCK(cudaMalloc((void**)&A.base, A.cap));
     float* d_prim9 = A.take<float>(N * 9); uint8_t* d_sph = A.take<uint8_t>(N); int32_t* d_pobj = A.take<int32_t>(N);
     uint8_t* d_ocls = A.take<uint8_t>((size_t)n_objects); float* d_pbox = A.take<float>(N * 6); float* d_pcen = A.take<float>(N * 3); unsigned* d_cb = A.take<unsigned>(6);
@@ -288,6 +306,12 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
         tree.left = d_left; tree.right = d_right; tree.rng_first = d_first; tree.rng_last = d_last; tree.parent_inner = d_par_i; tree.parent_leaf = d_par_l;
         tree.keep = d_flag; tree.root_gamma = A.take<int>(1); tree.small_last = A.take<int>(N); tree.small_parent = A.take<int>(N);
         tree.traverse_cost = traverse_cost;
+    }
+    int* d_wroot = nullptr; int* d_items = nullptr; int* d_newpos = nullptr; uint64_t* d_wcnt = nullptr; uint64_t* d_wscan = nullptr;
+    uint32_t* d_nodes8_tmp = nullptr;
+    if (wide) {
+        d_wroot = A.take<int>(NI); d_items = A.take<int>(NI * 8); d_newpos = A.take<int>(N);
+        d_wcnt = A.take<uint64_t>(NI + 1); d_wscan = A.take<uint64_t>(NI + 1); d_nodes8_tmp = A.take<uint32_t>(NI * 20);
     }
     if (A.used > A.cap) { what = "build_bvh_device: arena accounting"; cleanup_out(); return cudaErrorUnknown; }
     LBCK(cudaMalloc((void**)&d_prims, N * 12 * sizeof(float)));
@@ -343,10 +367,31 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
         k_fit<<<lb_grid(n), LB_BLOCK, 0, st>>>(n, d_left, d_right, d_first, d_last, d_par_i, d_par_l, d_pbox, d_order, d_ibox, d_height,
                                                 d_arrive, d_flag);
         LBCK(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, (const uint32_t*)d_flag, d_dense, n_inner + 1, st));
+        if (wide) {
+            // breadth-first over the wide nodes: a level's nodes are collapsed, their inner children and leaf primitives counted and
+            // scanned, then emitted -- which names the next level's roots and the record position of every leaf primitive
+            lbvh::Cw8In I{d_left, d_right, d_first, d_last, d_flag, d_ibox, d_pbox, d_order};
+            LBCK(cudaMemsetAsync(d_wroot, 0, sizeof(int), st));       // the root of the wide tree is binary node 0
+            int lvl_begin = 0, lvl_end = 1, prims_done = 0;
+            while (lvl_begin < lvl_end) {
+                const int m = lvl_end - lvl_begin;
+                k_cw8_collapse<<<lb_grid(m + 1), LB_BLOCK, 0, st>>>(lvl_begin, m, d_wroot, I, d_items, d_wcnt);
+                LBCK(cub::DeviceScan::ExclusiveSum(d_tmp, scan64_bytes, (const uint64_t*)d_wcnt, d_wscan, m + 1, st));
+                uint64_t totals = 0;
+                LBCK(cudaMemcpyAsync(&totals, d_wscan + m, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+                k_cw8_emit<<<lb_grid(m), LB_BLOCK, 0, st>>>(lvl_begin, m, d_wroot, I, d_items, d_wscan, lvl_end, prims_done, d_newpos, d_nodes8_tmp);
+                LBCK(cudaStreamSynchronize(st));
+                lvl_begin = lvl_end; lvl_end += (int)(uint32_t)totals; prims_done += (int)(uint32_t)(totals >> 32);
+                depth8++;
+                if ((size_t)lvl_end > NI || depth8 > 64) { what = "build_bvh_device: 8-wide level loop out of range"; cleanup_out(); return cudaErrorUnknown; }
+            }
+            n_nodes8 = lvl_end;
+            if (prims_done != n) { what = "build_bvh_device: 8-wide tree does not cover every primitive"; cleanup_out(); return cudaErrorUnknown; }
+        }
         k_emit_nodes<<<lb_grid(n_inner), LB_BLOCK, 0, st>>>(n_inner, d_left, d_right, d_first, d_last, d_pbox, d_order, d_ibox, d_dense, d_flag,
-                                                            d_nodes_tmp);
+                                                            d_nodes_tmp, wide ? d_newpos : nullptr);
     }
-    k_emit_prims<<<lb_grid(n), LB_BLOCK, 0, st>>>(n, d_order, d_prim9, d_sph, d_pobj, d_ocls, d_prims);
+    k_emit_prims<<<lb_grid(n), LB_BLOCK, 0, st>>>(n, d_order, d_prim9, d_sph, d_pobj, d_ocls, d_prims, wide ? d_newpos : nullptr);
     LBCK(cudaEventRecord(e1, st));
 
     // ---- results the host needs: node count, height and box of the root; then the exact-size node array
@@ -366,6 +411,10 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
     if (h_cnt < 1 || (size_t)h_cnt > NI) { what = "build_bvh_device: node count out of range"; cleanup_out(); return cudaErrorUnknown; }
     LBCK(cudaMalloc((void**)&d_nodes, (size_t)h_cnt * 16 * sizeof(float)));
     LBCK(cudaMemcpyAsync(d_nodes, d_nodes_tmp, (size_t)h_cnt * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (n_nodes8 > 0) {
+        LBCK(cudaMalloc((void**)&d_nodes8, (size_t)n_nodes8 * 20 * sizeof(uint32_t)));
+        LBCK(cudaMemcpyAsync(d_nodes8, d_nodes8_tmp, (size_t)n_nodes8 * 20 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
     LBCK(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -373,6 +422,7 @@ cudaError_t build_bvh_device(const float* primitives, const uint8_t* is_sphere, 
     out.nodes = reinterpret_cast<float4*>(d_nodes);
     out.leaf_prims = reinterpret_cast<float4*>(d_prims);
     out.n_nodes = (int)h_cnt; out.depth = depth; out.build_ms = ms;
+    out.nodes8 = reinterpret_cast<uint4*>(d_nodes8); out.n_nodes8 = n_nodes8; out.depth8 = depth8;
     for (int a = 0; a < 3; a++) { out.root_lo[a] = root[a]; out.root_hi[a] = root[3 + a]; }
     return cudaSuccess;
 }

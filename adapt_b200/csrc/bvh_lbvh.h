@@ -79,6 +79,13 @@ LB_HD float bits2f(uint32_t u) {
     union { float f; uint32_t u; } c; c.u = u; return c.f;
 #endif
 }
+LB_HD uint32_t f2bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
 LB_HD float next_down(float x) { return nextafterf(x, -3.0e38f); }
 LB_HD float next_up(float x) { return nextafterf(x, 3.0e38f); }
 
@@ -199,10 +206,12 @@ LB_HD void fit_node(int cur, const int* __restrict__ left, const int* __restrict
 LB_HD bool keep_by_size(const int* __restrict__ rng_first, const int* __restrict__ rng_last, int i, int max_leaf) {
     return rng_last[i] - rng_first[i] + 1 > max_leaf;
 }
+// newpos (optional): where the record of sorted position k goes in the leaf-record array -- the 8-wide collapse stores the records node
+// by node of the wide tree (cw8_emit); a leaf's records stay contiguous and in order
 LB_HD int child_code(int c, const int* __restrict__ rng_first, const int* __restrict__ rng_last, const uint32_t* __restrict__ dense,
-                     const uint32_t* __restrict__ keep) {
-    if (c < 0) return ~(((~c) << 3) | 0);
-    if (!keep[c]) return ~((rng_first[c] << 3) | (rng_last[c] - rng_first[c]));
+                     const uint32_t* __restrict__ keep, const int* __restrict__ newpos = nullptr) {
+    if (c < 0) return ~(((newpos ? newpos[~c] : ~c) << 3) | 0);
+    if (!keep[c]) return ~(((newpos ? newpos[rng_first[c]] : rng_first[c]) << 3) | (rng_last[c] - rng_first[c]));
     return (int)dense[c];
 }
 // node16: 16 floats of one 64-byte node (bvh_build.h: GpuNode)
@@ -215,7 +224,7 @@ LB_HD void put_child_box(float* __restrict__ node16, int child, const float* __r
 LB_HD void emit_node(int i, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rng_first,
                      const int* __restrict__ rng_last, const float* __restrict__ pbox, const uint32_t* __restrict__ order,
                      const float* __restrict__ ibox, const uint32_t* __restrict__ dense, const uint32_t* __restrict__ keep,
-                     float* __restrict__ nodes) {
+                     float* __restrict__ nodes, const int* __restrict__ newpos = nullptr) {
     if (!keep[i]) return;
     float* g = nodes + (size_t)dense[i] * 16;
     float a[6], b[6];
@@ -224,8 +233,8 @@ LB_HD void emit_node(int i, const int* __restrict__ left, const int* __restrict_
     put_child_box(g, 0, a);
     put_child_box(g, 1, b);
     int32_t* gc = reinterpret_cast<int32_t*>(g + 12);
-    gc[0] = child_code(left[i], rng_first, rng_last, dense, keep);
-    gc[1] = child_code(right[i], rng_first, rng_last, dense, keep);
+    gc[0] = child_code(left[i], rng_first, rng_last, dense, keep, newpos);
+    gc[1] = child_code(right[i], rng_first, rng_last, dense, keep, newpos);
     gc[2] = 0; gc[3] = 0;
 }
 // root of a scene with at most max_leaf primitives: one leaf, second child an empty box (to_gpu_layout's single-leaf case)
@@ -240,10 +249,11 @@ LB_HD void emit_single_leaf(const float* __restrict__ pbox, int n, float* __rest
 }
 // 48-byte leaf record of sorted position k (bvh_build.h: GpuPrim)
 LB_HD void emit_prim(int k, const uint32_t* __restrict__ order, const float* __restrict__ prim9, const uint8_t* __restrict__ sph,
-                     const int32_t* __restrict__ prim_obj, const uint8_t* __restrict__ obj_class, float* __restrict__ prims) {
+                     const int32_t* __restrict__ prim_obj, const uint8_t* __restrict__ obj_class, float* __restrict__ prims,
+                     const int* __restrict__ newpos = nullptr) {
     const uint32_t p = order[k];
     const float* v = prim9 + (size_t)p * 9;
-    float* g = prims + (size_t)k * 12;
+    float* g = prims + (size_t)(newpos ? newpos[k] : k) * 12;
     const bool s = sph && sph[p];
     if (s) {
         g[0] = v[0]; g[1] = v[1]; g[2] = v[2]; g[3] = v[3];
@@ -553,18 +563,136 @@ LB_HD int sah_scatter(int k, const int* __restrict__ pseg, const uint32_t* __res
     return child;
 }
 
+// ---- compressed 8-wide tree from the fitted binary hierarchy (bvh_build.h: GpuNode8; host counterpart bvh_build.cpp: to_gpu_layout) ----
+// Level by level over the wide nodes, breadth-first: cw8_collapse (per wide node: adopt the two children of the inner child with the
+// largest surface area until there are eight children or only leaves; counts of inner children and of leaf primitives) -> exclusive
+// scan of the counts (CUB) -> cw8_emit (octant-ordered slots, 8-bit boxes on the node's power-of-two grid, the next level's roots, and
+// where each leaf primitive's record goes: the records of a node's leaf children are stored back to back).  Needs leaves of at most
+// three primitives (max_leaf <= 3).  An "item" is a child code of the binary hierarchy: >= 0 an inner node id (kept: inner child of the
+// wide node; not kept: a leaf over its range), < 0 the single primitive at sorted position ~code.
+struct Cw8In {
+    const int* left; const int* right; const int* rng_first; const int* rng_last; const uint32_t* keep;
+    const float* ibox; const float* pbox; const uint32_t* order;
+};
+LB_HD bool cw8_is_inner(const Cw8In& I, int c) { return c >= 0 && I.keep[c] != 0u; }
+LB_HD void cw8_item_box(const Cw8In& I, int c, float* b6) {
+    const float* s = c >= 0 ? I.ibox + (size_t)c * 6 : I.pbox + (size_t)I.order[~c] * 6;
+    for (int a = 0; a < 6; a++) b6[a] = LB_LD(s + a);
+}
+LB_HD float cw8_half_area(const float* b6) {
+    const float dx = LB_FSUB(b6[3], b6[0]), dy = LB_FSUB(b6[4], b6[1]), dz = LB_FSUB(b6[5], b6[2]);
+    return LB_FADD(LB_FADD(LB_FMUL(dx, dy), LB_FMUL(dy, dz)), LB_FMUL(dz, dx));
+}
+LB_HD void cw8_item_range(const Cw8In& I, int c, int& first, int& cnt) {
+    if (c < 0) { first = ~c; cnt = 1; } else { first = I.rng_first[c]; cnt = I.rng_last[c] - first + 1; }
+}
+// wide node w (root = binary inner node wroot[w]): its up to eight items -> items[w * 8 ..], counts packed as inner | prims << 32
+LB_HD uint64_t cw8_collapse(int w, const int* __restrict__ wroot, const Cw8In& I, int* __restrict__ items) {
+    const int root = wroot[w];
+    int c[8]; float area[8]; int n = 2;
+    c[0] = I.left[root]; c[1] = I.right[root];
+    for (int k = 0; k < 2; k++) { float b[6]; cw8_item_box(I, c[k], b); area[k] = cw8_is_inner(I, c[k]) ? cw8_half_area(b) : -1.f; }
+    while (n < 8) {
+        int best = -1; float best_area = -1.f;
+        for (int k = 0; k < n; k++) if (area[k] > best_area) { best_area = area[k]; best = k; }
+        if (best < 0) break;
+        const int node = c[best];
+        c[best] = I.left[node]; c[n] = I.right[node];
+        float b[6];
+        cw8_item_box(I, c[best], b); area[best] = cw8_is_inner(I, c[best]) ? cw8_half_area(b) : -1.f;
+        cw8_item_box(I, c[n], b); area[n] = cw8_is_inner(I, c[n]) ? cw8_half_area(b) : -1.f;
+        n++;
+    }
+    uint32_t n_inner = 0, n_prims = 0;
+    for (int k = 0; k < 8; k++) {
+        items[(size_t)w * 8 + k] = k < n ? c[k] : (int)0x7fffffff;        // 0x7fffffff: no item
+        if (k >= n) continue;
+        if (cw8_is_inner(I, c[k])) n_inner++;
+        else { int f, m; cw8_item_range(I, c[k], f, m); n_prims += (uint32_t)m; }
+    }
+    return (uint64_t)n_inner | ((uint64_t)n_prims << 32);
+}
+// Octant-ordered slots, quantised boxes, node record; inner children become the roots of wide nodes child_base.., leaf primitives get their
+// record positions prim_base.. (newpos).  scan_w = exclusive sum of cw8_collapse's counts over this level's nodes.
+LB_HD void cw8_emit(int w, const int* __restrict__ wroot_in, const Cw8In& I, const int* __restrict__ items, uint64_t scan_w,
+                    int child_base0, int prim_base0, int* __restrict__ wroot_out, int* __restrict__ newpos, uint32_t* __restrict__ nodes8) {
+    const int root = wroot_in[w];
+    float nb[6];
+    cw8_item_box(I, root, nb);
+    int in[8]; float cb[8][6]; int n = 0;
+    for (int k = 0; k < 8; k++) { const int c = items[(size_t)w * 8 + k]; if (c != (int)0x7fffffff) { in[n] = c; cw8_item_box(I, c, cb[n]); n++; } }
+    // slot s stands for the corner (s & 1 ? +x : -x, s & 2 ? +y : -y, s & 4 ? +z : -z): greedy assignment of the (child, slot) pair whose
+    // centre offset from the node's centre points most towards that corner
+    float cost[8][8];
+    for (int k = 0; k < n; k++) {
+        float d[3];
+        for (int a = 0; a < 3; a++) d[a] = LB_FSUB(LB_FMUL(0.5f, LB_FADD(cb[k][a], cb[k][3 + a])), LB_FMUL(0.5f, LB_FADD(nb[a], nb[3 + a])));
+        for (int s8 = 0; s8 < 8; s8++)
+            cost[k][s8] = LB_FADD(LB_FADD((s8 & 1) ? d[0] : -d[0], (s8 & 2) ? d[1] : -d[1]), (s8 & 4) ? d[2] : -d[2]);
+    }
+    int slot_child[8]; bool child_done[8], slot_done[8];
+    for (int k = 0; k < 8; k++) { slot_child[k] = -1; child_done[k] = false; slot_done[k] = false; }
+    for (int it = 0; it < n; it++) {
+        int bk = -1, bs = -1; float best = -3.0e38f;
+        for (int k = 0; k < n; k++) if (!child_done[k])
+            for (int s8 = 0; s8 < 8; s8++) if (!slot_done[s8] && cost[k][s8] > best) { best = cost[k][s8]; bk = k; bs = s8; }
+        child_done[bk] = true; slot_done[bs] = true; slot_child[bs] = bk;
+    }
+    // grid: origin a quarter step below the node's box, the smallest power-of-two step that covers the box in 254 steps
+    float p[3], step[3]; uint32_t ebits[3];
+    for (int a = 0; a < 3; a++) {
+        const float ext = fmaxf(LB_FSUB(nb[3 + a], nb[a]), 1e-30f);
+        int e = -100;
+        while (e < 100 && LB_FMUL(ldexpf(1.0f, e), 254.0f) < ext) e++;
+        step[a] = ldexpf(1.0f, e);
+        ebits[a] = (uint32_t)(e + 127);
+        p[a] = LB_FSUB(nb[a], LB_FMUL(0.25f, step[a]));
+    }
+    uint32_t imask = 0; uint32_t meta[8], q[6][8];
+    for (int s8 = 0; s8 < 8; s8++) { meta[s8] = 0; for (int a = 0; a < 3; a++) { q[a][s8] = 255; q[3 + a][s8] = 0; } }   // empty slot: inverted box
+    const int child_base = child_base0 + (int)(uint32_t)scan_w, prim_base = prim_base0 + (int)(uint32_t)(scan_w >> 32);
+    int next_child = child_base, next_prim = prim_base;
+    for (int s8 = 0; s8 < 8; s8++) {
+        const int k = slot_child[s8];
+        if (k < 0) continue;
+        const int c = in[k];
+        if (cw8_is_inner(I, c)) {
+            imask |= 1u << s8; meta[s8] = (1u << 5) | (24u + (uint32_t)s8);
+            wroot_out[next_child++] = c;
+        } else {
+            int first, cnt; cw8_item_range(I, c, first, cnt);
+            meta[s8] = (((1u << cnt) - 1u) << 5) | (uint32_t)(next_prim - prim_base);
+            for (int i = 0; i < cnt; i++) newpos[first + i] = next_prim + i;
+            next_prim += cnt;
+        }
+        for (int a = 0; a < 3; a++) {
+            // lower planes rounded down, upper planes up, 1/64 step of margin, then the float re-check of  p + q * step  against the box
+            int lo = (int)floor((double)LB_FSUB(cb[k][a], p[a]) / (double)step[a] - 1.0 / 64.0);
+            int hi = (int)ceil((double)LB_FSUB(cb[k][3 + a], p[a]) / (double)step[a] + 1.0 / 64.0);
+            lo = lo < 0 ? 0 : (lo > 255 ? 255 : lo); hi = hi < 0 ? 0 : (hi > 255 ? 255 : hi);
+            while (lo > 0 && LB_FADD(p[a], LB_FMUL((float)lo, step[a])) > cb[k][a]) lo--;
+            while (hi < 255 && LB_FADD(p[a], LB_FMUL((float)hi, step[a])) < cb[k][3 + a]) hi++;
+            if (hi <= lo) { if (hi < 255) hi = lo + 1; else lo = hi - 1; }
+            q[a][s8] = (uint32_t)lo; q[3 + a][s8] = (uint32_t)hi;
+        }
+    }
+    uint32_t* g = nodes8 + (size_t)w * 20;
+    g[0] = f2bits(p[0]); g[1] = f2bits(p[1]); g[2] = f2bits(p[2]);
+    g[3] = ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24);
+    g[4] = (uint32_t)child_base; g[5] = (uint32_t)prim_base;
+    g[6] = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
+    g[7] = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
+    for (int a = 0; a < 6; a++) {
+        g[8 + a * 2] = q[a][0] | (q[a][1] << 8) | (q[a][2] << 16) | (q[a][3] << 24);
+        g[9 + a * 2] = q[a][4] | (q[a][5] << 8) | (q[a][6] << 16) | (q[a][7] << 24);
+    }
+}
+
 // ---- refit: the same tree over new vertices (adapt_refit_geometry) -------------------------------------------------------------
 // The launch sequence of refit_bvh_device (bvh_device.cu) and of tests/lbvh_host:  refit_prim for every record, refit_links for every
 // node, then for every node refit_leaf_children followed by the climb -- a node is complete once its own thread has written its leaf
 // children's boxes and every inner child has delivered its box (pending[i] arrivals); whoever completes it carries its box into the
 // parent's child slot (refit_carry) and goes on with the parent.
-LB_HD uint32_t f2bits(float f) {
-#if defined(__CUDA_ARCH__)
-    return __float_as_uint(f);
-#else
-    uint32_t u; memcpy(&u, &f, 4); return u;
-#endif
-}
 // leaf record k <- the new vertices of the primitive it names (record word 9 = primitive id, sphere flag in bit 31 of word 10)
 LB_HD void refit_prim(int k, const float* __restrict__ prim9, float* __restrict__ prims) {
     float* g = prims + (size_t)k * 12;

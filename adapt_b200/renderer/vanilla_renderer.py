@@ -248,13 +248,21 @@ class Renderer:
         self._cnt = int(spp)
 
     def bvh_export(self, arrays: bool = True) -> dict:
-        """Stage-level hook: the device acceleration structure (64-byte nodes, 48-byte leaf records), its builder and build time."""
+        """Stage-level hook: the device acceleration structure (64-byte nodes, 48-byte leaf records; the 80-byte nodes of the compressed
+        8-wide tree when the handle traces through one), its builder and build time."""
         fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
         nn, npr, dep, bld = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         ms = C.c_float()
         check(self._lib, self._lib.adapt_bvh_export(self._handle, C.byref(nn), C.byref(npr), C.byref(dep), C.byref(bld), C.byref(ms),
                                                     None, None), "adapt_bvh_export")
         out = dict(n_nodes=nn.value, n_prims=npr.value, depth=dep.value, builder=bld.value, build_ms=ms.value)
+        nn8, dep8 = C.c_int32(), C.c_int32()
+        check(self._lib, self._lib.adapt_bvh_export_wide(self._handle, C.byref(nn8), C.byref(dep8), None), "adapt_bvh_export_wide")
+        out.update(n_nodes8=nn8.value, depth8=dep8.value)           # 0: the handle traces through the binary tree
+        if arrays and nn8.value > 0:
+            nodes8 = np.zeros((nn8.value, 20), np.uint32)
+            check(self._lib, self._lib.adapt_bvh_export_wide(self._handle, None, None, nodes8.ctypes.data_as(C.POINTER(C.c_uint32))), "adapt_bvh_export_wide")
+            out.update(nodes8=nodes8)
         if arrays:
             nodes = np.zeros((nn.value, 16), np.float32); prims = np.zeros((npr.value, 12), np.float32)
             check(self._lib, self._lib.adapt_bvh_export(self._handle, None, None, None, None, None, nodes.ctypes.data_as(fp),

@@ -44,7 +44,7 @@ def _norm(prims, sph, prim_obj, obj_class):
     return prims, n, sph, prim_obj, obj_class
 
 
-def build_tree(prims, sph=None, prim_obj=None, obj_class=None, max_leaf=4, builder="lbvh", order_seed=0, traverse_cost=1.0):
+def build_tree(prims, sph=None, prim_obj=None, obj_class=None, max_leaf=4, builder="lbvh", order_seed=0, traverse_cost=1.0, eight=False):
     """-> dict(nodes (n_nodes,16), prims (n,12), depth, root_box) from the emulated device builders ("lbvh": linear BVH, "sah_device":
     level-synchronous binned SAH, its per-position steps run in an order permuted by order_seed) or the library's host SAH builder ("sah")."""
     L = load()
@@ -53,17 +53,24 @@ def build_tree(prims, sph=None, prim_obj=None, obj_class=None, max_leaf=4, build
     recs = np.zeros((n, 12), np.float32)
     nn, dp = C.c_int(), C.c_int()
     root = np.zeros(6, np.float32)
+    nodes8 = None
     if builder == "sah_device":
-        lv = C.c_int()
+        lv, nn8, dp8 = C.c_int(), C.c_int(), C.c_int()
+        nodes8 = np.zeros((max(1, n - 1), 20), np.uint32) if eight else None
         rc = L.lbvh_host_build_sah(_p(prims), _p(sph), _p(prim_obj), _p(obj_class), n, max_leaf, _p(nodes), _p(recs), C.byref(nn), C.byref(dp), _p(root),
-                                   C.c_uint(order_seed), C.byref(lv), C.c_float(traverse_cost))
+                                   C.c_uint(order_seed), C.byref(lv), C.c_float(traverse_cost), _p(nodes8) if eight else None, C.byref(nn8), C.byref(dp8))
+        if eight:
+            nodes8 = nodes8[:nn8.value].copy()
     elif builder == "lbvh":
         rc = L.lbvh_host_build(_p(prims), _p(sph), _p(prim_obj), _p(obj_class), n, max_leaf, _p(nodes), _p(recs), C.byref(nn), C.byref(dp), _p(root))
     else:
         rc = L.sah_host_build(_p(prims), _p(sph), _p(prim_obj), _p(obj_class), n, max_leaf, _p(nodes), _p(recs), C.byref(nn), C.byref(dp))
     if rc != 0:
         raise RuntimeError(f"{builder} host build failed: {rc}")
-    return dict(nodes=nodes[:nn.value].copy(), prims=recs, depth=dp.value, root_box=root)
+    out = dict(nodes=nodes[:nn.value].copy(), prims=recs, depth=dp.value, root_box=root)
+    if nodes8 is not None:
+        out["nodes8"] = nodes8; out["depth8"] = dp8.value
+    return out
 
 
 def validate(nodes, recs, prims, sph=None):
@@ -85,6 +92,18 @@ def trace_check(nodes, recs, rays_o, rays_d):
     op = np.zeros(nr, np.int32); ot = np.zeros(nr, np.float32); bp = np.zeros(nr, np.int32); bt = np.zeros(nr, np.float32)
     v = L.lbvh_trace_check(_p(nodes), _p(recs), recs.shape[0], _p(ro), _p(rd), nr, _p(op), _p(ot), _p(bp), _p(bt))
     return op, ot, bp, bt, v / 1000.0
+
+
+def cw8_trace_check(nodes8, recs, prims, sph, rays_o, rays_d):
+    """Closest hits through a compressed 8-wide tree with an independent decoder (+ structural checks) -> (rc, t, prim)."""
+    L = load()
+    prims, n, sph, _, _ = _norm(prims, sph, None, None)
+    nodes8 = np.ascontiguousarray(nodes8, np.uint32); recs = np.ascontiguousarray(recs, np.float32)
+    ro = np.ascontiguousarray(rays_o, np.float32).reshape(-1, 3); rd = np.ascontiguousarray(rays_d, np.float32).reshape(-1, 3)
+    nr = ro.shape[0]
+    ot = np.zeros(nr, np.float32); op = np.zeros(nr, np.int32)
+    rc = L.cw8_trace_check(_p(nodes8), nodes8.shape[0], _p(recs), n, _p(prims), _p(sph), _p(ro), _p(rd), nr, _p(ot), _p(op))
+    return rc, ot, op
 
 
 def last_prims_tested():

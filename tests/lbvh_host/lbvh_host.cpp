@@ -79,7 +79,7 @@ int lbvh_host_build(const float* prim9, const uint8_t* sph, const int32_t* prim_
 // through the scan, atomics only for min / max / count).
 int lbvh_host_build_sah(const float* prim9, const uint8_t* sph, const int32_t* prim_obj, const uint8_t* obj_class, int n, int max_leaf,
                         float* nodes_out, float* prims_out, int* n_nodes, int* depth, float* root_box, unsigned order_seed, int* levels_out,
-                        float traverse_cost) {
+                        float traverse_cost, uint32_t* nodes8_out, int* n_nodes8, int* depth8) {
     if (n <= 0 || max_leaf < 1 || max_leaf > 8) return -1;
     if (n <= max_leaf) return lbvh_host_build(prim9, sph, prim_obj, obj_class, n, max_leaf, nodes_out, prims_out, n_nodes, depth, root_box);
     std::vector<float> pbox((size_t)n * 6), pcen((size_t)n * 3);
@@ -161,11 +161,144 @@ int lbvh_host_build_sah(const float* prim9, const uint8_t* sph, const int32_t* p
     std::vector<uint32_t> dense(ni);
     uint32_t cnt = 0;
     for (int i = 0; i < ni; i++) { dense[i] = cnt; cnt += keep[i]; }
+    // the 8-wide collapse of build_bvh_device (breadth-first over the wide nodes), when asked for and the leaves allow it
+    std::vector<int> newpos;
+    if (nodes8_out && max_leaf <= 3) {
+        Cw8In I{left.data(), right.data(), first.data(), last.data(), keep.data(), ibox.data(), pbox.data(), ord.data()};
+        std::vector<int> wroot((size_t)ni, 0), items((size_t)ni * 8, 0);
+        std::vector<uint64_t> wcnt((size_t)ni + 1), wscan((size_t)ni + 1);
+        newpos.assign((size_t)n, -1);
+        int lvl_begin = 0, lvl_end = 1, prims_done = 0, d8 = 0;
+        while (lvl_begin < lvl_end) {
+            const int m = lvl_end - lvl_begin;
+            for (int i = 0; i < m; i++) wcnt[i] = cw8_collapse(lvl_begin + i, wroot.data(), I, items.data());
+            wcnt[m] = 0;
+            uint64_t a = 0;
+            for (int i = 0; i <= m; i++) { wscan[i] = a; a += wcnt[i]; }
+            for (int i = m - 1; i >= 0; i--)
+                cw8_emit(lvl_begin + i, wroot.data(), I, items.data(), wscan[i], lvl_end, prims_done, wroot.data(), newpos.data(), nodes8_out);
+            lvl_begin = lvl_end; lvl_end += (int)(uint32_t)wscan[m]; prims_done += (int)(uint32_t)(wscan[m] >> 32);
+            if (++d8 > 64 || lvl_end > ni) return -7;
+        }
+        if (prims_done != n) return -8;
+        for (int k = 0; k < n; k++) if (newpos[k] < 0) return -9;
+        *n_nodes8 = lvl_end; *depth8 = d8;
+    } else if (n_nodes8) { *n_nodes8 = 0; *depth8 = 0; }
+    const int* np = newpos.empty() ? nullptr : newpos.data();
     for (int i = 0; i < ni; i++)
-        emit_node(i, left.data(), right.data(), first.data(), last.data(), pbox.data(), ord.data(), ibox.data(), dense.data(), keep.data(), nodes_out);
-    for (int k = 0; k < n; k++) emit_prim(k, ord.data(), prim9, sph, prim_obj, obj_class, prims_out);
+        emit_node(i, left.data(), right.data(), first.data(), last.data(), pbox.data(), ord.data(), ibox.data(), dense.data(), keep.data(), nodes_out, np);
+    for (int k = 0; k < n; k++) emit_prim(k, ord.data(), prim9, sph, prim_obj, obj_class, prims_out, np);
     *n_nodes = (int)cnt; *depth = height[0];
     for (int a = 0; a < 6; a++) root_box[a] = ibox[a];
+    return 0;
+}
+
+// Closest hits through a compressed 8-wide tree (bvh_build.h: GpuNode8), decoded independently of the traversal kernel: every child box is
+// dequantised as  p + q * 2^(e - 127)  and tested with plain slabs, inner children are visited in slot order (no ordering, no culling
+// tricks), leaf children test the records their meta byte names.  out_t per ray; returns 0, or a negative code when the tree is malformed
+// (a record reached twice or never, a child index out of range).  Also checks that every child box encloses its primitives' boxes.
+int cw8_trace_check(const uint32_t* nodes8, int n_nodes8, const float* prims, int n, const float* prim9, const uint8_t* sph,
+                    const float* ro, const float* rd, int n_rays, float* out_t, int32_t* out_prim) {
+    auto f = [](uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; };
+    // structure: every record belongs to exactly one leaf child, every wide node is the child of exactly one node
+    std::vector<uint8_t> seen_rec((size_t)n, 0), seen_node((size_t)n_nodes8, 0);
+    std::vector<float> pbox((size_t)n * 6);
+    for (int i = 0; i < n; i++) prim_box(prim9, sph, i, pbox.data());
+    seen_node[0] = 1;
+    for (int w = 0; w < n_nodes8; w++) {
+        const uint32_t* g = nodes8 + (size_t)w * 20;
+        const float p[3] = {f(g[0]), f(g[1]), f(g[2])};
+        float step[3]; for (int a = 0; a < 3; a++) step[a] = std::ldexp(1.0f, (int)((g[3] >> (8 * a)) & 0xffu) - 127);
+        const uint32_t imask = g[3] >> 24;
+        int rank = 0;
+        for (int s = 0; s < 8; s++) {
+            const uint32_t meta = (g[6 + s / 4] >> (8 * (s & 3))) & 0xffu;
+            if (meta == 0) continue;
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; a++) {
+                lo[a] = p[a] + (float)((g[8 + 2 * a + s / 4] >> (8 * (s & 3))) & 0xffu) * step[a];
+                hi[a] = p[a] + (float)((g[14 + 2 * a + s / 4] >> (8 * (s & 3))) & 0xffu) * step[a];
+            }
+            if (imask & (1u << s)) {
+                const int c = (int)g[4] + rank++;
+                if (c <= w || c >= n_nodes8 || seen_node[c]) return -2;
+                seen_node[c] = 1;
+            } else {
+                const int first = (int)g[5] + (int)(meta & 31u), cnt = __builtin_popcount(meta >> 5);
+                if (cnt < 1 || cnt > 3 || first < 0 || first + cnt > n) return -3;
+                for (int k = first; k < first + cnt; k++) {
+                    if (seen_rec[k]) return -4;
+                    seen_rec[k] = 1;
+                    uint32_t pid; std::memcpy(&pid, prims + (size_t)k * 12 + 9, 4);
+                    if (pid >= (uint32_t)n) return -5;
+                    for (int a = 0; a < 3; a++) if (pbox[(size_t)pid * 6 + a] < lo[a] || pbox[(size_t)pid * 6 + 3 + a] > hi[a]) return -6;
+                }
+            }
+        }
+    }
+    for (int k = 0; k < n; k++) if (!seen_rec[k]) return -7;
+    for (int w = 0; w < n_nodes8; w++) if (!seen_node[w]) return -8;
+    auto prim_hit = [&](const float* g, const float* o, const float* d, float tmax, float& t_out) {
+        uint32_t ob; std::memcpy(&ob, g + 10, 4);
+        if (ob & 0x80000000u) {
+            float s[3] = {g[0] - o[0], g[1] - o[1], g[2] - o[2]};
+            float r2 = g[3] * g[3], c2 = s[0] * s[0] + s[1] * s[1] + s[2] * s[2], pr = d[0] * s[0] + d[1] * s[1] + d[2] * s[2];
+            float c2r = c2 - pr * pr;
+            if (c2r >= r2) return false;
+            float cut = std::sqrt(r2 - c2r), t = pr + (c2 > r2 + 1e-4f ? -cut : cut);
+            if (t > 1e-4f && t < tmax) { t_out = t; return true; }
+            return false;
+        }
+        const float* v0 = g; const float* e1 = g + 3; const float* e2 = g + 6;
+        float pv[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+        float det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+        float inv = 1.f / det;
+        float tv[3] = {o[0] - v0[0], o[1] - v0[1], o[2] - v0[2]};
+        float u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv;
+        float qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+        float v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv;
+        float t = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv;
+        if (u >= 0.f && v >= 0.f && u + v <= 1.f && t > 1e-4f && t < tmax) { t_out = t; return true; }
+        return false;
+    };
+    for (int r = 0; r < n_rays; r++) {
+        const float* o = ro + (size_t)r * 3; const float* d = rd + (size_t)r * 3;
+        float idir[3];
+        for (int a = 0; a < 3; a++) { float dd = std::fabs(d[a]) > 1e-20f ? d[a] : std::copysign(1e-20f, d[a]); idir[a] = 1.f / dd; }
+        float hit_t = 1e7f; int hp = -1;
+        std::vector<int> st; st.push_back(0);
+        while (!st.empty()) {
+            const int w = st.back(); st.pop_back();
+            const uint32_t* g = nodes8 + (size_t)w * 20;
+            const float p[3] = {f(g[0]), f(g[1]), f(g[2])};
+            float step[3]; for (int a = 0; a < 3; a++) step[a] = std::ldexp(1.0f, (int)((g[3] >> (8 * a)) & 0xffu) - 127);
+            const uint32_t imask = g[3] >> 24;
+            int rank = 0;
+            for (int s = 0; s < 8; s++) {
+                const uint32_t meta = (g[6 + s / 4] >> (8 * (s & 3))) & 0xffu;
+                const bool inner = (imask >> s) & 1u;
+                const int child = inner ? (int)g[4] + rank++ : -1;
+                if (meta == 0) continue;
+                float t0 = 0.f, t1 = hit_t;
+                for (int a = 0; a < 3; a++) {
+                    const float lo = p[a] + (float)((g[8 + 2 * a + s / 4] >> (8 * (s & 3))) & 0xffu) * step[a];
+                    const float hi = p[a] + (float)((g[14 + 2 * a + s / 4] >> (8 * (s & 3))) & 0xffu) * step[a];
+                    const float x0 = (lo - o[a]) * idir[a], x1 = (hi - o[a]) * idir[a];
+                    t0 = std::fmax(t0, std::fmin(x0, x1)); t1 = std::fmin(t1, std::fmax(x0, x1));
+                }
+                if (!(t0 <= t1 * 1.0000005f)) continue;
+                if (inner) st.push_back(child);
+                else {
+                    const int first = (int)g[5] + (int)(meta & 31u), cnt = __builtin_popcount(meta >> 5);
+                    for (int k = first; k < first + cnt; k++) {
+                        float t;
+                        if (prim_hit(prims + (size_t)k * 12, o, d, hit_t, t)) { hit_t = t; std::memcpy(&hp, prims + (size_t)k * 12 + 9, 4); }
+                    }
+                }
+            }
+        }
+        out_t[r] = hit_t; out_prim[r] = hp;
+    }
     return 0;
 }
 

@@ -63,7 +63,12 @@ def test_device_tree_equals_emulated_tree(Renderer, scene_root, scene, name, bui
     prims, sph = _tables(a, o)
     rc, depth = validate(ex["nodes"], ex["prims"], prims, sph)
     assert rc == 0 and depth == ex["depth"]
-    ref = build_tree(prims, sph, max_leaf=4, builder=builder, order_seed=3)   # the emulated threads run in a shuffled order
+    # scenes of <= 64 primitives are traced through the 8-wide tree: the device SAH builder then keeps leaves of <= 3 and collapses it too
+    wide = ex["n_nodes8"] > 0
+    assert not (wide and builder == "lbvh")
+    ref = build_tree(prims, sph, max_leaf=3 if wide else 4, builder=builder, order_seed=3, eight=wide)   # emulated threads in a shuffled order
+    if wide:
+        assert np.array_equal(ex["nodes8"], ref["nodes8"]) and ex["depth8"] == ref["depth8"]
     assert ex["n_nodes"] == ref["nodes"].shape[0] and ex["depth"] == ref["depth"]
     # geometry words of the records and the whole node array, bit for bit (object / class words depend on the scene tables)
     assert np.array_equal(ex["prims"][:, :10].view(np.uint32), ref["prims"][:, :10].view(np.uint32))
@@ -165,3 +170,38 @@ def test_refit_geometry_keeps_the_tree_and_renders_like_a_fresh_scene(Renderer, 
     fresh.render_batch(spp)
     assert np.isfinite(img).all() and rel_l2(img, fresh.pixels.to_numpy()) < 1e-5
     assert again["build_ms"] < 5.0
+
+
+@pytest.mark.parametrize("scene,name", [("test", "allbxdf.xml"), ("cbox", "bunny90k.xml")])
+def test_device_cw8_tree_equals_emulated_tree_and_renders_like_the_host_tree(Renderer, scene_root, scene, name, monkeypatch):
+    """The compressed 8-wide tree collapsed on the device from the device-SAH hierarchy (ADAPT_TRACE_MODE=3 + bvh_builder "sah_device"):
+    80-byte nodes and re-ordered records equal the CPU harness's bit for bit, an independent decoder traces it like brute force, and the
+    image equals the one rendered through the host builder's 8-wide tree."""
+    from lbvh_host import cw8_trace_check
+    monkeypatch.setenv("ADAPT_TRACE_MODE", "3")
+    size, spp = 64, 4
+    e, a, o, c = _load(scene_root, scene, name, size)
+    r_d = Renderer(e, a, o, c, seed=4, bvh_builder="sah_device")
+    ex = r_d.bvh_export()
+    assert ex["builder"] == 2 and ex["n_nodes8"] > 0 and ex["depth8"] >= 1
+    prims, sph = _tables(a, o)
+    ref = build_tree(prims, sph, max_leaf=3, builder="sah_device", eight=True, order_seed=2)
+    assert ex["n_nodes8"] == ref["nodes8"].shape[0] and ex["depth8"] == ref["depth8"]
+    assert np.array_equal(ex["nodes8"], ref["nodes8"])
+    assert np.array_equal(ex["nodes"].view(np.uint32), ref["nodes"].view(np.uint32))
+    assert np.array_equal(ex["prims"][:, :10].view(np.uint32), ref["prims"][:, :10].view(np.uint32))
+    ro, rd = _rays(prims, 3000, 5)
+    rc, t8, _ = cw8_trace_check(ex["nodes8"], ex["prims"], prims, sph, ro, rd)
+    assert rc == 0
+    h_d = r_d.intersect_batch(ro, rd)                               # single-ray hook: the binary tree over the same records
+    hit8 = t8 < 1e7                                                  # the CPU decoder rounds without FMA contraction: distances agree to a few ulp
+    both = hit8 & (h_d["prim"] >= 0)
+    assert (hit8 != (h_d["prim"] >= 0)).mean() < 2e-3              # grazing rays may fall either way between the two roundings
+    assert np.allclose(h_d["t"][both], t8[both], rtol=1e-4, atol=0) and (np.abs(h_d["t"][both] - t8[both]) > 1e-5 * t8[both]).mean() < 2e-3
+    r_h = Renderer(e, a, o, c, seed=4, bvh_builder="sah")
+    assert r_h.bvh_export(arrays=False)["n_nodes8"] > 0
+    r_d.render_batch(spp); r_h.render_batch(spp)
+    img_d, img_h = r_d.pixels.to_numpy(), r_h.pixels.to_numpy()
+    assert np.isfinite(img_d).all() and rel_l2(img_d, img_h) < 1e-5
+    assert r_d.stats()["rays_closest"] == r_h.stats()["rays_closest"]
+    r_d.close(); r_h.close()

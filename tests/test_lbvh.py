@@ -140,6 +140,38 @@ def test_sah_device_spheres_and_triangles_mixed(scene_root):
     _check(prims, sph, max_leaf=4, builder="sah_device")
 
 
+# ---- the compressed 8-wide tree collapsed from the device-SAH hierarchy (bvh_lbvh.h: cw8_*) -------------------------------------------
+@pytest.mark.parametrize("max_leaf", [1, 2, 3])
+def test_cw8_collapse_is_sound_and_traces_like_brute_force(max_leaf):
+    """An independent decoder of the 80-byte nodes (dequantised child boxes, slot metadata) finds every record exactly once, every child box
+    encloses its primitives, and its closest hits equal brute force bit for bit; the binary tree over the re-ordered records stays sound."""
+    from lbvh_host import cw8_trace_check
+    prims = _mesh()
+    t = build_tree(prims, max_leaf=max_leaf, builder="sah_device", eight=True)
+    assert validate(t["nodes"], t["prims"], prims)[0] == 0
+    assert 1 <= t["depth8"] <= 12 and t["nodes8"].shape[0] < t["nodes"].shape[0]
+    ro, rd = _rays(t["prims"], 1500, 2)
+    _, tt, _, bt, _ = trace_check(t["nodes"], t["prims"], ro, rd)
+    rc, t8, p8 = cw8_trace_check(t["nodes8"], t["prims"], prims, None, ro, rd)
+    assert rc == 0
+    assert np.array_equal(tt, bt) and np.array_equal(t8, bt)
+
+
+def test_cw8_collapse_spheres_triangles_and_tiny_ranges(scene_root):
+    from lbvh_host import cw8_trace_check
+    e, a, o, c = load_scene(scene_root, "test", "allbxdf.xml", 16, 16)
+    prims = a["primitives"].reshape(-1, 9)
+    sph = np.zeros(prims.shape[0], np.uint8)
+    if a["indices"] is not None:
+        sph[np.asarray(a["indices"], np.int64)] = 1
+    for sub in (prims.shape[0], 9, 5, 4):                       # the whole scene, and scenes of a few primitives (root with leaf children only)
+        t = build_tree(prims[:sub], sph[:sub], max_leaf=3, builder="sah_device", eight=True)
+        ro, rd = _rays(t["prims"], 400, sub)
+        _, tt, _, bt, _ = trace_check(t["nodes"], t["prims"], ro, rd)
+        rc, t8, _ = cw8_trace_check(t["nodes8"], t["prims"], prims[:sub], sph[:sub], ro, rd)
+        assert rc == 0 and np.array_equal(tt, bt) and np.array_equal(t8, bt)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9])
 def test_tiny_scenes(n):
     rng = np.random.default_rng(n)
