@@ -366,6 +366,6 @@ def pack_scene(emitters: List, array_info: dict, objects: List, prop: dict, seed
     # the reference's accelerator switch. The CUDA path always uses its BVH; the oracle
     # follows the reference and picks brute force unless the XML asked for "bvh".
     d.accelerator = 1 if prop.get("accelerator", "none") == "bvh" else 0
-    d.bvh_builder = {"sah": 0, "host": 0, "lbvh": 1, "device": 1, "sah_device": 2}[bvh_builder] if isinstance(bvh_builder, str) else int(bvh_builder)
+    d.bvh_builder = {"default": 0, "lbvh": 1, "sah_device": 2, "device": 2, "sah": 3, "host": 3}[bvh_builder] if isinstance(bvh_builder, str) else int(bvh_builder)
     ps.host.update(dict(num_objects=len(objects), num_prims=n_prims, src_num=len(emitters)))
     return ps

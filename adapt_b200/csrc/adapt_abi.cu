@@ -119,7 +119,8 @@ struct adapt_handle {
     bool want_wide = false;
     int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt / k_trace_vpt)
     VolumeView vv{};
-    int bvh_builder = 0;                      // 0 host SAH (bvh_build.cpp), 1 device linear BVH, 2 device binned SAH (bvh_device.cu)
+    int bvh_builder = 2;                      // 1 device linear BVH, 2 device binned SAH (bvh_device.cu), 3 host SAH (bvh_build.cpp)
+    bool builder_by_default = true;           // nobody asked for a builder: a failed device build falls back to the host builder
     int bvh_nodes = 0, bvh_depth = 0, bvh_nodes8 = 0, bvh_depth8 = 0;
     float bvh_build_ms = 0.f;
     BuildParams bvh_params;
@@ -426,7 +427,8 @@ static int build_accel(adapt_handle* h, const float* primitives) {
     auto drop_new = [&]() { dev_release(h, new_nodes); dev_release(h, new_nodes8); dev_release(h, new_prims); };
     bool wide_ok = true; int n_nodes = 0, depth = 0, n_nodes8 = 0, depth8 = 0; float build_ms = 0.f;
     float root_lo[3], root_hi[3];
-    if (h->bvh_builder >= 1) {
+    bool use_host = h->bvh_builder == 3;
+    if (!use_host) {
         // device build: linear BVH or binned SAH straight into the traversal layout; no 8-wide tree
         DeviceBvh db; std::string what;
         // the SAH builder also collapses its tree into the compressed 8-wide layout when the handle traces through that (leaves <= 3)
@@ -434,16 +436,26 @@ static int build_accel(adapt_handle* h, const float* primitives) {
         cudaError_t be = build_bvh_device(primitives, h->sph.data(), h->prim_obj.data(), h->obj_class.data(), np, no,
                                           eight ? std::min(h->bvh_params.max_leaf, 3) : h->bvh_params.max_leaf,
                                           h->stream, db, what, h->bvh_builder, h->bvh_params.traverse_cost, eight);
-        if (be != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH build: " + what + ": " + cudaGetErrorString(be));
-        h->allocs.push_back(db.nodes); h->allocs.push_back(db.leaf_prims);
-        if (db.nodes8) h->allocs.push_back(db.nodes8);
-        new_nodes = db.nodes; new_prims = db.leaf_prims; new_nodes8 = db.nodes8;
-        if (db.depth > PT_STACK_SIZE) { drop_new(); return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack (use the host builder for this scene)"); }
-        wide_ok = db.nodes8 != nullptr && db.depth8 + 1 <= PT_STACK8;
-        n_nodes8 = db.n_nodes8; depth8 = db.depth8;
-        n_nodes = db.n_nodes; depth = db.depth; build_ms = db.build_ms;
-        for (int a = 0; a < 3; a++) { root_lo[a] = db.root_lo[a]; root_hi[a] = db.root_hi[a]; }
-    } else {
+        // a handle whose builder nobody chose falls back to the host builder when the device build cannot serve it
+        const bool too_deep = be == cudaSuccess && db.depth > PT_STACK_SIZE;
+        if ((be != cudaSuccess || too_deep) && h->builder_by_default) {
+            if (be == cudaSuccess) { cudaFree(db.nodes); cudaFree(db.leaf_prims); if (db.nodes8) cudaFree(db.nodes8); }
+            else cudaGetLastError();
+            if (!std::getenv("ADAPT_QUIET")) std::fprintf(stderr, "[adapt_b200] device BVH build not usable (%s), building on the host\n", too_deep ? "tree deeper than the traversal stack" : what.c_str());
+            h->bvh_builder = 3; use_host = true;
+        } else {
+            if (be != cudaSuccess) return set_error(ADAPT_ERR_CUDA, "device BVH build: " + what + ": " + cudaGetErrorString(be));
+            h->allocs.push_back(db.nodes); h->allocs.push_back(db.leaf_prims);
+            if (db.nodes8) h->allocs.push_back(db.nodes8);
+            new_nodes = db.nodes; new_prims = db.leaf_prims; new_nodes8 = db.nodes8;
+            if (too_deep) { drop_new(); return set_error(ADAPT_ERR_INVALID, "BVH deeper than the traversal stack (use the host builder for this scene)"); }
+            wide_ok = db.nodes8 != nullptr && db.depth8 + 1 <= PT_STACK8;
+            n_nodes8 = db.n_nodes8; depth8 = db.depth8;
+            n_nodes = db.n_nodes; depth = db.depth; build_ms = db.build_ms;
+            for (int a = 0; a < 3; a++) { root_lo[a] = db.root_lo[a]; root_hi[a] = db.root_hi[a]; }
+        }
+    }
+    if (use_host) {
         const auto t0 = std::chrono::steady_clock::now();
         BuildResult br;
         BuildParams bp = h->bvh_params;
@@ -602,8 +614,13 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         h->obj_class[o] = (uint8_t)(b.kind == 0 ? std::min(std::max(b.type, 0), 7) : (b.type == 0 ? 8 : (b.type == 1 ? 9 : 10)));
     }
     if (np >= (1 << PT_HIT_PRIM_BITS)) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: more than 2^27 primitives"));
-    h->bvh_builder = d->bvh_builder ? d->bvh_builder : env_int("ADAPT_BVH_BUILDER", 0);
-    if (h->bvh_builder < 0 || h->bvh_builder > 2) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (host SAH), 1 (device LBVH) or 2 (device SAH)"));
+    {
+        // 0 = nobody chose: ADAPT_BVH_BUILDER if set, else the device SAH builder (the host tree's quality for a fraction of its build time)
+        const int req = d->bvh_builder ? d->bvh_builder : env_int("ADAPT_BVH_BUILDER", 0);
+        if (req < 0 || req > 3) return fail(set_error(ADAPT_ERR_INVALID, "adapt_create: bvh_builder must be 0 (default), 1 (device LBVH), 2 (device SAH) or 3 (host SAH)"));
+        h->builder_by_default = req == 0;
+        h->bvh_builder = req == 0 ? 2 : req;
+    }
     SceneView& sv = h->sv;
     sv.n_objects = no; sv.n_prims = np;
     // traversal: 1 = binary BVH, 3 = compressed 8-wide BVH collapsed from it (host builder only), 0 = baseline without lane refill.

@@ -64,8 +64,8 @@ class Renderer:
     def __init__(self, emitters: List, array_info: dict, objects: List, prop: dict, *, seed: int = 0,
                  device_id: int = 0, pixel_list: Optional[np.ndarray] = None, pool_size: int = 0,
                  max_bounce: Optional[int] = None, bvh_builder=0, integrator: str = "pt", device_ids=None):
-        """bvh_builder: 0 / "sah" = host binned-SAH build (default), 1 / "lbvh" = linear BVH built on the device,
-        2 / "sah_device" = binned-SAH tree built on the device.
+        """bvh_builder: 0 = default (the binned-SAH tree built on the device), 1 / "lbvh" = linear BVH built on the device,
+        2 / "sah_device" = binned SAH on the device, 3 / "sah" = the host (OpenMP) binned-SAH build.
         integrator: "pt" (renderer/vanilla_renderer.py) or "vpt" (renderer/vpt.py over homogeneous media; see VolumeRenderer).
         device_ids: several CUDA ordinals -> ONE renderer over all of them (single process): the library replicates the scene, splits the
         film into interleaved tiles and gathers the film over NVLink peer loads when it is read (include/adapt_b200.h: n_devices)."""

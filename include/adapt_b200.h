@@ -107,8 +107,10 @@ typedef struct {
     int32_t pool_size;          /* path slots kept in flight, 0 = auto                                       */
     int32_t accelerator;        /* the reference's <string name="accelerator"> switch: 1 = "bvh". This library always uses its
                                    BVH; the CPU oracle follows the reference (brute force unless 1)                           */
-    int32_t bvh_builder;        /* 0 = default (host binned-SAH build, or env ADAPT_BVH_BUILDER), 1 = linear BVH built on the device,
-                                   2 = binned-SAH tree built on the device (level-synchronous; the host tree's quality)               */
+    int32_t bvh_builder;        /* 0 = default (env ADAPT_BVH_BUILDER if set, else 2; a default handle falls back to 3 when the device
+                                   build cannot serve the scene), 1 = linear BVH built on the device, 2 = binned-SAH tree built on the
+                                   device (level-synchronous; the host tree's quality, incl. the compressed 8-wide collapse), 3 = host
+                                   binned-SAH build (OpenMP)                                                                       */
     int32_t reserved[5];
     /* textures: tracer/path_tracer.py:83-123 (albedo_map / normal_map / bump_map + their packed images). All optional. */
     const adapt_texture* textures;  /* [3][n_objects]: albedo, normal, bump descriptor per object, or NULL (no textures) */
@@ -211,13 +213,13 @@ int adapt_update_geometry(adapt_handle* h, const float* primitives, const float*
 int adapt_refit_geometry(adapt_handle* h, const float* primitives, const float* n_g, const float* n_s);
 
 /* Stage-level hook for the acceleration structure that replaces LinearBVH / LinearNode (tracer/ti_bvh.py:10-53) on the device:
- * sizes, builder used (0 host SAH, 1 device linear BVH, 2 device SAH) and its build time; nodes_out [n_nodes*16] receives the 64-byte nodes
+ * sizes, builder used (1 device linear BVH, 2 device SAH, 3 host SAH) and its build time; nodes_out [n_nodes*16] receives the 64-byte nodes
  * (x/y bounds of child 0, x/y bounds of child 1, z bounds of both, two child codes), prims_out [n_prims*12] the 48-byte leaf
  * records in leaf order (layout: csrc/bvh_build.h). Either array may be NULL. */
 int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_t* depth, int32_t* builder, float* build_ms,
                      float* nodes_out, float* prims_out);
 /* The compressed 8-wide tree the handle traces through when there is one (scenes of >= 400 k or <= 64 primitives, or ADAPT_TRACE_MODE=3;
- * built by the host builder or by the device SAH builder): *n_nodes8 = 0 when the handle uses the binary tree.  nodes8_out
+ * built by the device SAH builder or the host builder): *n_nodes8 = 0 when the handle uses the binary tree.  nodes8_out
  * [n_nodes8*20] receives the 80-byte nodes (layout: csrc/bvh_build.h, GpuNode8); its leaf children name records of adapt_bvh_export's
  * prims_out.  Either pointer may be NULL. */
 int adapt_bvh_export_wide(adapt_handle* h, int32_t* n_nodes8, int32_t* depth8, uint32_t* nodes8_out);

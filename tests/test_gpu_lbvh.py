@@ -1,5 +1,5 @@
 """Device BVH builders -- GPU half: the tree built by bvh_device.cu (through adapt_create with bvh_builder = 1, the linear BVH, or 2, the
-level-synchronous binned SAH, and read back with adapt_bvh_export) is held to the CPU emulation of the same per-element steps bit for bit, traced against the host-SAH handle,
+level-synchronous binned SAH and the default, and read back with adapt_bvh_export) is held to the CPU emulation of the same per-element steps bit for bit, traced against the host-SAH handle,
 and rendered: tree shape must not change a result (closest hit is unique)."""
 import os
 
@@ -83,7 +83,7 @@ def test_same_hits_and_same_image_as_host_sah_tree(Renderer, scene_root, scene, 
     e, a, o, c = _load(scene_root, scene, name, size)
     r_l = Renderer(e, a, o, c, seed=2, bvh_builder=builder)
     r_s = Renderer(e, a, o, c, seed=2, bvh_builder="sah")
-    assert r_s.bvh_export(arrays=False)["builder"] == int(os.environ.get("ADAPT_BVH_BUILDER", "0"))   # "sah" = the default builder
+    assert r_s.bvh_export(arrays=False)["builder"] == 3             # "sah" = the host builder, whatever the default is
     prims, _ = _tables(a, o)
     ro, rd = _rays(prims, 20000, 3)
     h_l, h_s = r_l.intersect_batch(ro, rd), r_s.intersect_batch(ro, rd)
@@ -205,3 +205,12 @@ def test_device_cw8_tree_equals_emulated_tree_and_renders_like_the_host_tree(Ren
     assert np.isfinite(img_d).all() and rel_l2(img_d, img_h) < 1e-5
     assert r_d.stats()["rays_closest"] == r_h.stats()["rays_closest"]
     r_d.close(); r_h.close()
+
+
+def test_default_builder_is_the_device_sah_builder(Renderer, scene_root, monkeypatch):
+    monkeypatch.delenv("ADAPT_BVH_BUILDER", raising=False)
+    e, a, o, c = _load(scene_root, "cbox", "bunny90k.xml", 32)
+    r = Renderer(e, a, o, c)
+    ex = r.bvh_export(arrays=False)
+    assert ex["builder"] == 2 and ex["build_ms"] < 15.0
+    r.close()
