@@ -115,6 +115,8 @@ struct adapt_handle {
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
     int trace_mode = 1;                       // 1 binary BVH, 3 compressed 8-wide BVH, 0 baseline without lane refill
     bool fuse_trace = true;
+    bool fuse_trace_vpt = false;              // vpt: transmittance + closest-hit streams in one launch (k_trace_vpt) or two (default)
+    int trace_grid_closest = 0;               // grid of k_closest when the vpt streams are not fused
     bool wide_ok = true;                      // the 8-wide tree was built and fits the traversal stack
     bool want_wide = false;
     int integrator = 0;                       // 0 pt, 1 vpt (k_logic_vpt / k_trace_vpt)
@@ -215,8 +217,18 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
                 parity, (unsigned)L.iterations);
         CK(cudaEventRecord(ev.e[1], st));
         CK(cudaEventRecord(ev.e[2], st));
-        if (h->trace_mode == 3) k_trace_vpt<3><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, h->leaf_t | (h->node_steps << 8), parity);
-        else k_trace_vpt<1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, h->leaf_t | (h->node_steps << 8), parity);
+        const int lt_v = h->leaf_t | (h->node_steps << 8);
+        if (!h->fuse_trace_vpt) {
+            // two launches: the transmittance stream, then the closest-hit stream through the leaner pt kernel (more resident warps)
+            if (h->trace_mode == 3) {
+                k_transmit_vpt<3><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, lt_v, parity);
+                k_closest<false, 3><<<h->trace_grid_closest, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, h->d_ctr, L.d_cur, h->refill, lt_v);
+            } else {
+                k_transmit_vpt<1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, lt_v, parity);
+                k_closest<false, 1><<<h->trace_grid_closest, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, h->d_ctr, L.d_cur, h->refill, lt_v);
+            }
+        } else if (h->trace_mode == 3) k_trace_vpt<3><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, lt_v, parity);
+        else k_trace_vpt<1><<<h->trace_grid, TRACE_BLOCK, 0, st>>>(h->sv, h->vv, L.pool, L.sq, h->d_ctr, L.d_cur, h->refill, lt_v, parity);
         CK(cudaEventRecord(ev.e[3], st));
         CK(cudaGetLastError());
         h->stats.iterations += 1; L.iterations += 1;
@@ -793,6 +805,14 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         if (oe != cudaSuccess || occ < 1) occ = 8;
         const int per_sm = std::max(1, std::min(occ, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 16)));
         h->trace_grid = prop.multiProcessorCount * per_sm;
+        int occ_c = 0;
+        cudaError_t oc = h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_closest<false, 3>, TRACE_BLOCK, 0)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_closest<false, 1>, TRACE_BLOCK, 0);
+        if (oc != cudaSuccess || occ_c < 1) occ_c = 8;
+        h->trace_grid_closest = prop.multiProcessorCount * std::max(1, std::min(occ_c, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 16)));
+        // session r02ze (profiles/r02ze_ab_vpt_trace_split.txt): two launches beat the fused kernel for vpt -- trace 23.2 -> 19.8 ms per 16 spp on
+        // the fog scene, 23.0 -> 20.4 on the media scene: the fused kernel's 82 registers hold the closest-hit stream to 16 warps per SM
+        h->fuse_trace_vpt = env_int("ADAPT_FUSE_TRACE_VPT", 0) != 0;
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
     if (const char* lp = std::getenv("ADAPT_ITER_LOG")) h->iter_log_path = lp;

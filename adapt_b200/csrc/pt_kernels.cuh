@@ -860,6 +860,18 @@ k_trace_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
     }
 }
 
+// The transmittance stream alone (adapt_abi.cu launches it in front of k_closest when the two streams are not fused: the closest-hit
+// stream then runs at k_closest's occupancy instead of the 82-register fused kernel's).
+template <int MODE>
+__global__ void __launch_bounds__(TRACE_BLOCK, 4)
+k_transmit_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
+               Cursors* __restrict__ cur, const int refill, const int leaf_t, const int parity) {
+    unsigned traced = 0, nn = 0, np = 0;
+    TransmitSource src{sv, vv, pool, sq, parity};
+    if (MODE == 3) trace_stream_cw8<false, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+    else trace_stream_vote<false, false>(sv, src, cur->shadow, refill, leaf_t, traced, nn, np);
+}
+
 // stage-level test hook
 __global__ void k_intersect_batch(const SceneView sv, int n, const float* __restrict__ ro, const float* __restrict__ rd,
                                   const float* __restrict__ tmax_in, int any_hit, int* __restrict__ hit_obj, int* __restrict__ hit_prim,
