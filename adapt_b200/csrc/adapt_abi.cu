@@ -797,9 +797,13 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     {
         // persistent trace kernels: exactly as many blocks as are resident at once (one wave), at most ADAPT_TRACE_BLOCKS_PER_SM per SM
         int occ = 0;
+        h->fuse_trace_vpt = env_int("ADAPT_FUSE_TRACE_VPT", 0) != 0;
         cudaError_t oe = h->integrator == 1
-            ? (h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_vpt<3>, TRACE_BLOCK, 0)
-                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_vpt<1>, TRACE_BLOCK, 0))
+            ? (h->fuse_trace_vpt
+                   ? (h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_vpt<3>, TRACE_BLOCK, 0)
+                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_vpt<1>, TRACE_BLOCK, 0))
+                   : (h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_transmit_vpt<3>, TRACE_BLOCK, 0)
+                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_transmit_vpt<1>, TRACE_BLOCK, 0)))
             : (h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<3>, TRACE_BLOCK, 0)
                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<1>, TRACE_BLOCK, 0));
         if (oe != cudaSuccess || occ < 1) occ = 8;
@@ -810,9 +814,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_closest<false, 1>, TRACE_BLOCK, 0);
         if (oc != cudaSuccess || occ_c < 1) occ_c = 8;
         h->trace_grid_closest = prop.multiProcessorCount * std::max(1, std::min(occ_c, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 16)));
-        // session r02ze (profiles/r02ze_ab_vpt_trace_split.txt): two launches beat the fused kernel for vpt -- trace 23.2 -> 19.8 ms per 16 spp on
-        // the fog scene, 23.0 -> 20.4 on the media scene: the fused kernel's 82 registers hold the closest-hit stream to 16 warps per SM
-        h->fuse_trace_vpt = env_int("ADAPT_FUSE_TRACE_VPT", 0) != 0;
+        // (fuse_trace_vpt, session r02ze, profiles/r02ze_ab_vpt_trace_split.txt: two launches beat the fused kernel for vpt -- trace 23.2 -> 19.8 ms
+        // per 16 spp on the fog scene, 23.0 -> 20.4 on the media scene: the fused kernel's 82 registers hold the closest-hit stream to 16 warps per SM)
     }
     h->fuse_trace = env_int("ADAPT_FUSE_TRACE", 1) != 0;
     if (const char* lp = std::getenv("ADAPT_ITER_LOG")) h->iter_log_path = lp;

@@ -862,8 +862,13 @@ k_trace_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const 
 
 // The transmittance stream alone (adapt_abi.cu launches it in front of k_closest when the two streams are not fused: the closest-hit
 // stream then runs at k_closest's occupancy instead of the 82-register fused kernel's).
+// resident blocks per SM (session r02zf, profiles/r02zf_ab_vpt_transmit_blocks.txt, trace ms per 16 spp fog / media scene): 4 blocks 19.8 / 20.4,
+// 6: 18.4 / 19.2, 7: 18.1 / 19.0, 8: 18.1 / 19.2, 9: 18.3 / 19.4
+#ifndef VPT_TRANSMIT_MIN_BLOCKS
+#define VPT_TRANSMIT_MIN_BLOCKS 7
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(TRACE_BLOCK, 4)
+__global__ void __launch_bounds__(TRACE_BLOCK, VPT_TRANSMIT_MIN_BLOCKS)
 k_transmit_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
                Cursors* __restrict__ cur, const int refill, const int leaf_t, const int parity) {
     unsigned traced = 0, nn = 0, np = 0;
