@@ -39,8 +39,9 @@ using namespace adapt;
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 9
 #endif
+// 8-wide kernel (session r02zg, profiles/r02zg_ab_cw8_blocks.txt, trace ms/step orb500k / balls-mono): 8 blocks 44.1 / 16.8, 9: 43.8 / 16.6, 10: 46.3 / 17.2
 #ifndef TRACE_MIN_BLOCKS8
-#define TRACE_MIN_BLOCKS8 8
+#define TRACE_MIN_BLOCKS8 9
 #endif
 // sort keys of k_logic's block-local regrouping: material classes 0..10 (BRDF type 0..7, BSDF det-refraction 8, BSDF
 // Lambertian transmission 9, null surface 10), 11 = path ends, 12 = free slot
