@@ -642,7 +642,9 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     // a binary step and those trees' hot levels sit in L1 anyway).
     h->trace_mode = env_int("ADAPT_TRACE_MODE", -1);
     const bool auto_mode = h->trace_mode < 0;
-    if (auto_mode) h->trace_mode = (np <= 64 || np >= 400000) ? 3 : 1;
+    // the 8-wide tree for scenes of >= 200 k or <= 64 primitives (session r02zj with the final kernels, trace ms/step binary / 8-wide:
+    // 90 k 34.0 / 34.4, 290 k 18.1 / 17.5, 500 k 50.4 / 43.8)
+    if (auto_mode) h->trace_mode = (np <= 64 || np >= 200000) ? 3 : 1;
     if (h->trace_mode != 0 && h->trace_mode != 3) h->trace_mode = 1;
     h->want_wide = h->trace_mode == 3 && h->bvh_builder != 1;          // the linear BVH is traced through the binary layout only
     CKH(build_accel(h, d->primitives));
@@ -822,7 +824,7 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     // scheduler knobs (pt_trace.cuh): lanes idle before a warp refills, lanes parked on a leaf before the leaf code runs.  Binary tree:
     // 16 / 8 (round 1); 8-wide tree: leaf threshold 4, refill 8 on large trees (orb500k 47.4 -> 45.2 ms/step, session r02f)
     const bool cw8 = h->trace_mode == 3;
-    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", cw8 && np >= 400000 ? 8 : 16)));
+    h->refill = std::min(32, std::max(1, env_int("ADAPT_REFILL", cw8 && np >= 400000 ? 8 : (cw8 && np >= 200000 ? 12 : 16))));
     h->leaf_t = std::min(32, std::max(1, env_int("ADAPT_LEAF_T", cw8 ? 4 : 8)));
     h->node_steps = std::min(8, std::max(1, env_int("ADAPT_NODE_STEPS", 4)));
     CKC(cudaEventCreateWithFlags(&h->ev_poll, cudaEventDisableTiming));

@@ -218,7 +218,7 @@ int adapt_refit_geometry(adapt_handle* h, const float* primitives, const float* 
  * records in leaf order (layout: csrc/bvh_build.h). Either array may be NULL. */
 int adapt_bvh_export(adapt_handle* h, int32_t* n_nodes, int32_t* n_prims, int32_t* depth, int32_t* builder, float* build_ms,
                      float* nodes_out, float* prims_out);
-/* The compressed 8-wide tree the handle traces through when there is one (scenes of >= 400 k or <= 64 primitives, or ADAPT_TRACE_MODE=3;
+/* The compressed 8-wide tree the handle traces through when there is one (scenes of >= 200 k or <= 64 primitives, or ADAPT_TRACE_MODE=3;
  * built by the device SAH builder or the host builder): *n_nodes8 = 0 when the handle uses the binary tree.  nodes8_out
  * [n_nodes8*20] receives the 80-byte nodes (layout: csrc/bvh_build.h, GpuNode8); its leaf children name records of adapt_bvh_export's
  * prims_out.  Either pointer may be NULL. */
