@@ -449,7 +449,8 @@ static int build_accel(adapt_handle* h, const float* primitives) {
                                           eight ? std::min(h->bvh_params.max_leaf, 3) : h->bvh_params.max_leaf,
                                           h->stream, db, what, h->bvh_builder, h->bvh_params.traverse_cost, eight);
         // a handle whose builder nobody chose falls back to the host builder when the device build cannot serve it
-        const bool too_deep = be == cudaSuccess && db.depth > PT_STACK_SIZE;
+        // (ADAPT_TEST_DEVICE_BUILD_TOO_DEEP=1: test hook that treats the device tree as deeper than the traversal stack)
+        const bool too_deep = be == cudaSuccess && (db.depth > PT_STACK_SIZE || env_int("ADAPT_TEST_DEVICE_BUILD_TOO_DEEP", 0) != 0);
         if ((be != cudaSuccess || too_deep) && h->builder_by_default) {
             if (be == cudaSuccess) { cudaFree(db.nodes); cudaFree(db.leaf_prims); if (db.nodes8) cudaFree(db.nodes8); }
             else cudaGetLastError();

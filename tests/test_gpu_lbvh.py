@@ -214,3 +214,23 @@ def test_default_builder_is_the_device_sah_builder(Renderer, scene_root, monkeyp
     ex = r.bvh_export(arrays=False)
     assert ex["builder"] == 2 and ex["build_ms"] < 15.0
     r.close()
+
+
+def test_default_handle_falls_back_to_the_host_builder(Renderer, scene_root, monkeypatch):
+    """A handle whose builder nobody chose builds on the host when the device tree cannot be used (here: a test hook declares it deeper than
+    the traversal stack); a handle that asked for the device builder gets the error instead."""
+    monkeypatch.delenv("ADAPT_BVH_BUILDER", raising=False)
+    monkeypatch.setenv("ADAPT_TEST_DEVICE_BUILD_TOO_DEEP", "1")
+    e, a, o, c = _load(scene_root, "test", "allbxdf.xml", 32)
+    r = Renderer(e, a, o, c, seed=1)
+    assert r.bvh_export(arrays=False)["builder"] == 3
+    r.render_batch(2)
+    img = r.pixels.to_numpy()
+    r.close()
+    with pytest.raises(Exception, match="deeper than the traversal stack"):
+        Renderer(e, a, o, c, seed=1, bvh_builder="sah_device")
+    monkeypatch.delenv("ADAPT_TEST_DEVICE_BUILD_TOO_DEEP")
+    r2 = Renderer(e, a, o, c, seed=1, bvh_builder="sah")
+    r2.render_batch(2)
+    assert rel_l2(img, r2.pixels.to_numpy()) < 1e-6
+    r2.close()
