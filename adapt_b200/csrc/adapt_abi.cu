@@ -67,7 +67,9 @@ static int env_int(const char* name, int dflt) {
 // then amortises its end-of-batch drain over twice the samples; two lanes inside one handle at the same samples per batch are within
 // +-1.5 % of one lane on all three workloads (the persistent trace kernel owns every register of the SM while it runs, so the other lane
 // only ever fills its tail), and two lanes double the pool memory.  Default: one lane.
+#ifndef PT_MAX_LANES
 #define PT_MAX_LANES 2
+#endif
 struct IterEvents { cudaEvent_t e[4]; };
 struct Lane {
     PathPool pool{};
@@ -89,7 +91,15 @@ struct adapt_handle {
     cudaStream_t own_stream = nullptr;        // created by adapt_create
     SceneView sv{};
     Lane lanes[PT_MAX_LANES];
-    int n_lanes = 1;
+    int n_lanes = 1;                          // lanes that exist (pools allocated)
+    // Lanes in use.  Two lanes win when there is enough work to overlap (+7 % on bunny90k at 256 spp per synchronisation) and lose when
+    // there is not (-5 % at 8 spp: the second pool's ramp and drain), so a handle starts every epoch -- the time between two points at
+    // which its pools are known to be empty -- with one lane and brings in the others once the work enqueued in that epoch passes
+    // lane_threshold.  A lane is only ever switched on in flight (its pool is empty then), never off.
+    std::atomic<int> active_lanes{1};
+    bool lanes_adaptive = false;
+    bool drained = true;                      // pools empty: set by adapt_sync, cleared by adapt_render (under wk_mutex)
+    unsigned long long epoch_items = 0, lane_threshold = 0;
     cudaEvent_t ev_fork = nullptr;            // orders the other lanes' streams after what the caller put on the handle's stream
     DeviceCounters* d_ctr = nullptr;
     WorkStripe* d_work = nullptr;
@@ -312,15 +322,19 @@ static int run_until(adapt_handle* h, Pred done) {
     CK(cudaMemcpyAsync(h->h_work, h->d_work, wbytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (done(work_totals(h->h_work))) return 0;
-    // the other lanes start after whatever the caller has queued on the handle's stream (film upload, a framebuffer reduce ...)
-    if (h->n_lanes > 1) {
-        CK(cudaEventRecord(h->ev_fork, h->stream));
-        for (int l = 1; l < h->n_lanes; l++) CK(cudaStreamWaitEvent(h->lanes[l].stream, h->ev_fork, 0));
-    }
-    // iterations of the lanes alternate in the launch order, so lane B's k_logic is queued right behind lane A's k_trace
+    // iterations of the lanes alternate in the launch order, so lane B's k_logic is queued right behind lane A's k_trace.  A lane
+    // starts after whatever the caller has queued on the handle's stream (film upload, a framebuffer reduce ...): ordered by an event
+    // at the start of every call, and again when a lane is switched on while the call runs.
+    int forked = 1;
     auto launch_batch = [&]() -> int {
+        const int n_act = std::min(h->n_lanes, std::max(1, h->active_lanes.load()));
+        if (n_act > forked) {
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            for (int l = forked; l < n_act; l++) CK(cudaStreamWaitEvent(h->lanes[l].stream, h->ev_fork, 0));
+            forked = n_act;
+        }
         for (int k = 0; k < batch; k++)
-            for (int l = 0; l < h->n_lanes; l++) { int rc = launch_iteration(h, h->lanes[l]); if (rc) return rc; }
+            for (int l = 0; l < n_act; l++) { int rc = launch_iteration(h, h->lanes[l]); if (rc) return rc; }
         return 0;
     };
     WorkTotals last{~0ull, ~0ull};
@@ -748,11 +762,19 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     int P = d->pool_size > 0 ? d->pool_size : env_int("ADAPT_POOL", 0);
     const bool explicit_pool = P > 0;
     if (P <= 0) P = (int)std::min<long long>(1ll << 22, std::max<long long>(1ll << 16, 32ll * (long long)h->n_pixels));
-    h->n_lanes = std::min(PT_MAX_LANES, std::max(1, env_int("ADAPT_LANES", 1)));
+    // lanes: ADAPT_LANES = n fixes the number (all of them always in use: A/B runs); otherwise a default-size pool gets a second lane
+    // that is brought in per epoch when enough work is enqueued (adapt_handle::active_lanes)
+    const int lanes_env = env_int("ADAPT_LANES", 0);
+    h->n_lanes = std::min(PT_MAX_LANES, std::max(1, lanes_env > 0 ? lanes_env : (explicit_pool ? 1 : 2)));
     if (h->count_nodes || (explicit_pool ? P < (1 << 17) : P < (1 << 22))) h->n_lanes = 1;
+    h->lanes_adaptive = lanes_env <= 0 && h->n_lanes > 1;
+    h->active_lanes.store(h->lanes_adaptive ? 1 : h->n_lanes);
     if (explicit_pool) P /= h->n_lanes;
     P = std::max(P, LOGIC_BLOCK);
     P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
+    // the second lane pays from about 0.75 * max_bounce pool fills of work per epoch on (sessions r02zl..r02zo: bunny90k, 16 bounces, breaks
+    // even near 7 fills and gains 3 % at 16; orb500k, 24 bounces through glass, breaks even near 17); ADAPT_LANE_THRESHOLD = pool fills
+    h->lane_threshold = (unsigned long long)P * (unsigned long long)std::max(1, env_int("ADAPT_LANE_THRESHOLD", std::max(4, (3 * d->max_bounce + 3) / 4)));
     // segment k takes the shadow rays of the warps w with w % PT_NCURSOR == k: at most ceil(n_warps / PT_NCURSOR) * 32 * nsr entries
     // per k_logic launch.  Scenes with several material groups run up to five launches per iteration (k_classify lists), each
     // packing its slots from warp 0 on, so every launch can add one more partly filled warp per segment: 8 warps of slack.
@@ -950,8 +972,15 @@ int adapt_render(adapt_handle* h, int32_t n_spp) {
     {
         std::lock_guard<std::mutex> lk(h->wk_mutex);
         if (h->wk_rc) return set_error(h->wk_rc, "adapt_render (asynchronous) failed: " + h->wk_error);
-        h->work_hi.fetch_add((unsigned long long)h->n_pixels * (unsigned long long)n_spp);
+        const unsigned long long items = (unsigned long long)h->n_pixels * (unsigned long long)n_spp;
+        h->work_hi.fetch_add(items);
         h->cnt += n_spp;
+        if (h->lanes_adaptive) {
+            if (h->drained) { h->epoch_items = 0; h->active_lanes.store(1); }
+            h->epoch_items += items;
+            if (h->epoch_items >= h->lane_threshold) h->active_lanes.store(h->n_lanes);
+        }
+        h->drained = false;
         h->wk_busy = true;
     }
     h->wk_wake.notify_one();
@@ -975,6 +1004,7 @@ int adapt_sync(adapt_handle* h) {
     if (rc) { h->poisoned = true; return rc; }
     rc = sync_lanes(h);
     if (rc) return rc;
+    { std::lock_guard<std::mutex> lk(h->wk_mutex); if (h->work_hi.load() == target) h->drained = true; }   // every pool is empty now
     return drain_events(h);
 }
 
@@ -1090,8 +1120,9 @@ int adapt_get_stats(adapt_handle* h, adapt_stats* out) {
     out->rays_closest = (c.rays_closest - h->ctr_base.rays_closest) + (c.rays_culled - h->ctr_base.rays_culled);
     out->reserved[0] = c.rays_culled - h->ctr_base.rays_culled;
     out->reserved[1] = (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) ? 1 : 0;
-    out->reserved[2] = (uint64_t)h->lanes[0].pool.n_slots * (uint64_t)h->n_lanes;
-    out->reserved[3] = (uint64_t)h->n_lanes;
+    const int act = std::min(h->n_lanes, std::max(1, h->active_lanes.load()));      // lanes in use in the current epoch
+    out->reserved[2] = (uint64_t)h->lanes[0].pool.n_slots * (uint64_t)act;
+    out->reserved[3] = (uint64_t)act;
     out->rays_shadow = (c.rays_shadow - h->ctr_base.rays_shadow) + (c.shadow_inline - h->ctr_base.shadow_inline);
     out->nodes_visited = c.nodes_visited - h->ctr_base.nodes_visited;
     out->prims_tested = c.prims_tested - h->ctr_base.prims_tested;

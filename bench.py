@@ -374,7 +374,10 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "stage_ms_per_step": {"logic": tot[7] / world / args.steps, "shadow": tot[8] / world / args.steps, "closest": tot[5] / world / args.steps},
+            # event-timed per launch and summed: with two lanes the launches of one lane run WHILE the other lane's do, so the stages add up
+            # to more than the step (and avg_launch_ms below is the wall duration of a launch that shares the SMs with the other lane's)
+            "stage_ms_per_step": {"logic": tot[7] / world / args.steps, "shadow": tot[8] / world / args.steps, "closest": tot[5] / world / args.steps,
+                                  "overlapping_lanes": lanes},
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "frac_source": frac_source, "traffic": traffic,
                          "traffic_capture": ({k: cap.get(k) for k in ("duration_us", "launches_captured", "rays_in_launch", "shadow_rays_in_launch", "session")} if cap else None),
