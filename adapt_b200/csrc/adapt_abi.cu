@@ -59,14 +59,14 @@ static int env_int(const char* name, int dflt) {
 // ================================================================================================
 // handle
 // ================================================================================================
-// A lane is one path pool with its queues, cursors and stream.  A handle can run up to PT_MAX_LANES of them side by side
-// (ADAPT_LANES=2): while lane A's persistent k_trace drains its tail, lane B's k_logic / k_trace blocks take the free SMs.  Lanes share
+// A lane is one path pool with its queues, cursors and stream.  A handle can run up to PT_MAX_LANES of them side by side: while lane
+// A's persistent k_trace runs, lane B's k_logic takes the issue slots and the tail it leaves free, and the other way round.  Lanes share
 // the scene, the work stripes (both claim from the same counters, so the load balances itself), the statistics counters and the film
 // (atomics); everything a kernel resets or double-buffers per iteration is per lane.
-// Measured (sessions r02c / r02d): two HANDLES on two host threads reach +11 % aggregate throughput on bunny90k, but only because each
-// then amortises its end-of-batch drain over twice the samples; two lanes inside one handle at the same samples per batch are within
-// +-1.5 % of one lane on all three workloads (the persistent trace kernel owns every register of the SM while it runs, so the other lane
-// only ever fills its tail), and two lanes double the pool memory.  Default: one lane.
+// Measured: sessions r02c / r02d compared one and two lanes at 32 samples per synchronisation and found +-1.5 % (the second pool's ramp
+// and drain eat the overlap there); at the batch sizes the asynchronous adapt_render made normal the overlap wins (sessions r02zl..r02zp,
+// bunny90k: -5 % at 8 spp per synchronisation, +3.5 % at 32, +4.5 % at 64, +7.5 % at 256; three and four lanes: no further gain).  Hence:
+// two lanes exist for default-size pools and the second one is brought in per epoch (adapt_handle::active_lanes).
 #ifndef PT_MAX_LANES
 #define PT_MAX_LANES 2
 #endif
