@@ -122,6 +122,7 @@ struct adapt_handle {
     std::string wk_error;
     std::vector<void*> allocs;
     int trace_grid = 0;
+    int trace_grid_2lanes = 0;                // k_trace's grid while two lanes are active (fewer resident blocks: room for the other lane's k_logic)
     int mats = M_ALL;                         // material groups present -> which k_logic instantiation runs
     int trace_mode = 1;                       // 1 binary BVH, 3 compressed 8-wide BVH, 0 baseline without lane refill
     bool fuse_trace = true;
@@ -275,7 +276,9 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
 #undef LAUNCH_LOGIC_X
     }
     CK(cudaEventRecord(ev.e[1], st));
-    const int tg = h->trace_grid, rf = h->refill, lt = h->leaf_t | (h->node_steps << 8);   // node steps per scheduling round ride in the high bits
+    // two lanes in flight: k_trace leaves part of every SM to the other lane's k_logic (sessions r02zl, r03h)
+    const int tg = h->active_lanes.load() >= 2 ? h->trace_grid_2lanes : h->trace_grid;
+    const int rf = h->refill, lt = h->leaf_t | (h->node_steps << 8);   // node steps per scheduling round ride in the high bits
     if (h->fuse_trace && h->trace_mode >= 1 && !h->count_nodes) {
         CK(cudaEventRecord(ev.e[2], st));          // fused: the whole trace time is booked under "closest"
         if (h->trace_mode == 3) k_trace<3><<<tg, TRACE_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, L.d_cur, rf, lt, parity, h->bvh_nodes);
@@ -834,6 +837,12 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
         if (oe != cudaSuccess || occ < 1) occ = 8;
         const int per_sm = std::max(1, std::min(occ, env_int("ADAPT_TRACE_BLOCKS_PER_SM", 16)));
         h->trace_grid = prop.multiProcessorCount * per_sm;
+        // with both lanes active the logic kernel of one lane should run beside the trace kernel of the other, not after it: at nine blocks of
+        // 128 x 56 registers k_trace fills the register file and k_logic only gets the SMs as trace blocks retire.  Six blocks (sessions r02zl /
+        // r03h, 256 spp per step): bunny90k 4126 -> 4162..4170 Mrays/s (five: 4170..4180), car290k +0.5 %, orb500k +-0.3 %; a single lane wants
+        // all nine (trace time +16 % at six).  ADAPT_TRACE_BLOCKS_PER_SM, when set, applies to both.
+        h->trace_grid_2lanes = std::getenv("ADAPT_TRACE_BLOCKS_PER_SM") ? h->trace_grid
+                             : prop.multiProcessorCount * std::max(1, std::min(per_sm, env_int("ADAPT_TRACE_BLOCKS_2LANES", 6)));
         int occ_c = 0;
         cudaError_t oc = h->trace_mode == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_closest<false, 3>, TRACE_BLOCK, 0)
                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_closest<false, 1>, TRACE_BLOCK, 0);

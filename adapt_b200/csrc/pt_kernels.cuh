@@ -33,6 +33,9 @@ using namespace adapt;
 // Measured and rejected for k_logic in session r02k (profiles/r02k_ab_logic_variants.txt, logic ms/step bunny90k / orb500k / balls-mono,
 // shipped 17.4 / 23.5 / 22.3): requesting a slot's whole state in one batch before the misc word is looked at (18.1 / 25.0 / 23.3 -- the
 // extra live registers cost more than the saved round trip), five resident blocks per SM instead of four (18.0 / 24.2 / 23.0), six (18.8).
+// Session r03h (profiles/r03h_ab_pf3_noalloc.txt, code removed): the pool words read with ld.global.L1::no_allocate (LDG.E.128.NA) so that, with two
+// lanes, logic blocks do not evict the tree nodes of the trace blocks they share an SM with: logic 17.11 -> 17.03 ms/step, 4126 -> 4131 Mrays/s with two
+// lanes, 4170 -> 4185 at five trace blocks per SM, orb500k 1990 -> 1963 -- noise.
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 128
 #endif

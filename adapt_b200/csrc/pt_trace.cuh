@@ -24,6 +24,11 @@ namespace adapt {
 // local memory (+1 %), one primitive per leaf phase (+4..24 %), ld/st.global.cs hints on the ray / hit / queue words (+-1 %).  The staged
 // top of the tree is kept compiled out: +8 % trace time on bunny90k, +4 % on orb500k -- the top levels are L1-resident anyway (L1 hit
 // 32 cycles against 29 for shared memory) and the pointer select turns LDG.E.128.CONSTANT into generic loads.
+// Measured and rejected in sessions r03g / r03h (profiles/r03g_ab_prefetch.txt, r03h_ab_pf3_noalloc.txt; code removed): asking L1 for a leaf's
+// primitive records when a lane lands on the leaf, ahead of the leaf phase -- with prefetch.global.L1 (SASS CCTL.E.PF1) for the first record
+// (bunny90k 3716 -> 2446 Mrays/s at 32 spp per step) or all of them (1516), for the far child's node when it is pushed (3091), or with two plain
+// one-word loads nobody waits for (trace 34.0 -> 37.2 ms/step).  CCTL is far more expensive than a load here, and even the free-running loads
+// only add L1 traffic to a kernel that is short of L1 capacity, not of memory-level parallelism.
 #ifndef TRACE_TOP_NODES
 #define TRACE_TOP_NODES 0
 #endif
