@@ -209,21 +209,21 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
         // volumetric integrator: k_logic_vpt (samples -> shadow queue) + k_trace_vpt (transmittance stream, then the closest-hit stream)
         // two instantiations: every material group; the same plus two-sided BRDFs and albedo textures
         if (h->sv.two_sides || h->sv.textures)
-            k_logic_vpt<M_ALL | M_TEXTURED><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+            k_logic_vpt<M_ALL | M_TEXTURED><<<L.pool.n_slots / VPT_BLOCK, VPT_BLOCK, 0, st>>>(
                 h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
                 parity, (unsigned)L.iterations);
         else if ((h->mats & (M_GLOSSY | M_COAT_GGX)) == 0 && env_int("ADAPT_VPT_SPECIALISE", 1)) {
             // scenes of Lambertian / Phong / mirror surfaces (+ the BSDF containers of media): the small instantiations
             if (h->mats & M_BSDF)
-                k_logic_vpt<M_SIMPLE | M_BSDF><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                k_logic_vpt<M_SIMPLE | M_BSDF><<<L.pool.n_slots / VPT_BLOCK, VPT_BLOCK, 0, st>>>(
                     h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
                     parity, (unsigned)L.iterations);
             else
-                k_logic_vpt<M_SIMPLE><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+                k_logic_vpt<M_SIMPLE><<<L.pool.n_slots / VPT_BLOCK, VPT_BLOCK, 0, st>>>(
                     h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
                     parity, (unsigned)L.iterations);
         } else
-            k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<L.pool.n_slots / LOGIC_BLOCK, LOGIC_BLOCK, 0, st>>>(
+            k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF><<<L.pool.n_slots / VPT_BLOCK, VPT_BLOCK, 0, st>>>(
                 h->sv, h->vv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin,
                 parity, (unsigned)L.iterations);
         CK(cudaEventRecord(ev.e[1], st));
@@ -248,8 +248,7 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
     }
     int n_logic = 0;
     {
-        const int lg = L.pool.n_slots / LOGIC_BLOCK;
-#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { k_logic<M, LISTED><<<lg, LOGIC_BLOCK, 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, \
+#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { k_logic<M, LISTED><<<L.pool.n_slots / LOGIC_BLK(LISTED), LOGIC_BLK(LISTED), 0, st>>>(h->sv, L.pool, L.sq, h->d_ctr, h->d_work, L.d_cur, h->d_accum, \
         h->d_pixel_list, h->n_pixels, h->work_hi.load(), h->cnt_origin, parity, (unsigned)L.iterations, \
         L.d_cls_items, L.d_cls_count, (KEYS)); n_logic++; } while (0)
         // two-sided BRDFs and texture lookups are compile-time variants of every instantiation
@@ -263,7 +262,7 @@ static int launch_iteration(adapt_handle* h, Lane& L) {
             LAUNCH_LOGIC_V(M_SIMPLE, false, no_keys);
         } else {
             // several material groups: global class lists, then one launch per group present (k_classify)
-            k_classify<<<lg, LOGIC_BLOCK, 0, st>>>(L.pool, L.sq, L.d_cur, L.d_cls_items, L.d_cls_count, parity);
+            k_classify<<<L.pool.n_slots / CLASSIFY_BLOCK, CLASSIFY_BLOCK, 0, st>>>(L.pool, L.sq, L.d_cur, L.d_cls_items, L.d_cls_count, parity);
             n_logic++;
             const KeySet k_simple = {{0, 1, 2, 6, LOGIC_NKEY - 2, LOGIC_NKEY - 1, -1, -1}}, k_glossy = {{4, 5, -1, -1, -1, -1, -1, -1}};
             const KeySet k_coat = {{3, 7, -1, -1, -1, -1, -1, -1}}, k_bsdf = {{8, 9, 10, -1, -1, -1, -1, -1}};
@@ -773,8 +772,8 @@ int adapt_create(adapt_handle** out, const adapt_scene_desc* d) {
     h->lanes_adaptive = lanes_env <= 0 && h->n_lanes > 1;
     h->active_lanes.store(h->lanes_adaptive ? 1 : h->n_lanes);
     if (explicit_pool) P /= h->n_lanes;
-    P = std::max(P, LOGIC_BLOCK);
-    P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
+    P = std::max(P, POOL_GRANULE);
+    P = (P + POOL_GRANULE - 1) / POOL_GRANULE * POOL_GRANULE;
     // the second lane pays from about 0.75 * max_bounce pool fills of work per epoch on (sessions r02zl..r02zo: bunny90k, 16 bounces, breaks
     // even near 7 fills and gains 3 % at 16; orb500k, 24 bounces through glass, breaks even near 17); ADAPT_LANE_THRESHOLD = pool fills
     h->lane_threshold = (unsigned long long)P * (unsigned long long)std::max(1, env_int("ADAPT_LANE_THRESHOLD", std::max(4, (3 * d->max_bounce + 3) / 4)));

@@ -15,17 +15,35 @@ using namespace adapt;
 // device helpers
 // ================================================================================================
 
+// threads per block.  k_logic where thread t owns slot t (one material group): 128 -- session r03k / r03l, profiles/r03k_ab_logic_block128.txt,
+// r03l_ab_logic_block.txt: with eight blocks of 128 x 64 registers per SM instead of four of 256 the kernel is 4 % faster alone (logic 17.13 -> 16.46
+// ms/step on bunny90k) and, with two lanes, more of its blocks fit beside the other lane's trace blocks (4160 -> 4306 Mrays/s at 256 spp per step).
+// The class-list launches (LISTED) stay at 256: at 128 orb500k 2032 -> 2012, the sphere scene 2644 -> 2556, car290k 3491 -> 3515.  k_classify
+// (block-local counting sort, 13 atomics per block) and k_logic_vpt are 256 as well.  Pools are sized in multiples of POOL_GRANULE so that every
+// launch covers them exactly.
 #ifndef LOGIC_BLOCK
-#define LOGIC_BLOCK 256
+#define LOGIC_BLOCK 128
 #endif
+#ifndef LOGIC_BLOCK_LISTED
+#define LOGIC_BLOCK_LISTED 256
+#endif
+#ifndef CLASSIFY_BLOCK
+#define CLASSIFY_BLOCK 256
+#endif
+#ifndef VPT_BLOCK
+#define VPT_BLOCK 256
+#endif
+#define POOL_GRANULE 256
+static_assert(POOL_GRANULE % LOGIC_BLOCK == 0 && POOL_GRANULE % LOGIC_BLOCK_LISTED == 0 && POOL_GRANULE % CLASSIFY_BLOCK == 0 && POOL_GRANULE % VPT_BLOCK == 0, "pool granule");
 // resident blocks per SM the k_logic instantiations are compiled for (measured on B200, profiles/r01c_ab.txt: the heavy-material
 // kernels gain 20 % going from 2 to 3 blocks and another 4-8 % at 4 although ptxas then spills; the simple one 5 % from 3 to 4)
 #ifndef LOGIC_MIN_BLOCKS
-#define LOGIC_MIN_BLOCKS 4
+#define LOGIC_MIN_BLOCKS 4           // per 256 threads: scaled by 256 / block size in the launch bounds
 #endif
 #ifndef LOGIC_MIN_BLOCKS_SIMPLE
 #define LOGIC_MIN_BLOCKS_SIMPLE 4
 #endif
+#define LOGIC_BLK(LISTED) ((LISTED) ? LOGIC_BLOCK_LISTED : LOGIC_BLOCK)
 // Measured and rejected for k_logic in sessions r02d / r02e (bunny90k, code removed): the block's 256-slot tile staged in shared memory
 // with six TMA bulk copies (cp.async.bulk + mbarrier, the BulkLoad helper below) issued by one thread at block start: 17.3 -> 18.5
 // ms/step -- the 23 KB per block come out of L1, every warp waits for the whole tile instead of its own 128-byte lines, and the kernel
@@ -62,7 +80,7 @@ __device__ __forceinline__ CounterT block_alloc(bool want, CounterT* counter, un
     if (threadIdx.x == 0) {
         unsigned tot = 0;
         #pragma unroll
-        for (int w = 0; w < LOGIC_BLOCK / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
         *s_base = tot ? atomicAdd(counter, (CounterT)tot) : (CounterT)0;
     }
     __syncthreads();
@@ -158,12 +176,12 @@ struct BulkLoad {
 // shadow queue's.
 struct KeySet { int k[8]; };          // the class keys one k_logic launch covers (-1 = unused)
 
-__global__ void __launch_bounds__(LOGIC_BLOCK)
+__global__ void __launch_bounds__(CLASSIFY_BLOCK)
 k_classify(const PathPool pool, const ShadowQueue sq, Cursors* __restrict__ cur, unsigned* __restrict__ cls_items,
            CursorStripe* __restrict__ cls_count, const int parity) {
-    __shared__ unsigned s_cnt[LOGIC_NKEY * (LOGIC_BLOCK / 32)];
+    __shared__ unsigned s_cnt[LOGIC_NKEY * (CLASSIFY_BLOCK / 32)];
     __shared__ unsigned s_base[LOGIC_NKEY];
-    const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
+    const int tslot = blockIdx.x * CLASSIFY_BLOCK + threadIdx.x;
     if (tslot < PT_NCURSOR) {
         cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0;
         cls_count[(parity ^ 1) * 16 + tslot].v = 0;
@@ -181,11 +199,11 @@ k_classify(const PathPool pool, const ShadowQueue sq, Cursors* __restrict__ cur,
     for (int k = 0; k < LOGIC_NKEY; k++) {
         const unsigned b = __ballot_sync(0xffffffffu, key == k);
         if (key == k) my_rank = __popc(b & ((1u << lane) - 1u));
-        if (lane == 0) s_cnt[k * (LOGIC_BLOCK / 32) + warp] = __popc(b);
+        if (lane == 0) s_cnt[k * (CLASSIFY_BLOCK / 32) + warp] = __popc(b);
     }
     __syncthreads();
     if (warp == 0) {
-        constexpr int n_ent = LOGIC_NKEY * (LOGIC_BLOCK / 32);
+        constexpr int n_ent = LOGIC_NKEY * (CLASSIFY_BLOCK / 32);
         constexpr int EPL = (n_ent + 31) / 32;
         unsigned v[EPL], sum = 0;
         #pragma unroll
@@ -199,12 +217,12 @@ k_classify(const PathPool pool, const ShadowQueue sq, Cursors* __restrict__ cur,
     }
     __syncthreads();
     if (threadIdx.x < LOGIC_NKEY) {
-        const unsigned lo = s_cnt[threadIdx.x * (LOGIC_BLOCK / 32)];
-        const unsigned hi = threadIdx.x + 1 < LOGIC_NKEY ? s_cnt[(threadIdx.x + 1) * (LOGIC_BLOCK / 32)] : (unsigned)LOGIC_BLOCK;
+        const unsigned lo = s_cnt[threadIdx.x * (CLASSIFY_BLOCK / 32)];
+        const unsigned hi = threadIdx.x + 1 < LOGIC_NKEY ? s_cnt[(threadIdx.x + 1) * (CLASSIFY_BLOCK / 32)] : (unsigned)CLASSIFY_BLOCK;
         s_base[threadIdx.x] = hi > lo ? atomicAdd(&cls_count[parity * 16 + threadIdx.x].v, hi - lo) : 0u;
     }
     __syncthreads();
-    const unsigned in_key = s_cnt[key * (LOGIC_BLOCK / 32) + warp] + my_rank - s_cnt[key * (LOGIC_BLOCK / 32)];
+    const unsigned in_key = s_cnt[key * (CLASSIFY_BLOCK / 32) + warp] + my_rank - s_cnt[key * (CLASSIFY_BLOCK / 32)];
     cls_items[(size_t)key * (size_t)pool.n_slots + s_base[key] + in_key] = (unsigned)tslot;
 }
 
@@ -212,12 +230,12 @@ k_classify(const PathPool pool, const ShadowQueue sq, Cursors* __restrict__ cur,
 // k_logic
 // ================================================================================================
 template <int MATS, bool LISTED>
-__global__ void __launch_bounds__(LOGIC_BLOCK, ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS))
+__global__ void __launch_bounds__(LOGIC_BLK(LISTED), ((MATS & M_TEXTURED) ? 3 : (MATS & (M_GLOSSY | M_COAT_GGX | M_BSDF)) == 0 ? LOGIC_MIN_BLOCKS_SIMPLE : LOGIC_MIN_BLOCKS) * 256 / LOGIC_BLK(LISTED))
 k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr, WorkStripe* __restrict__ work,
         Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list, const int n_pixels,
         const unsigned long long work_hi, const long long cnt_origin, const int parity, const unsigned rot,
         const unsigned* __restrict__ cls_items, const CursorStripe* __restrict__ cls_count, const KeySet keys) {
-    const int tslot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
+    const int tslot = blockIdx.x * LOGIC_BLK(LISTED) + threadIdx.x;
     // cursors of the coming trace kernel, and the shadow-queue counters of the NEXT iteration (pt_common.cuh: ShadowQueue)
     if (!LISTED && tslot < PT_NCURSOR) { cur->closest[tslot].v = 0; cur->shadow[tslot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + tslot].v = 0; }
     // work stripe of this warp (pt_common.cuh: WorkStripe).  The window of four stripes a warp probes moves on with every
@@ -546,11 +564,11 @@ k_logic(const SceneView sv, const PathPool pool, const ShadowQueue sq, DeviceCou
 #define VPT_MIN_BLOCKS 3
 #endif
 template <int MATS>
-__global__ void __launch_bounds__(LOGIC_BLOCK, VPT_MIN_BLOCKS)
+__global__ void __launch_bounds__(VPT_BLOCK, VPT_MIN_BLOCKS)
 k_logic_vpt(const SceneView sv, const VolumeView vv, const PathPool pool, const ShadowQueue sq, DeviceCounters* __restrict__ ctr,
             WorkStripe* __restrict__ work, Cursors* __restrict__ cur, float* __restrict__ accum, const int* __restrict__ pixel_list,
             const int n_pixels, const unsigned long long work_hi, const long long cnt_origin, const int parity, const unsigned rot) {
-    const int slot = blockIdx.x * LOGIC_BLOCK + threadIdx.x;
+    const int slot = blockIdx.x * VPT_BLOCK + threadIdx.x;
     if (slot < PT_NCURSOR) { cur->closest[slot].v = 0; cur->shadow[slot].v = 0; sq.seg_count[(parity ^ 1) * PT_NCURSOR + slot].v = 0; }
     const int home = (int)(((unsigned)(slot >> 5) + 4u * rot) % PT_NSTRIPE);
     uint4 misc = pool.misc[slot];

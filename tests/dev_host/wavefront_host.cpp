@@ -34,22 +34,21 @@ void launch_iteration(Wavefront& w) {
     const SceneView& sv = w.scene->sv;
     const int parity = (int)(w.iter_parity & 1u);
     w.iter_parity ^= 1u;
-    const int lg = w.pool.n_slots / LOGIC_BLOCK;
     const int lt = w.leaf_t | (w.node_steps << 8);
     DeviceCounters* ctr = &w.ctr; Cursors* cur = &w.cur;
     if (w.integrator == 1) {
         if (sv.two_sides || sv.textures)
-            simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_ALL | M_TEXTURED>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
+            simt::launch(w.pool.n_slots / VPT_BLOCK, VPT_BLOCK, [&] { k_logic_vpt<M_ALL | M_TEXTURED>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
                 w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
         else
-            simt::launch(lg, LOGIC_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
+            simt::launch(w.pool.n_slots / VPT_BLOCK, VPT_BLOCK, [&] { k_logic_vpt<M_SIMPLE | M_GLOSSY | M_COAT_GGX | M_BSDF>(sv, w.scene->vv, w.pool, w.sq, ctr, w.work.data(), cur,
                 w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations); });
         if (w.trace_mode == 3) simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt<3>(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
         else simt::launch(w.trace_grid, TRACE_BLOCK, [&] { k_trace_vpt<1>(sv, w.scene->vv, w.pool, w.sq, ctr, cur, w.refill, lt, parity); });
         w.iterations++; w.launches += 2;
         return;
     }
-#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { const KeySet ks_ = (KEYS); simt::launch(lg, LOGIC_BLOCK, [&] { k_logic<M, LISTED>(sv, w.pool, w.sq, ctr, w.work.data(), cur, \
+#define LAUNCH_LOGIC_X(M, LISTED, KEYS) do { const KeySet ks_ = (KEYS); simt::launch(w.pool.n_slots / LOGIC_BLK(LISTED), LOGIC_BLK(LISTED), [&] { k_logic<M, LISTED>(sv, w.pool, w.sq, ctr, w.work.data(), cur, \
         w.accum.data(), w.pixels.data(), (int)w.pixels.size(), w.work_hi, w.cnt_origin, parity, (unsigned)w.iterations, w.cls_items.data(), w.cls_count.data(), ks_); }); \
         w.launches++; } while (0)
 #define LAUNCH_LOGIC_V(M, LISTED, KEYS) do { \
@@ -60,7 +59,7 @@ void launch_iteration(Wavefront& w) {
         const KeySet no_keys = {{-1, -1, -1, -1, -1, -1, -1, -1}};
         LAUNCH_LOGIC_V(M_SIMPLE, false, no_keys);
     } else {
-        simt::launch(lg, LOGIC_BLOCK, [&] { k_classify(w.pool, w.sq, cur, w.cls_items.data(), w.cls_count.data(), parity); });
+        simt::launch(w.pool.n_slots / CLASSIFY_BLOCK, CLASSIFY_BLOCK, [&] { k_classify(w.pool, w.sq, cur, w.cls_items.data(), w.cls_count.data(), parity); });
         w.launches++;
         const KeySet k_simple = {{0, 1, 2, 6, LOGIC_NKEY - 2, LOGIC_NKEY - 1, -1, -1}}, k_glossy = {{4, 5, -1, -1, -1, -1, -1, -1}};
         const KeySet k_coat = {{3, 7, -1, -1, -1, -1, -1, -1}}, k_bsdf = {{8, 9, 10, -1, -1, -1, -1, -1}};
@@ -140,8 +139,8 @@ int wavefront_render(const adapt_scene_desc* d, int n_spp, int pool_slots, int t
                 for (int j = bj; j < std::min(bj + 8, ey); j++) w.pixels.push_back(i * d->height + j);
     }
     // pool, queues, counters (adapt_create)
-    int P = std::max(pool_slots, LOGIC_BLOCK);
-    P = (P + LOGIC_BLOCK - 1) / LOGIC_BLOCK * LOGIC_BLOCK;
+    int P = std::max(pool_slots, POOL_GRANULE);
+    P = (P + POOL_GRANULE - 1) / POOL_GRANULE * POOL_GRANULE;
     w.pool.n_slots = P;
     {
         // adapt_create: one allocation of six words per slot
