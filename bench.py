@@ -356,7 +356,7 @@ def run_b200(args):
         traffic = cap["dram_bytes_per_launch"] if cap else None
         if cap:
             achieved = cap["dram_bytes_per_launch"] / (cap["duration_us"] * 1e-6) / 1e9
-            frac_source = f"ncu dram bytes / capture duration (profiles/ncu_summary.json, session {cap.get('session')}: cold-cache, serialised launches)"
+            frac_source = f"ncu dram bytes / capture duration (profiles/ncu_summary.json, session {cap.get('session')}: cold-cache, serialised launches, the kernel alone at nine resident blocks per SM; in the timed region two lanes overlap and k_trace runs six blocks per SM beside the other lane's k_logic, so avg_launch_ms is longer than the capture's duration)"
         else:
             achieved = queue_gbs
             frac_source = "compulsory queue bytes / live launch duration (no ncu capture for this workload)"
